@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the acoustic hot path (MFCC -> GMM emissions -> Viterbi word decision).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+
+Metric (BASELINE.json): frames/sec through MFCC + GMM log-likelihood + Viterbi.  One "step" = one pass of the hot
+path over one batch of synthetic 16 kHz utterances with random-init GMM-HMMs:
+  c2 (default, BASELINE configs[1]): isolated-word models, 10 words x 5 states x 4 mixtures x 39 dims, 4096
+      utterances of 0.5-1.5 s per GPU; the word is the argmax over models of the Viterbi score.
+  c4 (BASELINE configs[3] shape): one 2000-state x 16-mixture x 39-dim left-to-right model, tensor-core emissions.
+`value` is timed with the PCM already in HBM; `e2e` goes through the public API from pinned host buffers with the
+host->device copy and the device->host read of the decoded words inside the timed region.  Multi-GPU: one process
+per GPU (torchrun), utterances sharded by rank, no data-path collective ("weak" scaling: per-GPU batch fixed).
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/lnasr_oracle.py; the reference itself
+is pure Python/numpy and /root/reference does not exist on the GPU box) on all host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "ln-asr_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames/sec (MFCC+GMM loglik+Viterbi)"
+UNIT = "frames/s"
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def synth_batch(seed: int, n_utt: int, min_s: int, max_s: int):
+    """SURVEY.md 8(d) synthetic audio: int16 = clip(round(3000 N(0,1)) + 2000 sin(2 pi f0 t)), f0 ~ U(80,400)."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(min_s, max_s + 1, size=n_utt)
+    off = np.zeros(n_utt + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    total = int(off[-1])
+    pcm = np.round(3000.0 * rng.standard_normal(total, dtype=np.float32))
+    f0 = rng.uniform(80.0, 400.0, size=n_utt)
+    for u in range(n_utt):
+        t = np.arange(lens[u], dtype=np.float32) / 16000.0
+        pcm[off[u]:off[u + 1]] += 2000.0 * np.sin(2 * np.pi * f0[u] * t)
+    return np.clip(pcm, -32767, 32767).astype(np.int16), off
+
+
+def make_models(workload: str, seed: int = 1234):
+    """Random-init GMM-HMMs with GMMHMM.reset('random') semantics (oracle.random_gmmhmm), scaled into the range of
+    MFCC features (|x| up to ~200) so that every state has a sensible likelihood."""
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(seed)
+    if workload == "c2":
+        models = [O.random_gmmhmm(5, 4, 39, rng) for _ in range(10)]
+    else:
+        m = O.random_gmmhmm(2000, 16, 39, rng, left_to_right=True)
+        m["pi"] = np.full(2000, -np.inf)
+        m["pi"][0] = 0.0
+        models = [m]
+    for m in models:
+        m["mu"] = m["mu"] * 100.0
+        m["var"] = m["var"] * 400.0
+    return models
+
+
+WORKLOADS = {
+    "c2": dict(desc="isolated-word GMM-HMM: 10 words x 5 states x 4 mixtures x 39 dims, batched Viterbi",
+               n_utt=4096, min_s=8000, max_s=24000, emission="exact"),
+    "c4": dict(desc="large-vocab acoustic scoring: 2000 states x 16 mixtures x 39 dims (left-to-right), TC emissions",
+               n_utt=1250, min_s=48000, max_s=48000, emission="tc"),
+}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """One utterance through the CPU restatement: MFCC -> emissions of every model -> Viterbi -> word."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import lnasr_oracle as O
+    pcm, models = args
+    _, _, F = O.mfcc(pcm)
+    O.score_words_viterbi(F, models)
+    return F.shape[0]
+
+
+def cpu_arm(workload: str, n_utt_sample: int, cores: int):
+    """Frames/s of the CPU port on `cores` single-threaded worker processes (faster than threaded BLAS on these
+    shapes)."""
+    import multiprocessing as mp
+    cfg = WORKLOADS[workload]
+    models = make_models(workload)
+    if workload == "c4":
+        # N=2000: ~20 frames/s/core in the reference; bound the sample to short utterances
+        pcm, off = synth_batch(99, n_utt_sample, 2640, 2640)      # 15 frames each
+    else:
+        pcm, off = synth_batch(99, n_utt_sample, cfg["min_s"], cfg["max_s"])
+    jobs = [(pcm[off[u]:off[u + 1]], models) for u in range(n_utt_sample)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, jobs[:cores])                         # warm the workers (imports, first-call costs)
+        t0 = time.perf_counter()
+        frames = sum(pool.map(_cpu_worker, jobs, chunksize=1))
+        dt = time.perf_counter() - t0
+    return frames / dt, frames, dt
+
+
+def run_reference(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = max(8 * cores, 32) if args.workload == "c2" else cores
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, frames, dt = cpu_arm(args.workload, per_step, cores)
+        if i >= args.warmup:
+            vals.append((v, frames, dt))
+        if time.perf_counter() - t_all > 240:
+            break
+    frames = sum(x[1] for x in vals)
+    dt = sum(x[2] for x in vals)
+    value = frames / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "sample_utts_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} utterances/step x {len(vals)} steps, one single-threaded process per core"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = WORKLOADS[args.workload]
+    models = make_models(args.workload)
+    pipe = AcousticPipeline(MFCC(), ModelBank(models, emission=cfg["emission"]))
+    # every rank owns its own shard of utterances (weak scaling: per-GPU batch fixed)
+    pcm_np, off = synth_batch(1000 + rank, cfg["n_utt"], cfg["min_s"], cfg["max_s"])
+    n_utt = cfg["n_utt"]
+    pcm_host = torch.from_numpy(pcm_np).pin_memory()
+    pcm_dev = pcm_host.cuda()
+    pcm_stage = torch.empty_like(pcm_dev)
+    want_paths = True
+
+    def step_device():
+        res, mb = pipe.recognize_batch(pcm_dev, off, want_paths=want_paths)
+        return res, mb
+
+    def step_e2e():
+        pcm_stage.copy_(pcm_host, non_blocking=True)
+        res, mb = pipe.recognize_batch(pcm_stage, off, want_paths=want_paths)
+        words = res.words.cpu()
+        best = res.best.cpu()
+        return words, best
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res, mb = step_device()
+    torch.cuda.synchronize()
+    frames = int(mb.frame_offsets_host[-1])
+    words0 = res.words.cpu().numpy().copy()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    assert np.array_equal(step_e2e()[0].numpy(), words0), "e2e path decoded different words"
+
+    total_frames = frames * world if world == 1 else None
+    fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+    total_frames = float(fr.item())
+    value = total_frames / (ms_dev / 1e3 / args.steps)
+    e2e_value = total_frames / (ms_e2e / 1e3 / args.steps)
+
+    # ---- per-kernel shares + roofline of the dominant kernel (rank 0, CUDA events around each C-ABI call)
+    line = None
+    if rank == 0:
+        stages = stage_times(pipe, pcm_dev, off, want_paths, reps=max(3, args.steps // 2))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        top = max(stages, key=lambda k: stages[k]["ms"])
+        roof = roofline_for(top, stages[top], frames, cfg, models, hbm_peak, peaks)
+        roof["kernel"] = top
+        roof["peak_source"] = peak_src
+        roof["stage_ms"] = {k: round(v["ms"], 4) for k, v in stages.items()}
+        cores = os.cpu_count() or 1
+        cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "skipped (--no-cpu)"}
+        if world == 1 and not args.no_cpu:
+            os.environ["OMP_NUM_THREADS"] = "1"
+            n_s = max(16 * cores, 64) if args.workload == "c2" else cores
+            v, f_s, dt = cpu_arm(args.workload, n_s, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_s} utterances ({f_s} frames) in {dt:.1f} s, one single-threaded numpy process per core"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 MFCC / f64 emissions+trellis" if cfg["emission"] == "exact" else "f32 MFCC / 3xTF32 emissions / f64 trellis",
+            "data": "synthetic",
+            "config": {"workload": args.workload + ": " + cfg["desc"], "utts_per_gpu": n_utt, "frames_per_gpu_step": frames,
+                       "pcm_bytes_per_gpu_step": int(pcm_np.nbytes), "l2": "inputs larger than L2 (PCM + intermediates > 126 MB per step)",
+                       "parallelism": f"utterance-sharded x{world}, no data-path collective", "viterbi_paths": want_paths},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(pcm_np.nbytes) + int(off.nbytes) * 2, "d2h_bytes_per_step": n_utt * 12},
+            "gpu_launches": launches_per_step(pipe, want_paths) * args.steps,
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def launches_per_step(pipe, want_paths):
+    # mfcc_frames, mfcc_finalize, gmm (exact or tc), trellis (viterbi), [backtrace], argmax_rows
+    return 5 + (1 if want_paths else 0)
+
+
+def stage_times(pipe, pcm_dev, off, want_paths, reps=5):
+    """CUDA-event time of each C-ABI call of one step (current stream), averaged over `reps` full passes."""
+    import torch
+    from lnasr import _capi, _dev
+    t = torch
+    acc = {"mfcc": 0.0, "gmm": 0.0, "viterbi": 0.0}
+    for rep in range(reps + 1):
+        ev = [t.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        mb = pipe.mfcc.calc_mfcc_batch(pcm_dev, sample_offsets=off)
+        ev[1].record()
+        b = pipe.bank.emissions(mb.feats)
+        ev[2].record()
+        n_utt, total = len(off) - 1, int(mb.frame_offsets_host[-1])
+        r = pipe.bank.trans.viterbi(b, mb.frame_offsets, n_utt, total, want_path=want_paths, want_score=True)
+        ev[3].record()
+        t.cuda.synchronize()
+        if rep == 0:
+            continue
+        acc["mfcc"] += ev[0].elapsed_time(ev[1])
+        acc["gmm"] += ev[1].elapsed_time(ev[2])
+        acc["viterbi"] += ev[2].elapsed_time(ev[3])
+    return {k: {"ms": v / reps} for k, v in acc.items()}
+
+
+def roofline_for(name, st, frames, cfg, models, hbm_peak, peaks):
+    """Algorithmic bytes / flops per frame x frames per launch / measured duration."""
+    K = len(models)
+    n, m = models[0]["w"].shape
+    N = K * n
+    sec = st["ms"] / 1e3
+    if name == "mfcc":
+        per = 160 * 2 + 39 * 4                    # new int16 samples in + 39 fp32 features out (476 B)
+        ach = per * frames / sec / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "algorithmic_bytes_per_frame": per, "note": "front end is fp32-ALU bound (~35 kFLOP/frame), see DESIGN.md"}
+    if name == "viterbi":
+        per = 8 * N                               # read b (4N as fp32-equivalent) + write backpointers (4N): SURVEY.md 8(d)
+        ach = per * frames / sec / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "algorithmic_bytes_per_frame": per}
+    # gmm
+    if cfg["emission"] == "tc":
+        flops = 2 * 79 * N * m                    # algorithmic; executed = 3x (3xTF32), K padded to 80
+        ach = flops * frames / sec / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "algorithmic_flops_per_frame": flops, "executed_over_algorithmic": 3.04,
+                "note": "peak = 1/2 of measured sustained bf16 (TF32 runs at half the bf16 rate); no TF32 figure is measured"}
+    per = 39 * 4 + 8 * N                          # fp32 features in + float64 emissions out
+    ach = per * frames / sec / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "algorithmic_bytes_per_frame": per, "note": "float64 SIMT: 2*39*N*m fp64 FMA-pairs per frame, FP64-pipe bound"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

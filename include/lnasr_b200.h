@@ -1,0 +1,230 @@
+/*
+ * lnasr_b200.h -- C ABI of liblnasr_b200.so: the ln-asr acoustic hot path on one B200 (sm_100a).
+ *
+ * The reference (yehuohan/ln-asr) has NO FFI for this path: the boundary is the Python API of
+ * lnasr/mfcc.py, lnasr/gmm.py, lnasr/hmm.py and lnasr/gmmhmm.py.  Each entry
+ * point below names the reference method whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes stubs a maintainer of the reference would add to bind them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LNASR_E* code otherwise; the message of the
+ *     last failure on the calling thread is returned by lnasr_last_error();
+ *   - all data pointers are DEVICE pointers unless the parameter comment says "host";
+ *   - the caller owns every buffer; the library allocates nothing that outlives a call;
+ *   - every launch goes to the CUDA stream passed as `stream` (a cudaStream_t cast to void*); no call
+ *     synchronises the device;
+ *   - utterances are ragged and concatenated: frames of utterance u are rows
+ *     [frame_offsets[u], frame_offsets[u+1]) of every per-frame matrix;
+ *   - per-frame matrices are FRAME-major ([T_total, n_models*N]); the reference keeps b state-major
+ *     [N, T] (lnasr/hmm.py:59) -- the Python mirror transposes on the way out;
+ *   - log quantities are natural logs; "model" k of a bank owns states [k*N, (k+1)*N).
+ */
+#ifndef LNASR_B200_H
+#define LNASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNASR_OK            0
+#define LNASR_EINVAL       -1   /* bad argument / unsupported shape */
+#define LNASR_ECUDA        -2   /* a CUDA runtime call or launch failed */
+#define LNASR_EWORKSPACE   -3   /* workspace too small */
+
+#define LNASR_DT_I16 0
+#define LNASR_DT_F32 1
+#define LNASR_DT_F64 2
+
+/* ------------------------------------------------------------------------------------------------ */
+const char* lnasr_last_error(void);
+int lnasr_version(void);
+/* host out-params; reports the current device */
+int lnasr_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
+
+/* ================================ (1) MFCC front end ============================================
+ * Replaces MFCC.calc_mfcc (lnasr/mfcc.py:108-175) including calc_high_pass_filter (mfcc.py:50-64),
+ * utils.split_frames (utils.py:106-130), utils.create_hamming (utils.py:132-138), the 512-point rFFT
+ * power spectrum (mfcc.py:141-142), the mel filter bank product (mfcc.py:145-148), 20*log10 + per
+ * utterance mean removal (mfcc.py:149-151), DCT-II ortho (mfcc.py:152), c1..c12 + ln energy
+ * (mfcc.py:155-160) and delta / delta-delta (mfcc.py:162-172), for a batch of utterances.
+ *
+ * The constant tables are built by the caller with the reference's formulas (create_hamming,
+ * create_filter_bank, the DCT-II ortho matrix) and passed as device arrays. */
+typedef struct lnasr_mfcc_tables {
+    int32_t frame_len;        /* MFCC.frame_L   (400) ; must be <= fft_n */
+    int32_t frame_step;       /* MFCC.frame_step (160) */
+    int32_t fft_n;            /* MFCC.fft_N; this build supports 512 only */
+    int32_t n_mel;            /* MFCC.mfbank_num (40) ; <= 64 */
+    int32_t n_ceps;           /* MFCC.cepstrum_num (12) ; < n_mel, <= 31 */
+    float   hpf_alpha;        /* MFCC.hpf_alpha (0.97) */
+    int32_t fb_stride;        /* row stride of fb_weight (>= max filter width, <= 64) */
+    const float*   window;    /* [frame_len]  Hamming window */
+    const float*   twiddle;   /* [fft_n] pairs (cos, -sin)(2 pi m / fft_n) as float2 */
+    const int32_t* fb_start;  /* [n_mel] first FFT bin with non-zero weight */
+    const int32_t* fb_len;    /* [n_mel] number of consecutive non-zero bins */
+    const float*   fb_weight; /* [n_mel, fb_stride] the non-zero weights of each triangular filter */
+    const float*   dct_t;     /* [n_mel(n), n_mel(k)] DCT-II ortho matrix, transposed: dct_t[n*n_mel+k] */
+} lnasr_mfcc_tables;
+
+/* MFCC.calc_high_pass_filter (lnasr/mfcc.py:50-64) alone: y[0]=x[0]; y[t]=x[t]-alpha*x[t-1]; float64 out */
+int lnasr_preemphasis(const void* pcm, int pcm_dtype /*I16|F32|F64*/, int64_t n_samples, double alpha,
+                      double* out, void* stream);
+/* frames of one utterance: ceil(|S-(L-step)|/step), utils.py:118 (host helper, no device work) */
+int64_t lnasr_mfcc_num_frames(int64_t n_samples, int32_t frame_len, int32_t frame_step);
+/* workspace bytes needed by lnasr_mfcc_batch */
+int lnasr_mfcc_workspace_bytes(int64_t total_frames, int32_t n_utt, size_t* bytes /*host out*/);
+/*
+ * pcm            : concatenated samples, int16 (LNASR_DT_I16) or float32 (LNASR_DT_F32)
+ * sample_offsets : [n_utt+1] int64, device
+ * frame_offsets  : [n_utt+1] int64, device; frame_offsets[u+1]-frame_offsets[u] must equal
+ *                  lnasr_mfcc_num_frames(samples of u) and be >= 2 (the reference needs row 1, mfcc.py:164)
+ * feats          : [total_frames, ld_feats] float32 out, 3*(n_ceps+1) = 39 columns used
+ * power_out      : [total_frames, fft_n/2+1] float32 or NULL   (1st return value of calc_mfcc)
+ * ceps_out       : [total_frames, n_mel] float32 or NULL       (2nd return value, incl. its in-place quirk)
+ */
+int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* sample_offsets,
+                     const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames,
+                     const lnasr_mfcc_tables* tables /*host struct of device pointers*/,
+                     float* feats, int32_t ld_feats, float* power_out, float* ceps_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ================================ (2) GMM emission log-likelihoods ==============================
+ * Replaces GMMHMM._map_b (lnasr/gmmhmm.py:46-67) and gmm.gaussian_multi_distribution_log
+ * (lnasr/gmm.py:59-68) for diagonal covariances: bm[t,j,m] = -1/2 (D ln 2pi + sum ln var + sum (x-mu)^2/var),
+ * b[t,j] = lse_m (w[j,m] + bm[t,j,m]).
+ *
+ * Two kernels behind one packed-model idea:
+ *   exact : float64 SIMT evaluation of (x-mu)^2/var -- small models (configs 1-3), optional bm output;
+ *   tc    : [x^2, x, 1] . [-1/(2 var), mu/var, c]^T as a 3xTF32 tcgen05 contraction with the log-sum-exp
+ *           over mixtures fused into the TMEM epilogue -- large models (config 4).
+ */
+/* packed exact model: per Gaussian 2*dim+2 doubles [ -1/(2 var_d) | mu_d | -1/2 (D ln 2pi + sum ln var) | log w ] */
+int lnasr_gmm_pack_exact(const double* logw /*[n_states,n_mix]*/, const double* mu /*[n_states,n_mix,dim]*/,
+                         const double* var /*[n_states,n_mix,dim]*/, int32_t n_states, int32_t n_mix, int32_t dim,
+                         double* packed /*[n_states*n_mix, 2*dim+2]*/, void* stream);
+int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype /*F32|F64*/, int32_t ld_feats, int64_t n_frames,
+                           const double* packed, int32_t n_states, int32_t n_mix, int32_t dim,
+                           void* b_out /*[n_frames, ld_b]*/, int b_dtype /*F32|F64*/, int64_t ld_b,
+                           double* bm_out /*[n_frames, n_states*n_mix] or NULL*/, void* stream);
+
+/* full covariance (the reference's Sigma is a full D x D matrix, lnasr/gmm.py:59-68): the caller factorises
+ * Sigma = L L^T once and passes linv = L^-1 [n_states*n_mix, dim, dim] (lower triangular, row-major),
+ * nu = L^-1 mu [.., dim], cst = -1/2 (D ln 2pi + 2 sum ln L_ii) [..], logw [..]. */
+int lnasr_gmm_loglik_full(const void* feats, int feats_dtype, int32_t ld_feats, int64_t n_frames, const double* linv,
+                          const double* nu, const double* cst, const double* logw, int32_t n_states, int32_t n_mix,
+                          int32_t dim, void* b_out, int b_dtype, int64_t ld_b, double* bm_out, void* stream);
+
+/* tensor-core path (csrc/gmm_tc.cu).  n_mix <= 16 (padded to a power of two inside the packed image), dim <= 39.
+ * The packed image holds, per tile of states, the hi and lo TF32 halves of [-1/(2 var) | mu/var | c] * log2(e) in
+ * the UMMA K-major shared-memory layout, plus the optional feature centre `shift` (host semantics: the kernel
+ * evaluates the same density on x - shift and mu - shift, which halves the fp32 cancellation error). */
+int lnasr_gmm_tc_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes /*host out*/);
+int lnasr_gmm_pack_tc(const double* logw, const double* mu, const double* var, int32_t n_states, int32_t n_mix,
+                      int32_t dim, const double* shift /*[dim] device, or NULL*/, void* packed, void* stream);
+/* feats [n_frames, ld_feats] float32 (ld_feats % 4 == 0 and >= 40 enables 16-byte loads); b_out [n_frames, ld_b] float32 */
+int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed,
+                        int32_t n_states, int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b, void* stream);
+
+/* discrete emissions: HMM._map_b (lnasr/hmm.py:47-61): b[t, j] = B[j, obs[t]] */
+int lnasr_emit_gather(const double* logB /*[n_states, n_symbols]*/, const int32_t* obs /*[n_frames]*/,
+                      int64_t n_frames, int32_t n_states, int32_t n_symbols, double* b_out /*[n_frames,n_states]*/,
+                      void* stream);
+
+/* ================================ (3) HMM log-trellis ===========================================
+ * Replaces HMM._forward (lnasr/hmm.py:63-100), HMM._backward (hmm.py:102-131), HMM._viterbi incl. the
+ * backtrace (hmm.py:133-172), HMM.calc_prob (hmm.py:268-274) and HMM.decode (hmm.py:276-283) for a batch of
+ * utterances x a bank of n_models models that share (N) but not parameters.
+ *
+ * Transitions: dense log A [n_models,N,N] always; for N > 32 the kernels walk predecessor / successor
+ * lists of the FINITE entries (ELL layout, built once per model by lnasr_trans_pack).
+ * All trellis state is float64; emissions b may be float32 (tc path) or float64 (exact path).
+ */
+/* max number of finite entries in any column / row of any model -> device int32[2] {max_in, max_out} */
+int lnasr_trans_degree(const double* logA, int32_t n_models, int32_t N, int32_t* deg_out /*device [2]*/, void* stream);
+/* pred_idx/val: [n_models, max_in, N]  (k-th finite predecessor i of state j, ascending i; pad idx=0,val=-inf)
+ * succ_idx/val: [n_models, max_out, N] (k-th finite successor j of state i) */
+int lnasr_trans_pack(const double* logA, int32_t n_models, int32_t N, int32_t max_in, int32_t max_out,
+                     int32_t* pred_idx, double* pred_val, int32_t* succ_idx, double* succ_val, void* stream);
+
+typedef struct lnasr_hmm_bank {
+    int32_t n_models, N;
+    const double* logA;      /* [n_models, N, N] */
+    const double* logpi;     /* [n_models, N] */
+    int32_t max_in, max_out; /* 0 when the ELL arrays are absent (N <= 32) */
+    const int32_t* pred_idx; const double* pred_val;
+    const int32_t* succ_idx; const double* succ_val;
+} lnasr_hmm_bank;
+
+size_t lnasr_viterbi_workspace_bytes(int64_t total_frames, int32_t n_utt, int32_t n_models, int32_t N);
+/*
+ * b          : [total_frames, ld_b] emissions (b_dtype F32|F64), columns k*N+j
+ * path_out   : [n_models, total_frames] uint32 (hmm.py:168 dtype) or NULL
+ * score_out  : [n_utt, n_models] float64 = max_j v[T-1, j]          (NULL allowed)
+ * v_out      : [total_frames, n_models*N] float64 or NULL ; bt_out same shape uint32 or NULL (hmm.py:157-158)
+ */
+int lnasr_viterbi_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                        int64_t total_frames, const lnasr_hmm_bank* bank /*host struct*/,
+                        uint32_t* path_out, double* score_out, double* v_out, uint32_t* bt_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* alpha_out [total_frames, n_models*N] or NULL ; logprob_out [n_utt, n_models] = lse_j alpha[T-1,j] */
+int lnasr_forward_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                        int64_t total_frames, const lnasr_hmm_bank* bank, double* alpha_out, double* logprob_out,
+                        void* stream);
+int lnasr_backward_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                         int64_t total_frames, const lnasr_hmm_bank* bank, double* beta_out, void* stream);
+
+/* isolated-word decision: arg_out[u] = argmax_k score[u,k], lowest index on ties; best_out optional */
+int lnasr_argmax_rows(const double* score /*[n_rows,n_cols]*/, int32_t n_rows, int32_t n_cols, int32_t* arg_out,
+                      double* best_out, void* stream);
+
+/* ================================ (4) Baum-Welch accumulation + M-step ==========================
+ * Replaces HMM._baumwelch (lnasr/hmm.py:174-200) and GMMHMM._estimate (lnasr/gmmhmm.py:69-156) in
+ * sufficient-statistic form, never materialising xi [T,N,N] or the
+ * [N,M,T,D,D] scatter.  The backward recursion and the accumulation are ONE kernel.
+ *
+ * Accumulator layout (float64, lnasr_em_acc_doubles() values), summed over utterances and -- across
+ * GPUs -- by one all-reduce:
+ *   S0[N*M] | S1[N*M*D] | S2c[N*M*D] (scatter about the OLD mean) | xi_sum[N*N] | pi_occ[N] | loglik | n_utt
+ */
+int64_t lnasr_em_acc_doubles(int32_t N, int32_t n_mix, int32_t dim);
+/* alpha must come from lnasr_forward_batch, b/bm (float64) from lnasr_gmm_loglik_exact; single model (n_models=1) */
+int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
+                        const double* alpha, const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames,
+                        const double* logA, const double* logw, const double* mu, int32_t N, int32_t n_mix,
+                        int32_t dim, double* acc /*in/out, caller zeroes*/, double* gamma_out /*[T,N] log or NULL*/,
+                        double* beta_out /*[T,N] log or NULL*/, void* stream);
+/* M-step from (all-reduced) statistics; writes the new model in place of the old device arrays */
+int lnasr_mstep_finalize(const double* acc, int32_t N, int32_t n_mix, int32_t dim, double min_std,
+                         double* logA, double* logpi, double* logw, double* mu, double* var, void* stream);
+
+/* discrete-emission statistics for plain HMM._estimate (lnasr/hmm.py:202-225):
+ * acc layout: xi_sum[N*N] | gamma_sum[N] (t<T-1) | B_sum[N*n_symbols] | pi_occ[N] | loglik | n_utt */
+int64_t lnasr_hmm_acc_doubles(int32_t N, int32_t n_symbols);
+int lnasr_hmm_fb_accumulate(const double* b, const double* alpha, const int32_t* obs, const int64_t* frame_offsets,
+                            int32_t n_utt, int64_t total_frames, const double* logA, int32_t N, int32_t n_symbols,
+                            double* acc, double* gamma_out, double* beta_out /*[T,N] log or NULL*/, void* stream);
+int lnasr_hmm_mstep_finalize(const double* acc, int32_t N, int32_t n_symbols, double* logA, double* logB,
+                             double* logpi, void* stream);
+
+/* HMM._baumwelch (lnasr/hmm.py:174-200) with its return values materialised: xi [T,N,N] and gamma [T,N] (log),
+ * row T-1 of every utterance = -inf.  API parity only; train() uses the fused accumulation above. */
+int lnasr_baumwelch_xi(const double* alpha, const double* beta, const double* b, const double* logA,
+                       const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames, int32_t N,
+                       double* xi_out, double* gamma_out, void* stream);
+
+/* ================================ debug / bring-up ==============================================
+ * One tcgen05.mma (M=128, N=128, K=8, kind::tf32) on caller-provided shared-memory images with caller-chosen
+ * descriptor fields; used by tests/test_umma_probe.py to pin the descriptor semantics on hardware. */
+int lnasr_debug_umma_probe(const float* a_image /*[a_bytes/4]*/, int32_t a_bytes, const float* b_image, int32_t b_bytes,
+                           uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout_type,
+                           uint32_t idesc, float* d_out /*[128,128]*/, void* stream);
+/* bring-up switch: exchange the LBO / SBO fields of the descriptors lnasr_gmm_loglik_tc builds (0 = as documented) */
+int lnasr_debug_set_umma_swap(int swap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNASR_B200_H */

@@ -1,0 +1,520 @@
+// gmm_tc.cu -- GMM emission log-likelihoods on the 5th-generation tensor cores (kernel (2) of the north star).
+//
+// Replaces GMMHMM._map_b (/root/reference/lnasr/gmmhmm.py:46-67) + gaussian_multi_distribution_log
+// (/root/reference/lnasr/gmm.py:59-68) for diagonal covariances and LARGE models (config 4: 2000 states x 16
+// mixtures x 39 dims = 32 000 Gaussians per frame):
+//
+//     log N(x; mu, diag var) + log w  =  [x^2 | x | 1] . [ -1/(2 var) | mu/var | c ]^T          
+//
+// is a dense [frames, K] x [K, states*mixtures] contraction with K = 2*dim+1 (79 -> 80).  It runs as
+// tcgen05.mma kind::tf32 with 3xTF32 error compensation: every fp32 operand is split v = hi + lo with hi
+// rounded to TF32, and   D = Ah.Bh + Ah.Bl + Al.Bh   is accumulated in fp32 in TMEM (the dropped Al.Bl term is
+// 2^-22 relative).  The log-sum-exp over the mixtures of a state is fused into the TMEM epilogue: the packed
+// weights put the M mixtures of a state in M adjacent accumulator columns, so one tcgen05.ld gives a thread
+// (= one frame) all mixtures of a state and the reduction needs no shuffles.  Weights are pre-scaled by
+// log2(e) so the epilogue is max / ex2 / lg2.
+//
+// CTA = 9 warps, one CTA per SM, each owning one W tile (NT <= 224 accumulator columns, resident in shared
+// memory for the whole pass) and streaming 128-frame tiles:
+//   warps 4-7  producers : thread = frame row; reads the 39 features, forms [x^2|x|1], splits hi/lo and writes
+//                          the UMMA canonical K-major (no-swizzle) layout straight into a 4-slot ring
+//                          (slot = half of K of the hi or lo image), fence.proxy.async, mbarrier arrive;
+//   warp 8     MMA       : one thread issues 30 tcgen05.mma (M=128, N=NT, K=8) per tile, tcgen05.commit frees
+//                          ring slots and publishes the accumulator stage (2 TMEM stages of NT columns);
+//   warps 0-3  epilogue  : tcgen05.ld 32x32b.x16, LSE over mixtures, b[frame, state] fp32 stores.
+// No tensor maps are needed: A never exists in global memory (156 B/frame are read instead of 640 B) and W
+// is a linear copy of a pre-packed image.
+#include <algorithm>
+#include "common.cuh"
+
+namespace lnasr {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, fp32 accumulate, TF32 inputs
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout type [61,64) (0 = no swizzle / interleave)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout_type & 7u) << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, A and B K-major
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------------ bring-up probe
+// One tcgen05.mma (shape from idesc) on caller-provided shared-memory images; D [128 lanes, 128 columns] is returned.
+__global__ void __launch_bounds__(128) umma_probe_kernel(const float* __restrict__ a_img, int a_bytes, const float* __restrict__ b_img,
+                                                         int b_bytes, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                                                         uint32_t layout_type, uint32_t idesc, float* __restrict__ d_out) {
+    extern __shared__ __align__(1024) uint8_t probe_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    float* sa = (float*)probe_smem;
+    float* sb = (float*)(probe_smem + ((a_bytes + 1023) & ~1023));
+    for (int i = threadIdx.x; i < a_bytes / 4; i += 128) sa[i] = a_img[i];
+    for (int i = threadIdx.x; i < b_bytes / 4; i += 128) sb[i] = b_img[i];
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint64_t ad = make_smem_desc(smem_u32(sa), a_lbo, a_sbo, layout_type);
+        const uint64_t bd = make_smem_desc(smem_u32(sb), b_lbo, b_sbo, layout_type);
+        umma_tf32(tmem_base, ad, bd, idesc, 0u);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d_out[(warp * 32 + lane) * 128 + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------ packed image
+constexpr uint32_t TC_MAGIC = 0x4c4e5443u;   // "LNTC"
+constexpr int TC_BM = 128;                    // frames per tile (UMMA M)
+constexpr int TC_THREADS = 288;               // 4 epilogue + 4 producer + 1 MMA warp
+constexpr int TC_MAX_DIM = 39;                // the K axis is laid out for 39 dims; smaller dims are zero-padded
+constexpr int TC_KP = 80;                     // 2*39 + 1 -> 80
+constexpr int TC_KH = TC_KP / 2;              // K values per ring slot
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr float TC_LOG2E = 1.4426950408889634f;
+constexpr float TC_LN2 = 0.6931471805599453f;
+
+struct TcHeader {       // 512 bytes at the start of the packed image
+    uint32_t magic;
+    int32_t n_states, n_mix, Mp, dim, Kp, SPT, NT, n_wtiles;
+    int32_t pad[7];
+    float shift[64];
+    uint8_t reserved[512 - 16 * 4 - 64 * 4];
+};
+static_assert(sizeof(TcHeader) == 512, "TcHeader must be 512 bytes");
+
+struct TcGeom { int Mp, Kp, SPT, NT, n_wtiles; size_t tile_bytes, total_bytes, smem_bytes; };
+
+static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
+    if (n_states < 1 || n_mix < 1 || n_mix > 16 || dim < 1 || dim > TC_MAX_DIM) return false;
+    int Mp = 1;
+    while (Mp < n_mix) Mp <<= 1;
+    const int Kp = TC_KP;                                      // fixed K axis [x^2 (39) | x (39) | 1 | 0]; dims beyond `dim` are zero
+    const int gran = 16 / Mp;                                  // states per 16 accumulator columns
+    // shared memory: W hi+lo = 2*NT*Kp*4, A ring = 4 * 128 * (Kp/2) * 4, barriers + slack 1 KB
+    const int ring = 4 * TC_BM * (Kp / 2) * 4;
+    int nt_max = (TC_SMEM_LIMIT - ring - 1024) / (2 * Kp * 4);
+    nt_max = std::min(nt_max, 256) / 16 * 16;
+    if (nt_max < 16) return false;
+    const int spt_max = nt_max / Mp;
+    const int n_wtiles = (n_states + spt_max - 1) / spt_max;
+    int spt = (n_states + n_wtiles - 1) / n_wtiles;
+    spt = (spt + gran - 1) / gran * gran;
+    g->Mp = Mp; g->Kp = Kp; g->SPT = spt; g->NT = spt * Mp;
+    g->n_wtiles = (n_states + spt - 1) / spt;
+    g->tile_bytes = (size_t)2 * g->NT * Kp * 4;
+    g->total_bytes = sizeof(TcHeader) + g->tile_bytes * g->n_wtiles;
+    g->smem_bytes = g->tile_bytes + ring + 1024;
+    return true;
+}
+
+// byte offset of element (row n, k) inside one K-major no-swizzle image of `rows` x `K` fp32:
+// core matrix = 8 rows x 16 bytes; [n/8][k/4][n%8][k%4]  ->  LBO (next K chunk) = 128 B, SBO (next 8 rows) = (K/4)*128 B
+__host__ __device__ inline uint32_t kmajor_off(int n, int k, int K) {
+    return (uint32_t)(((n >> 3) * (K >> 2) + (k >> 2)) * 128 + (n & 7) * 16 + (k & 3) * 4);
+}
+
+__global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double* __restrict__ mu, const double* __restrict__ var,
+                                   int n_states, int n_mix, int dim, const double* __restrict__ shift, TcGeom g,
+                                   uint8_t* __restrict__ packed) {
+    const int64_t cols_total = (int64_t)g.n_wtiles * g.NT;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        TcHeader* h = reinterpret_cast<TcHeader*>(packed);
+        h->magic = TC_MAGIC; h->n_states = n_states; h->n_mix = n_mix; h->Mp = g.Mp; h->dim = dim; h->Kp = g.Kp;
+        h->SPT = g.SPT; h->NT = g.NT; h->n_wtiles = g.n_wtiles;
+        for (int d = 0; d < 64; ++d) h->shift[d] = (shift && d < dim) ? (float)shift[d] : 0.f;
+    }
+    if (idx >= cols_total * g.Kp) return;
+    const int64_t col = idx / g.Kp;
+    const int k = (int)(idx - col * g.Kp);
+    const int tile = (int)(col / g.NT), n = (int)(col - (int64_t)tile * g.NT);
+    const int j = tile * g.SPT + n / g.Mp, m = n % g.Mp;
+    double v = 0.0;
+    if (j < n_states && m < n_mix) {
+        const int64_t gi = (int64_t)j * n_mix + m;
+        if (k < TC_MAX_DIM) {
+            if (k < dim) v = -0.5 / var[gi * dim + k];
+        } else if (k < 2 * TC_MAX_DIM) {
+            const int d = k - TC_MAX_DIM;
+            if (d < dim) {
+                const double sh = shift ? shift[d] : 0.0;
+                v = (mu[gi * dim + d] - sh) / var[gi * dim + d];
+            }
+        } else if (k == 2 * TC_MAX_DIM) {
+            double c = (double)dim * 1.8378770664093453;
+            for (int d = 0; d < dim; ++d) {
+                const double sh = shift ? shift[d] : 0.0;
+                const double mm = mu[gi * dim + d] - sh;
+                c += log(var[gi * dim + d]) + mm * mm / var[gi * dim + d];
+            }
+            v = logw[gi] - 0.5 * c;
+            if (!(v > -1e30)) v = -1e30;                 // log w = -inf: keep the hi/lo split finite
+        }
+        v *= 1.4426950408889634;                          // log2(e): the epilogue works in base 2
+    } else if (k == 2 * TC_MAX_DIM) {
+        v = -1e30;                                        // padded mixture / state: contributes exp2(-huge) = 0
+    }
+    const float hi = tf32_round((float)v);
+    const float lo = (float)(v - (double)hi);
+    uint8_t* base = packed + sizeof(TcHeader) + (size_t)tile * g.tile_bytes;
+    const uint32_t off = kmajor_off(n, k, g.Kp);
+    *reinterpret_cast<float*>(base + off) = hi;
+    *reinterpret_cast<float*>(base + (size_t)g.NT * g.Kp * 4 + off) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+struct TcArgs {
+    const float* feats; int ld_feats; int64_t n_frames;
+    const uint8_t* packed; float* b_out; int64_t ld_b;
+    int n_states, dim, Mp, Kp, SPT, NT, n_wtiles, n_fsplit;
+    int64_t frames_per_split;
+    uint32_t swap_lbo_sbo;
+};
+
+template <int MP>
+__device__ __forceinline__ void lse_store(const float* v, float* out_row, int st0, int st_end) {
+    // 16 accumulator columns = 16/MP states, MP mixtures each, base-2 domain
+#pragma unroll
+    for (int g = 0; g < 16 / MP; ++g) {
+        float mx = v[g * MP];
+#pragma unroll
+        for (int i = 1; i < MP; ++i) mx = fmaxf(mx, v[g * MP + i]);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MP; ++i) s += exp2f(v[g * MP + i] - mx);
+        const float r = (mx + __log2f(s)) * TC_LN2;
+        if (st0 + g < st_end) out_row[st0 + g] = r;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    constexpr int Kp = TC_KP, KH = TC_KH;
+    const int NT = a.NT;
+    const uint32_t w_part = (uint32_t)NT * Kp * 4;
+    const uint32_t slot_bytes = TC_BM * KH * 4;
+    uint8_t* s_w = tc_smem;                       // [hi | lo]
+    uint8_t* s_a = tc_smem + 2 * w_part;          // 4 slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + 4 * slot_bytes);
+    uint64_t* a_full = bars;                      // [4] producers -> MMA
+    uint64_t* a_empty = bars + 4;                 // [4] MMA (commit) -> producers
+    uint64_t* t_full = bars + 8;                  // [2] MMA (commit) -> epilogue
+    uint64_t* t_empty = bars + 10;                // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* s_shift = reinterpret_cast<float*>(bars + 13);          // [TC_MAX_DIM+1] feature centre
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 128); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const TcHeader* hdr = reinterpret_cast<const TcHeader*>(a.packed);
+    if (tid <= TC_MAX_DIM) s_shift[tid] = hdr->shift[tid];
+    const uint32_t idesc = make_idesc_tf32(TC_BM, NT);
+    // descriptor strides of the K-major no-swizzle images (kmajor_off): next K chunk 128 B, next 8 rows (K/4)*128 B
+    uint32_t a_lbo = 128, a_sbo = (uint32_t)(KH / 4) * 128, b_lbo = 128, b_sbo = (uint32_t)(Kp / 4) * 128;
+    if (a.swap_lbo_sbo) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+
+    uint32_t prod_cnt = 0;      // ring-slot visits (producer view)
+    uint32_t mma_cnt = 0;       // ring-slot visits (MMA view)
+    uint32_t tile_cnt = 0;      // accumulator stages used (MMA and epilogue keep their own copies in lock step)
+    int cur_wtile = -1;
+    const int n_items = a.n_wtiles * a.n_fsplit;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int wt = item % a.n_wtiles, fsp = item / a.n_wtiles;
+        const int64_t fs = (int64_t)fsp * a.frames_per_split;
+        const int64_t fe = min(a.n_frames, fs + a.frames_per_split);
+        if (fs >= fe) continue;
+        if (wt != cur_wtile) {
+            // (re)load the resident W tile: plain 16-byte copies, then make them visible to the tensor-core proxy
+            __syncthreads();
+            const uint4* src = reinterpret_cast<const uint4*>(a.packed + sizeof(TcHeader) + (size_t)wt * 2 * w_part);
+            uint4* dst = reinterpret_cast<uint4*>(s_w);
+            for (uint32_t i = tid; i < 2 * w_part / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+            fence_proxy_async();
+            __syncthreads();
+            cur_wtile = wt;
+        }
+        const int n_tiles = (int)((fe - fs + TC_BM - 1) / TC_BM);
+
+        if (warp >= 4 && warp < 8) {
+            // ===================== producers: thread = frame row
+            const int r = tid - 128;
+            const uint32_t row_off = (uint32_t)((r >> 3) * (KH >> 2) * 128 + (r & 7) * 16);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int64_t f = fs + (int64_t)t * TC_BM + r;
+                float x[TC_MAX_DIM + 1];
+                const bool valid = f < fe;
+                const float* xr = a.feats + f * a.ld_feats;
+                if (valid && (a.ld_feats & 3) == 0 && a.ld_feats >= TC_MAX_DIM + 1 && ((uintptr_t)a.feats & 15) == 0) {
+#pragma unroll
+                    for (int c = 0; c < (TC_MAX_DIM + 1) / 4; ++c) {
+                        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c * 4 < a.dim) q = __ldg(reinterpret_cast<const float4*>(xr) + c);
+                        x[4 * c] = q.x; x[4 * c + 1] = q.y; x[4 * c + 2] = q.z; x[4 * c + 3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < TC_MAX_DIM; ++d) x[d] = (valid && d < a.dim) ? __ldg(xr + d) : 0.f;
+                }
+#pragma unroll
+                for (int d = 0; d < TC_MAX_DIM; ++d) x[d] = (valid && d < a.dim) ? x[d] - s_shift[d] : 0.f;
+                // ring slot s holds K half (s&1) of the hi (s<2) or lo (s>=2) image of [x^2 (39) | x (39) | 1 | 0]
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int half = s & 1;
+                    const bool islo = (s >> 1) != 0;
+                    mbar_wait(a_empty + s, ((prod_cnt >> 2) & 1) ^ 1);
+                    uint8_t* slot = s_a + s * slot_bytes + row_off;
+#pragma unroll
+                    for (int cc = 0; cc < KH / 4; ++cc) {
+                        float q[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = half * KH + cc * 4 + e;          // compile-time after unrolling
+                            float v;
+                            if (k < TC_MAX_DIM) v = x[k] * x[k];
+                            else if (k < 2 * TC_MAX_DIM) v = x[k - TC_MAX_DIM];
+                            else v = (k == 2 * TC_MAX_DIM) ? 1.f : 0.f;
+                            const float hi = tf32_round(v);
+                            q[e] = islo ? (v - hi) : hi;
+                        }
+                        *reinterpret_cast<float4*>(slot + cc * 128) = make_float4(q[0], q[1], q[2], q[3]);
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(a_full + s);
+                    ++prod_cnt;
+                }
+            }
+        } else if (warp == 8) {
+            // ===================== MMA issuer: one thread
+            if (lane == 0) {
+                const uint32_t wh = smem_u32(s_w), wl = wh + w_part;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const uint32_t stage = tile_cnt & 1;
+                    mbar_wait(t_empty + stage, ((tile_cnt >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + stage * (uint32_t)NT;
+                    uint32_t acc = 0;
+                    for (int s = 0; s < 4; ++s) {
+                        const int half = s & 1, islo = s >> 1;
+                        mbar_wait(a_full + s, (mma_cnt >> 2) & 1);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(s_a + s * slot_bytes);
+                        for (int j = 0; j < KH / 8; ++j) {
+                            const int gk = half * (KH / 8) + j;
+                            const uint64_t ad = make_smem_desc(sa + j * 2 * (a.swap_lbo_sbo ? a_sbo : a_lbo), a_lbo, a_sbo, 0);
+                            const uint64_t bh = make_smem_desc(wh + gk * 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo), b_lbo, b_sbo, 0);
+                            umma_tf32(d_tmem, ad, bh, idesc, acc);
+                            acc = 1;
+                            if (!islo) {
+                                const uint64_t bl = make_smem_desc(wl + gk * 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo), b_lbo, b_sbo, 0);
+                                umma_tf32(d_tmem, ad, bl, idesc, 1u);
+                            }
+                        }
+                        umma_commit(a_empty + s);       // slot free once these MMAs have read it
+                        ++mma_cnt;
+                    }
+                    umma_commit(t_full + stage);        // accumulator stage complete
+                    ++tile_cnt;
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===================== epilogue: warp w reads TMEM lanes 32w..32w+31 (= frame rows)
+            const int row = warp * 32 + lane;
+            const int st_tile0 = wt * a.SPT;
+            const int st_end = min(a.n_states, st_tile0 + a.SPT);
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t stage = tile_cnt & 1;
+                mbar_wait(t_full + stage, (tile_cnt >> 1) & 1);
+                tc_fence_after();
+                const int64_t f = fs + (int64_t)t * TC_BM + row;
+                float* out_row = a.b_out + f * a.ld_b;
+                const bool valid = f < fe;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * (uint32_t)NT;
+                for (int c0 = 0; c0 < NT; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
+                    const int st0 = st_tile0 + c0 / a.Mp;
+                    const int se = valid ? st_end : 0;
+                    switch (a.Mp) {
+                        case 16: lse_store<16>(v, out_row, st0, se); break;
+                        case 8: lse_store<8>(v, out_row, st0, se); break;
+                        case 4: lse_store<4>(v, out_row, st0, se); break;
+                        case 2: lse_store<2>(v, out_row, st0, se); break;
+                        default: lse_store<1>(v, out_row, st0, se); break;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(t_empty + stage);
+                ++tile_cnt;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+static uint32_t g_umma_swap = 0;
+
+}  // namespace lnasr
+
+using namespace lnasr;
+
+extern "C" int lnasr_debug_set_umma_swap(int swap) { g_umma_swap = swap ? 1u : 0u; return LNASR_OK; }
+
+extern "C" int lnasr_debug_umma_probe(const float* a_image, int32_t a_bytes, const float* b_image, int32_t b_bytes, uint32_t a_lbo,
+                                      uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout_type, uint32_t idesc,
+                                      float* d_out, void* stream) {
+    LNASR_CHECK_ARG(a_image && b_image && d_out, "umma_probe: null pointer");
+    LNASR_CHECK_ARG(a_bytes > 0 && b_bytes > 0 && a_bytes % 16 == 0 && b_bytes % 16 == 0 && a_bytes + b_bytes <= 128 * 1024,
+                    "umma_probe: image sizes must be multiples of 16 and fit 128 KB");
+    const size_t smem = (size_t)((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023) + 1024;
+    LNASR_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a_image, a_bytes, b_image, b_bytes, a_lbo, a_sbo, b_lbo, b_sbo,
+                                                             layout_type, idesc, d_out);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_gmm_tc_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes) {
+    TcGeom g;
+    LNASR_CHECK_ARG(bytes, "gmm_tc_packed_bytes: null pointer");
+    LNASR_CHECK_ARG(tc_geometry(n_states, n_mix, dim, &g), "gmm_tc: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", TC_MAX_DIM, n_mix, dim);
+    *bytes = g.total_bytes;
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_gmm_pack_tc(const double* logw, const double* mu, const double* var, int32_t n_states, int32_t n_mix,
+                                 int32_t dim, const double* shift, void* packed, void* stream) {
+    TcGeom g;
+    LNASR_CHECK_ARG(logw && mu && var && packed, "gmm_pack_tc: null pointer");
+    LNASR_CHECK_ARG(tc_geometry(n_states, n_mix, dim, &g), "gmm_tc: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", TC_MAX_DIM, n_mix, dim);
+    const int64_t n = (int64_t)g.n_wtiles * g.NT * g.Kp;
+    gmm_pack_tc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, shift, g,
+                                                                                     (uint8_t*)packed);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed, int32_t n_states,
+                                   int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b, void* stream) {
+    TcGeom g;
+    LNASR_CHECK_ARG(feats && packed && b_out, "gmm_loglik_tc: null pointer");
+    LNASR_CHECK_ARG(tc_geometry(n_states, n_mix, dim, &g), "gmm_tc: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", TC_MAX_DIM, n_mix, dim);
+    LNASR_CHECK_ARG(ld_feats >= dim && ld_b >= n_states, "gmm_loglik_tc: bad leading dimensions");
+    if (n_frames == 0) return LNASR_OK;
+    TcArgs a{};
+    a.feats = feats; a.ld_feats = ld_feats; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
+    a.n_states = n_states; a.dim = dim; a.Mp = g.Mp; a.Kp = g.Kp; a.SPT = g.SPT; a.NT = g.NT; a.n_wtiles = g.n_wtiles;
+    const int sms = sm_count();
+    const int64_t frame_tiles = ceil_div(n_frames, TC_BM);
+    int n_fsplit = (int)std::max<int64_t>(1, std::min<int64_t>(frame_tiles, sms / std::max(1, g.n_wtiles)));
+    const int64_t tiles_per_split = ceil_div(frame_tiles, n_fsplit);
+    n_fsplit = (int)ceil_div(frame_tiles, tiles_per_split);
+    a.n_fsplit = n_fsplit;
+    a.frames_per_split = tiles_per_split * TC_BM;
+    a.swap_lbo_sbo = g_umma_swap;
+    const int grid = std::min(sms, g.n_wtiles * n_fsplit);
+    LNASR_CUDA(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    gmm_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}

@@ -1,0 +1,547 @@
+// trellis.cu -- HMM log-trellis: forward, backward, Viterbi (+ backtrace) for ragged utterance batches
+// scored against a bank of models (kernel (3) of the north star).
+//
+// Replaces, from /root/reference/lnasr/hmm.py: _forward (63-100), _backward (102-131), _viterbi (133-172),
+// calc_prob (268-274), decode (276-283).
+//
+// Two kernels, both persistent over the time axis of their utterance with the trellis column held
+// on chip in float64:
+//   * small  (N <= 32): a group of G=2^k lanes owns one (utterance, model) pair, lane = state; the
+//     predecessor column of log A lives in registers, the previous trellis column is exchanged with
+//     warp shuffles, max / log-sum-exp over predecessors are register loops.  32/G pairs per warp.
+//   * general (any N): one CTA per (utterance, model) pair, trellis column double-buffered in shared
+//     memory, transitions walked as ELL lists of the FINITE entries of log A (left-to-right
+//     topologies have 2-3 per state), one __syncthreads per frame.
+// Backpointers go to HBM as uint16 state indices; the backtrace (hmm.py:168-171) is a separate
+// one-thread-per-pair pointer chase so that it runs for all pairs concurrently.
+//
+// Tie rule: np.argmax takes the first maximum (hmm.py:166,169) -> strict '>' while scanning ascending i.
+#include <algorithm>
+#include "common.cuh"
+
+namespace lnasr {
+
+enum { MODE_VITERBI = 0, MODE_FORWARD = 1, MODE_BACKWARD = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// transition packing
+__global__ void trans_degree_kernel(const double* __restrict__ logA, int n_models, int N, int* __restrict__ deg) {
+    // one thread per (model, state): counts finite entries of its column and of its row
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_models * N) return;
+    const int k = (int)(idx / N), s = (int)(idx % N);
+    const double* A = logA + (int64_t)k * N * N;
+    int cin = 0, cout = 0;
+    for (int i = 0; i < N; ++i) {
+        cin += (A[(int64_t)i * N + s] != neg_inf());
+        cout += (A[(int64_t)s * N + i] != neg_inf());
+    }
+    atomicMax(deg + 0, cin);
+    atomicMax(deg + 1, cout);
+}
+
+__global__ void trans_pack_kernel(const double* __restrict__ logA, int n_models, int N, int max_in, int max_out,
+                                  int* __restrict__ pred_idx, double* __restrict__ pred_val,
+                                  int* __restrict__ succ_idx, double* __restrict__ succ_val) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_models * N) return;
+    const int k = (int)(idx / N), s = (int)(idx % N);
+    const double* A = logA + (int64_t)k * N * N;
+    int c = 0;
+    for (int i = 0; i < N && c < max_in; ++i) {
+        const double a = A[(int64_t)i * N + s];
+        if (a != neg_inf()) {
+            pred_idx[((int64_t)k * max_in + c) * N + s] = i;
+            pred_val[((int64_t)k * max_in + c) * N + s] = a;
+            ++c;
+        }
+    }
+    for (; c < max_in; ++c) {
+        pred_idx[((int64_t)k * max_in + c) * N + s] = 0;
+        pred_val[((int64_t)k * max_in + c) * N + s] = neg_inf();
+    }
+    c = 0;
+    for (int j = 0; j < N && c < max_out; ++j) {
+        const double a = A[(int64_t)s * N + j];
+        if (a != neg_inf()) {
+            succ_idx[((int64_t)k * max_out + c) * N + s] = j;
+            succ_val[((int64_t)k * max_out + c) * N + s] = a;
+            ++c;
+        }
+    }
+    for (; c < max_out; ++c) {
+        succ_idx[((int64_t)k * max_out + c) * N + s] = 0;
+        succ_val[((int64_t)k * max_out + c) * N + s] = neg_inf();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-N kernel
+struct TrellisArgs {
+    const void* b; int64_t ld_b;
+    const int64_t* frame_off; int n_utt; int n_models; int N;
+    const double* logA; const double* logpi;
+    double* full_out;        // v / alpha / beta, [T_total, n_models*N] or null
+    uint32_t* bt_out;        // viterbi only, optional
+    uint16_t* bt_ws;         // viterbi only, required when a path is wanted
+    double* score_out;       // [n_utt, n_models]: max v[T-1] (viterbi) / lse alpha[T-1] (forward); unused for backward
+    int32_t* last_state;     // [n_utt*n_models], viterbi only
+    int max_in, max_out;
+    const int* pred_idx; const double* pred_val; const int* succ_idx; const double* succ_val;
+};
+
+constexpr int TS_WARPS = 4;
+constexpr int TS_PF = 4;     // emission prefetch depth (frames)
+
+template <int G, typename BT, int MODE>
+__global__ void __launch_bounds__(TS_WARPS * 32)
+trellis_small_kernel(TrellisArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PPW = 32 / G;                                   // pairs per warp
+    const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
+    const int64_t p = ((int64_t)blockIdx.x * TS_WARPS + warp) * PPW + lane / G;
+    const int j = lane % G;
+    const int N = a.N;
+    const bool pair_ok = p < n_pairs;
+    const bool active = pair_ok && j < N;
+    const int u = pair_ok ? (int)(p / a.n_models) : 0;
+    const int k = pair_ok ? (int)(p % a.n_models) : 0;
+    const int64_t f0 = pair_ok ? __ldg(a.frame_off + u) : 0;
+    const int T = pair_ok ? (int)(__ldg(a.frame_off + u + 1) - f0) : 0;
+    int Tmax = T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+    if (Tmax == 0) return;
+
+    // transition column (forward/viterbi: A[:, j]) or row (backward: A[j, :]) in registers
+    double tr[G];
+    const double* A = a.logA + (int64_t)k * N * N;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        double v = neg_inf();
+        if (active && i < N) v = (MODE == MODE_BACKWARD) ? __ldg(A + (int64_t)j * N + i) : __ldg(A + (int64_t)i * N + j);
+        tr[i] = v;
+    }
+    const BT* bcol = (const BT*)a.b + (int64_t)k * N + j;
+    const int64_t ncol = (int64_t)a.n_models * N;
+    const int64_t col = (int64_t)k * N + j;
+    // emission row used at step s: forward/viterbi -> frame s ; backward -> frame T-s (s>=1), frame T-1 at s=0 (unused)
+    auto emis_row = [&](int s) -> int64_t {
+        if (MODE == MODE_BACKWARD) return f0 + (s == 0 ? T - 1 : T - s);
+        return f0 + s;
+    };
+    BT bq[TS_PF];
+#pragma unroll
+    for (int i = 0; i < TS_PF; ++i) bq[i] = (active && i < T) ? __ldg(bcol + emis_row(i) * a.ld_b) : BT(0);
+
+    double cur = neg_inf();       // trellis value of my state
+    for (int s0 = 0; s0 < Tmax; s0 += TS_PF) {
+#pragma unroll
+        for (int i = 0; i < TS_PF; ++i) {
+            const int s = s0 + i;
+            const double e = (double)bq[i];
+            bq[i] = (active && s + TS_PF < T) ? __ldg(bcol + emis_row(s + TS_PF) * a.ld_b) : BT(0);
+            const bool live = active && s < T;
+            double nv;
+            int arg = 0;
+            if (MODE == MODE_BACKWARD) {
+                // beta[T-1] = 0 ; beta[t,i] = lse_j (beta[t+1,j] + A[i,j] + b[j,t+1])     (hmm.py:126-130)
+                const double uj = cur + e;                       // beta[t+1,j] + b[t+1,j], my j
+                double cand[G];
+                double mx = neg_inf();
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    cand[q] = shfl_d(uj, q, G) + tr[q];
+                    mx = fmax(mx, cand[q]);
+                }
+                double sum = 0.0;
+#pragma unroll
+                for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
+                nv = (s == 0) ? 0.0 : ((mx == neg_inf()) ? mx : mx + log(sum));
+            } else if (MODE == MODE_FORWARD) {
+                // alpha[0] = pi + b[:,0] ; alpha[t,j] = lse_i (alpha[t-1,i] + A[i,j]) + b[j,t]   (hmm.py:95-99)
+                double cand[G];
+                double mx = neg_inf();
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    cand[q] = shfl_d(cur, q, G) + tr[q];
+                    mx = fmax(mx, cand[q]);
+                }
+                double sum = 0.0;
+#pragma unroll
+                for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
+                const double l = (mx == neg_inf()) ? mx : mx + log(sum);
+                nv = (s == 0) ? (active ? __ldg(a.logpi + (int64_t)k * N + j) + e : neg_inf()) : l + e;
+            } else {
+                // v[0] = pi + b[:,0] ; v[t,j] = max_i (v[t-1,i] + A[i,j]) + b[j,t] ; bt = first argmax (hmm.py:160-166)
+                double best = neg_inf();
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    const double c = shfl_d(cur, q, G) + tr[q];
+                    if (c > best) { best = c; arg = q; }
+                }
+                nv = (s == 0) ? (active ? __ldg(a.logpi + (int64_t)k * N + j) + e : neg_inf()) : best + e;
+                if (s == 0) arg = 0;
+            }
+            if (live) {
+                cur = nv;
+                const int64_t row = (MODE == MODE_BACKWARD) ? (f0 + T - 1 - s) : (f0 + s);
+                if (a.full_out) a.full_out[row * ncol + col] = nv;
+                if (MODE == MODE_VITERBI) {
+                    if (a.bt_ws) a.bt_ws[row * ncol + col] = (uint16_t)arg;
+                    if (a.bt_out) a.bt_out[row * ncol + col] = (uint32_t)arg;
+                }
+            }
+        }
+    }
+    // termination: max / argmax (viterbi, hmm.py:169) or lse (forward, hmm.py:274) over the last column
+    if (MODE == MODE_VITERBI) {
+        double best = neg_inf();
+        int arg = 0;
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            const double c = shfl_d(cur, q, G);
+            if (q < N && c > best) { best = c; arg = q; }
+        }
+        if (pair_ok && j == 0) {
+            if (a.score_out) a.score_out[p] = best;
+            if (a.last_state) a.last_state[p] = arg;
+        }
+    } else if (MODE == MODE_FORWARD) {
+        double mx = neg_inf();
+        double cand[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            cand[q] = (q < N) ? shfl_d(cur, q, G) : neg_inf();
+            mx = fmax(mx, cand[q]);
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
+        if (pair_ok && j == 0 && a.score_out) a.score_out[p] = (mx == neg_inf()) ? mx : mx + log(sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// general kernel: one CTA per (utterance, model)
+constexpr int TG_THREADS = 256;
+
+template <typename BT, int MODE>
+__global__ void __launch_bounds__(TG_THREADS)
+trellis_general_kernel(TrellisArgs a) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    const int N = a.N;
+    double* buf0 = (double*)tg_smem;
+    double* buf1 = buf0 + N;
+    __shared__ double red_v[TG_THREADS / 32];
+    __shared__ int red_i[TG_THREADS / 32];
+    const int64_t p = blockIdx.x;
+    const int u = (int)(p / a.n_models), k = (int)(p % a.n_models);
+    const int64_t f0 = __ldg(a.frame_off + u);
+    const int T = (int)(__ldg(a.frame_off + u + 1) - f0);
+    if (T == 0) return;
+    const int64_t ncol = (int64_t)a.n_models * N;
+    const int64_t cbase = (int64_t)k * N;
+    const BT* b = (const BT*)a.b;
+    const int deg = (MODE == MODE_BACKWARD) ? a.max_out : a.max_in;
+    const int* eidx = ((MODE == MODE_BACKWARD) ? a.succ_idx : a.pred_idx) + (int64_t)k * deg * N;
+    const double* eval = ((MODE == MODE_BACKWARD) ? a.succ_val : a.pred_val) + (int64_t)k * deg * N;
+    double* prev = buf0;
+    double* next = buf1;
+    // step 0
+    for (int j = threadIdx.x; j < N; j += TG_THREADS) {
+        double v;
+        if (MODE == MODE_BACKWARD) {
+            v = 0.0;
+            if (a.full_out) a.full_out[(f0 + T - 1) * ncol + cbase + j] = 0.0;
+            v += (double)__ldg(b + (f0 + T - 1) * a.ld_b + cbase + j);    // buffer holds beta[t]+b[t]
+        } else {
+            v = __ldg(a.logpi + cbase + j) + (double)__ldg(b + f0 * a.ld_b + cbase + j);
+            if (a.full_out) a.full_out[f0 * ncol + cbase + j] = v;
+            if (MODE == MODE_VITERBI) {
+                if (a.bt_ws) a.bt_ws[f0 * ncol + cbase + j] = 0;
+                if (a.bt_out) a.bt_out[f0 * ncol + cbase + j] = 0;
+            }
+        }
+        prev[j] = v;
+    }
+    __syncthreads();
+    for (int s = 1; s < T; ++s) {
+        const int64_t row = (MODE == MODE_BACKWARD) ? (f0 + T - 1 - s) : (f0 + s);
+        for (int j = threadIdx.x; j < N; j += TG_THREADS) {
+            const double e = (double)__ldg(b + row * a.ld_b + cbase + j);
+            double nv;
+            if (MODE == MODE_VITERBI) {
+                double best = neg_inf();
+                int arg = 0;
+                for (int d = 0; d < deg; ++d) {
+                    const int i = __ldg(eidx + (int64_t)d * N + j);
+                    const double c = prev[i] + __ldg(eval + (int64_t)d * N + j);
+                    if (c > best) { best = c; arg = i; }
+                }
+                nv = best + e;
+                if (a.bt_ws) a.bt_ws[row * ncol + cbase + j] = (uint16_t)arg;
+                if (a.bt_out) a.bt_out[row * ncol + cbase + j] = (uint32_t)arg;
+                if (a.full_out) a.full_out[row * ncol + cbase + j] = nv;
+                next[j] = nv;
+            } else {
+                double mx = neg_inf();
+                for (int d = 0; d < deg; ++d) {
+                    const int i = __ldg(eidx + (int64_t)d * N + j);
+                    mx = fmax(mx, prev[i] + __ldg(eval + (int64_t)d * N + j));
+                }
+                double sum = 0.0;
+                if (mx != neg_inf()) {
+                    for (int d = 0; d < deg; ++d) {
+                        const int i = __ldg(eidx + (int64_t)d * N + j);
+                        const double c = prev[i] + __ldg(eval + (int64_t)d * N + j);
+                        sum += (c == neg_inf()) ? 0.0 : exp(c - mx);
+                    }
+                }
+                const double l = (mx == neg_inf()) ? mx : mx + log(sum);
+                if (MODE == MODE_FORWARD) {
+                    nv = l + e;
+                    if (a.full_out) a.full_out[row * ncol + cbase + j] = nv;
+                    next[j] = nv;
+                } else {
+                    if (a.full_out) a.full_out[row * ncol + cbase + j] = l;   // beta[t, j]
+                    next[j] = l + e;                                          // beta[t] + b[t] for the next step
+                }
+            }
+        }
+        __syncthreads();
+        double* t = prev; prev = next; next = t;
+    }
+    if (MODE == MODE_BACKWARD) return;
+    // termination over prev[0..N)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MODE == MODE_VITERBI) {
+        double best = neg_inf();
+        int arg = 0x7fffffff;
+        for (int j = threadIdx.x; j < N; j += TG_THREADS) {
+            const double c = prev[j];
+            if (c > best) { best = c; arg = j; }      // ascending j per thread -> first max per thread
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = shfl_d(best, lane ^ o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (lane == 0) { red_v[warp] = best; red_i[warp] = arg; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < TG_THREADS / 32; ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < arg)) { best = red_v[w]; arg = red_i[w]; }
+            if (arg == 0x7fffffff) arg = 0;           // all -inf: np.argmax gives 0
+            if (a.score_out) a.score_out[p] = best;
+            if (a.last_state) a.last_state[p] = arg;
+        }
+    } else {
+        double mx = neg_inf();
+        for (int j = threadIdx.x; j < N; j += TG_THREADS) mx = fmax(mx, prev[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_d(mx, lane ^ o));
+        if (lane == 0) red_v[warp] = mx;
+        __syncthreads();
+        mx = red_v[0];
+        for (int w = 1; w < TG_THREADS / 32; ++w) mx = fmax(mx, red_v[w]);
+        __syncthreads();
+        double sum = 0.0;
+        if (mx != neg_inf())
+            for (int j = threadIdx.x; j < N; j += TG_THREADS) sum += (prev[j] == neg_inf()) ? 0.0 : exp(prev[j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += shfl_d(sum, lane ^ o);
+        if (lane == 0) red_v[warp] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < TG_THREADS / 32; ++w) sum += red_v[w];
+            if (a.score_out) a.score_out[p] = (mx == neg_inf()) ? mx : mx + log(sum);
+        }
+    }
+}
+
+// path[T-1] = argmax v[T-1]; path[t] = bt[t+1, path[t+1]]                                  (hmm.py:168-171)
+__global__ void backtrace_kernel(const uint16_t* __restrict__ bt, const int32_t* __restrict__ last_state,
+                                 const int64_t* __restrict__ frame_off, int n_utt, int n_models, int N,
+                                 int64_t total_frames, uint32_t* __restrict__ path) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (int64_t)n_utt * n_models) return;
+    const int u = (int)(p / n_models), k = (int)(p % n_models);
+    const int64_t f0 = frame_off[u];
+    const int T = (int)(frame_off[u + 1] - f0);
+    if (T == 0) return;
+    const int64_t ncol = (int64_t)n_models * N;
+    uint32_t* out = path + (int64_t)k * total_frames + f0;
+    int s = last_state[p];
+    out[T - 1] = (uint32_t)s;
+    for (int t = T - 2; t >= 0; --t) {
+        s = bt[(f0 + t + 1) * ncol + (int64_t)k * N + s];
+        out[t] = (uint32_t)s;
+    }
+}
+
+// word = argmax_k score[u, k], first maximum (np.argmax); all -inf / NaN-free input assumed
+__global__ void argmax_rows_kernel(const double* __restrict__ score, int n_rows, int n_cols, int32_t* __restrict__ arg,
+                                   double* __restrict__ best_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    double best = neg_inf();
+    int a = 0;
+    for (int k = 0; k < n_cols; ++k) {
+        const double v = score[(int64_t)r * n_cols + k];
+        if (v > best) { best = v; a = k; }
+    }
+    arg[r] = a;
+    if (best_out) best_out[r] = best;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename BT, int MODE>
+static int launch_small(const TrellisArgs& a, cudaStream_t stream) {
+    const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
+    int G = 1;
+    while (G < a.N) G <<= 1;
+    if (G < 4) G = 4;
+    const int ppw = 32 / G;
+    const unsigned grid = (unsigned)ceil_div(n_pairs, (int64_t)TS_WARPS * ppw);
+    switch (G) {
+        case 4:  trellis_small_kernel<4, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
+        case 8:  trellis_small_kernel<8, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
+        case 16: trellis_small_kernel<16, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
+        default: trellis_small_kernel<32, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
+    }
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+template <typename BT, int MODE>
+static int launch_general(const TrellisArgs& a, cudaStream_t stream) {
+    const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
+    const size_t smem = 2 * (size_t)a.N * sizeof(double);
+    if (smem > 200 * 1024) { set_error("trellis: N=%d does not fit the shared-memory column buffers", a.N); return LNASR_EINVAL; }
+    if (smem > 48 * 1024)
+        LNASR_CUDA(cudaFuncSetAttribute(trellis_general_kernel<BT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trellis_general_kernel<BT, MODE><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+template <int MODE>
+static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, cudaStream_t stream) {
+    a.n_models = bank->n_models; a.N = bank->N; a.logA = bank->logA; a.logpi = bank->logpi;
+    a.max_in = bank->max_in; a.max_out = bank->max_out;
+    a.pred_idx = bank->pred_idx; a.pred_val = bank->pred_val; a.succ_idx = bank->succ_idx; a.succ_val = bank->succ_val;
+    const bool f32 = (b_dtype == LNASR_DT_F32);
+    if (a.N <= 32) return f32 ? launch_small<float, MODE>(a, stream) : launch_small<double, MODE>(a, stream);
+    const bool have = (MODE == MODE_BACKWARD) ? (a.succ_idx && a.succ_val && a.max_out > 0) : (a.pred_idx && a.pred_val && a.max_in > 0);
+    if (!have) { set_error("trellis: N=%d > 32 needs the packed transition lists (lnasr_trans_pack)", a.N); return LNASR_EINVAL; }
+    return f32 ? launch_general<float, MODE>(a, stream) : launch_general<double, MODE>(a, stream);
+}
+
+static int check_common(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                        const lnasr_hmm_bank* bank, const char* who) {
+    if (!b || !frame_offsets || !bank || !bank->logA || !bank->logpi) { set_error("%s: null pointer", who); return LNASR_EINVAL; }
+    if (b_dtype != LNASR_DT_F32 && b_dtype != LNASR_DT_F64) { set_error("%s: b dtype must be float32/float64", who); return LNASR_EINVAL; }
+    if (bank->n_models < 1 || bank->N < 1 || bank->N > 65535) { set_error("%s: need 1 <= N <= 65535, n_models >= 1", who); return LNASR_EINVAL; }
+    if (ld_b < (int64_t)bank->n_models * bank->N) { set_error("%s: ld_b too small", who); return LNASR_EINVAL; }
+    if (n_utt < 0) { set_error("%s: n_utt < 0", who); return LNASR_EINVAL; }
+    return LNASR_OK;
+}
+
+}  // namespace lnasr
+
+using namespace lnasr;
+
+extern "C" int lnasr_trans_degree(const double* logA, int32_t n_models, int32_t N, int32_t* deg_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LNASR_CHECK_ARG(logA && deg_out && n_models >= 1 && N >= 1, "trans_degree: bad arguments");
+    LNASR_CUDA(cudaMemsetAsync(deg_out, 0, 2 * sizeof(int32_t), stream));
+    const int64_t n = (int64_t)n_models * N;
+    trans_degree_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(logA, n_models, N, deg_out);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_trans_pack(const double* logA, int32_t n_models, int32_t N, int32_t max_in, int32_t max_out,
+                                int32_t* pred_idx, double* pred_val, int32_t* succ_idx, double* succ_val, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LNASR_CHECK_ARG(logA && pred_idx && pred_val && succ_idx && succ_val, "trans_pack: null pointer");
+    LNASR_CHECK_ARG(n_models >= 1 && N >= 1 && max_in >= 1 && max_out >= 1, "trans_pack: bad shape");
+    const int64_t n = (int64_t)n_models * N;
+    trans_pack_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(logA, n_models, N, max_in, max_out, pred_idx, pred_val, succ_idx, succ_val);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+extern "C" size_t lnasr_viterbi_workspace_bytes(int64_t total_frames, int32_t n_utt, int32_t n_models, int32_t N) {
+    // uint16 backpointers [total_frames, n_models*N] + int32 final state per (utterance, model)
+    size_t bt = (size_t)total_frames * n_models * N * sizeof(uint16_t);
+    bt = (bt + 255) & ~(size_t)255;
+    return bt + (size_t)n_utt * n_models * sizeof(int32_t);
+}
+
+extern "C" int lnasr_viterbi_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                                   int64_t total_frames, const lnasr_hmm_bank* bank, uint32_t* path_out,
+                                   double* score_out, double* v_out, uint32_t* bt_out, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_common(b, b_dtype, ld_b, frame_offsets, n_utt, bank, "viterbi_batch");
+    if (rc) return rc;
+    if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    TrellisArgs a{};
+    a.b = b; a.ld_b = ld_b; a.frame_off = frame_offsets; a.n_utt = n_utt;
+    a.full_out = v_out; a.bt_out = bt_out; a.score_out = score_out;
+    const int64_t n_pairs = (int64_t)n_utt * bank->n_models;
+    if (path_out) {
+        size_t bt_bytes = ((size_t)total_frames * bank->n_models * bank->N * sizeof(uint16_t) + 255) & ~(size_t)255;
+        size_t need = bt_bytes + (size_t)n_pairs * sizeof(int32_t);
+        if (!workspace || workspace_bytes < need) {
+            set_error("viterbi_batch: workspace %zu < %zu bytes", workspace_bytes, need);
+            return LNASR_EWORKSPACE;
+        }
+        a.bt_ws = (uint16_t*)workspace;
+        a.last_state = (int32_t*)((char*)workspace + bt_bytes);
+    }
+    rc = run_trellis<MODE_VITERBI>(a, b_dtype, bank, stream);
+    if (rc) return rc;
+    if (path_out) {
+        backtrace_kernel<<<(unsigned)ceil_div(n_pairs, 64), 64, 0, stream>>>(a.bt_ws, a.last_state, frame_offsets, n_utt,
+                                                                          bank->n_models, bank->N, total_frames, path_out);
+        LNASR_LAUNCH_CHECK();
+    }
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_forward_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                                   int64_t total_frames, const lnasr_hmm_bank* bank, double* alpha_out,
+                                   double* logprob_out, void* stream_) {
+    int rc = check_common(b, b_dtype, ld_b, frame_offsets, n_utt, bank, "forward_batch");
+    if (rc) return rc;
+    if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    TrellisArgs a{};
+    a.b = b; a.ld_b = ld_b; a.frame_off = frame_offsets; a.n_utt = n_utt;
+    a.full_out = alpha_out; a.score_out = logprob_out;
+    return run_trellis<MODE_FORWARD>(a, b_dtype, bank, (cudaStream_t)stream_);
+}
+
+extern "C" int lnasr_backward_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t* frame_offsets, int32_t n_utt,
+                                    int64_t total_frames, const lnasr_hmm_bank* bank, double* beta_out, void* stream_) {
+    int rc = check_common(b, b_dtype, ld_b, frame_offsets, n_utt, bank, "backward_batch");
+    if (rc) return rc;
+    LNASR_CHECK_ARG(beta_out, "backward_batch: beta_out is null");
+    if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    TrellisArgs a{};
+    a.b = b; a.ld_b = ld_b; a.frame_off = frame_offsets; a.n_utt = n_utt;
+    a.full_out = beta_out;
+    return run_trellis<MODE_BACKWARD>(a, b_dtype, bank, (cudaStream_t)stream_);
+}
+
+extern "C" int lnasr_argmax_rows(const double* score, int32_t n_rows, int32_t n_cols, int32_t* arg_out, double* best_out,
+                                 void* stream) {
+    LNASR_CHECK_ARG(score && arg_out && n_rows >= 0 && n_cols >= 1, "argmax_rows: bad arguments");
+    if (n_rows == 0) return LNASR_OK;
+    argmax_rows_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(score, n_rows, n_cols, arg_out, best_out);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}

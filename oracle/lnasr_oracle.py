@@ -27,7 +27,7 @@ __all__ = [
     "hmm_map_b", "forward", "backward", "viterbi", "baumwelch",
     "estimate_hmm", "estimate_gmmhmm", "estimate_gmmhmm_diag",
     "calc_prob", "decode", "train_gmmhmm", "em_accumulate_diag", "em_finalize_diag",
-    "em_step_multi_diag", "random_gmmhmm", "score_words",
+    "em_step_multi_diag", "random_gmmhmm", "score_words", "score_words_viterbi",
 ]
 
 NEG_INF = -np.inf
@@ -462,3 +462,15 @@ def score_words(obs, models):
     scores = np.array(scores)
     probs = np.array(probs)
     return int(np.argmax(scores)), scores, int(np.argmax(probs)), probs, paths
+
+
+def score_words_viterbi(obs, models):
+    """Viterbi-only isolated-word decision (what the batched GPU decode computes): word, scores, paths."""
+    scores, paths = [], []
+    for mdl in models:
+        b, _ = map_b(obs, mdl["w"], mdl["mu"], mdl["var"])
+        v, _, path = viterbi(mdl["pi"], mdl["A"], b)
+        scores.append(np.max(v[-1]))
+        paths.append(path)
+    scores = np.array(scores)
+    return int(np.argmax(scores)), scores, paths

@@ -1,0 +1,77 @@
+"""MFCC kernel (csrc/mfcc.cu through lnasr.mfcc.MFCC) against the golden vectors of the unmodified reference
+and against the numpy oracle.  Tolerance: 1e-4 relative (BASELINE.json), see helpers.assert_close."""
+import numpy as np
+import pytest
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["", "_s401", "_s1000", "_s16000", "_s48017", "_float", "_zero"]
+
+
+@pytest.fixture(scope="module")
+def mfcc():
+    from lnasr.mfcc import MFCC
+    return MFCC()
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_calc_mfcc_matches_reference_golden(golden, mfcc, tag):
+    g = golden("mfcc")
+    pcm = g["pcm_data_raw"] if tag == "" else g["pcm" + tag]
+    P, C, F = mfcc.calc_mfcc(pcm)
+    assert P.dtype == np.float64 and F.shape == g["feats" + tag].shape
+    assert_close(P, g["power" + tag], 1e-4, "power" + tag)
+    assert_close(C, g["ceps" + tag], 1e-4, "cepstrum" + tag)
+    assert_close(F, g["feats" + tag], 1e-4, "features" + tag)
+
+
+def test_attributes_and_tables(golden, mfcc):
+    g = golden("mfcc")
+    assert (mfcc.frame_L, mfcc.frame_step, mfcc.fft_size, mfcc.D) == (400, 160, 257, 39)
+    assert np.array_equal(mfcc.create_filter_bank(), g["fbank"])
+    x = g["pcm_data_raw"]
+    y = mfcc.calc_high_pass_filter(x)
+    ref = np.append(x[0], x[1:] - 0.97 * x[:-1])
+    np.testing.assert_allclose(y, ref, rtol=1e-14, atol=1e-9)
+
+
+def test_ragged_batch_equals_per_utterance_oracle(mfcc):
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(5)
+    lens = [401, 16000, 800, 5000, 48017, 720, 2400, 33333]
+    sigs = []
+    for n in lens:
+        t = np.arange(n) / 16000.0
+        x = np.round(3000.0 * rng.standard_normal(n)) + 2000.0 * np.sin(2 * np.pi * rng.uniform(80, 400) * t)
+        sigs.append(np.clip(x, -32767, 32767).astype(np.int16))
+    res = mfcc.calc_mfcc_batch(sigs)
+    feats = res.feats.double().cpu().numpy()
+    off = res.frame_offsets_host
+    assert list(np.diff(off)) == [O.num_frames(n) for n in lens]
+    for u, s in enumerate(sigs):
+        _, _, F = O.mfcc(s)
+        assert_close(feats[off[u]:off[u + 1]], F, 1e-4, f"utt{u}")
+
+
+def test_short_utterance_raises_like_reference(mfcc):
+    # S=300 -> 1 frame: the reference indexes features[1] and raises IndexError (mfcc.py:164)
+    with pytest.raises(IndexError):
+        mfcc.calc_mfcc(np.ones(300, dtype=np.int16))
+
+
+def test_large_batch_properties(mfcc):
+    """Full-size property checks (no oracle): shape rule, per-utterance zero mean of c1..c12, delta identities."""
+    rng = np.random.default_rng(11)
+    n_utt, n = 512, 16000
+    pcm = np.clip(np.round(3000.0 * rng.standard_normal(n_utt * n)), -32767, 32767).astype(np.int16)
+    off = np.arange(n_utt + 1, dtype=np.int64) * n
+    res = mfcc.calc_mfcc_batch(pcm, sample_offsets=off)
+    F = res.feats.double().cpu().numpy().reshape(n_utt, 99, 39)
+    assert np.all(np.isfinite(F))
+    assert np.abs(F[:, :, :12].mean(axis=1) + 1e-8).max() < 1e-3                      # CMN (mfcc.py:156)
+    np.testing.assert_allclose(F[:, 1:, 13:26], F[:, 1:, :13] - F[:, :-1, :13], atol=2e-4)    # delta (mfcc.py:162-166)
+    np.testing.assert_allclose(F[:, 0, 13:26], F[:, 1, :13], atol=1e-6)                       # delta row 0 = static row 1
+    np.testing.assert_allclose(F[:, 1:, 26:], F[:, 1:, 13:26] - F[:, :-1, 13:26], atol=4e-4)  # delta-delta
+    np.testing.assert_allclose(F[:, 0, 26:], F[:, 1, 13:26], atol=1e-6)

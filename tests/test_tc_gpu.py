@@ -1,0 +1,122 @@
+"""Tensor-core GMM path (csrc/gmm_tc.cu): descriptor bring-up probe and parity of the 3xTF32 contraction + fused
+log-sum-exp against the float64 oracle.  Bar: emission log-likelihoods within 1e-4 relative (BASELINE.json)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf32(x):
+    """Round float32 to TF32 precision (10-bit mantissa) so that products are exact in fp32."""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32)
+    u = (u + 0x1000) & 0xFFFFE000
+    return u.view(np.float32)
+
+
+def _kmajor_image(mat):
+    """[rows, K] float32 -> UMMA canonical K-major no-swizzle image [rows/8][K/4][8][4] (csrc/gmm_tc.cu kmajor_off)."""
+    rows, K = mat.shape
+    return np.ascontiguousarray(mat.reshape(rows // 8, 8, K // 4, 4).transpose(0, 2, 1, 3)).ravel()
+
+
+def _probe(a, b, a_lbo, a_sbo, b_lbo, b_sbo):
+    import torch
+    from lnasr import _capi
+    lib = _capi.lib()
+    a_img = torch.from_numpy(_kmajor_image(a)).cuda()
+    b_img = torch.from_numpy(_kmajor_image(b)).cuda()
+    d = torch.zeros((128, 128), dtype=torch.float32, device="cuda")
+    idesc = (1 << 4) | (2 << 7) | (2 << 10) | ((128 >> 3) << 17) | ((128 >> 4) << 24)
+    _capi.check(lib.lnasr_debug_umma_probe(_capi.ptr(a_img), a_img.numel() * 4, _capi.ptr(b_img), b_img.numel() * 4,
+                                           a_lbo, a_sbo, b_lbo, b_sbo, 0, idesc, _capi.ptr(d), _capi.stream_ptr()), "probe")
+    torch.cuda.synchronize()
+    return d.cpu().numpy()
+
+
+def test_umma_descriptor_convention():
+    """One tcgen05.mma M=128 N=128 K=8 kind::tf32: D = A . B^T with LBO = K-chunk stride, SBO = 8-row-group stride."""
+    rng = np.random.default_rng(0)
+    a = _tf32(rng.standard_normal((128, 8)))
+    b = _tf32(rng.standard_normal((128, 8)))
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    d = _probe(a, b, 128, 256, 128, 256)
+    err_doc = np.abs(d - ref).max()
+    d_sw = _probe(a, b, 256, 128, 256, 128)
+    err_sw = np.abs(d_sw - ref).max()
+    print(f"umma probe: max err documented convention {err_doc:.3e}, swapped {err_sw:.3e}")
+    assert err_doc < 1e-4, f"documented LBO/SBO convention is wrong on this hardware (swapped err {err_sw:.3e})"
+
+
+@pytest.mark.parametrize("n,mix,d,T", [(14, 16, 39, 128), (30, 16, 39, 1000), (200, 16, 39, 777), (64, 4, 13, 300),
+                                       (100, 8, 39, 129), (33, 3, 20, 260)])
+def test_gmm_tc_matches_oracle(n, mix, d, T):
+    import torch
+    from lnasr.gmm_tc import PackedGmmTC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(n + 7 * mix)
+    mdl = O.random_gmmhmm(n, mix, d, rng)
+    x = (0.5 * rng.standard_normal((T, d))).astype(np.float32)
+    b_ref, _ = O.map_b(x.astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
+    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"])
+    b = g.loglik(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    got = b.cpu().numpy().T
+    err = np.abs(got - b_ref)
+    print(f"tc n={n} m={mix} d={d} T={T}: max abs err {err.max():.3e}, max rel {np.max(err / np.abs(b_ref)):.3e}")
+    assert np.max(err / np.abs(b_ref)) < 1e-4
+    assert err.max() < 2e-4         # fp32-level: what the per-utterance 1e-3 log-probability budget needs
+    # padded feature rows (ld = 40) take the 16-byte load path and must give identical numbers
+    xp = torch.zeros((T, 40), dtype=torch.float32, device="cuda")
+    xp[:, :d] = torch.from_numpy(x).cuda()
+    b2 = g.loglik(xp)
+    assert torch.equal(b, b2)
+
+
+def test_gmm_tc_large_feature_magnitudes_with_shift():
+    """Real MFCC magnitudes (|x| ~ 100) need the centring shift to stay inside 1e-4 relative comfortably."""
+    import torch
+    from lnasr.gmm_tc import PackedGmmTC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(2)
+    n, mix, d, T = 28, 16, 39, 256
+    mdl = O.random_gmmhmm(n, mix, d, rng)
+    centre = rng.uniform(-50, 50, size=d)
+    mdl["mu"] = mdl["mu"] * 10 + centre
+    x = (centre + 3.0 * rng.standard_normal((T, d))).astype(np.float32)
+    b_ref, _ = O.map_b(x.astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
+    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], shift=centre)
+    b = g.loglik(torch.from_numpy(x).cuda()).cpu().numpy().T
+    assert np.max(np.abs(b - b_ref) / np.abs(b_ref)) < 1e-4
+
+
+def test_bank_with_tc_emissions_decodes_like_oracle():
+    """Viterbi on tensor-core emissions: paths bit-exact, ties / fp32 near-ties aside."""
+    import torch
+    from lnasr.bank import ModelBank
+    from oracle import lnasr_oracle as O
+    from helpers import path_score
+    rng = np.random.default_rng(21)
+    mdl = O.random_gmmhmm(140, 16, 39, rng, left_to_right=True)
+    mdl["pi"] = np.full(140, -np.inf)
+    mdl["pi"][0] = 0.0
+    lens = [300, 150, 299]
+    utts = [(0.5 * rng.standard_normal((T, 39))).astype(np.float32) for T in lens]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    bank = ModelBank([mdl], emission="tc")
+    res = bank.score(torch.from_numpy(np.concatenate(utts)).cuda(), torch.from_numpy(off).cuda(), 3, int(off[-1]),
+                     want_paths=True, want_logprob=True)
+    paths = res.paths.cpu().numpy()[0]
+    with np.errstate(all="ignore"):
+        for u, x in enumerate(utts):
+            b, _ = O.map_b(x.astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
+            v, _, p_ref = O.viterbi(mdl["pi"], mdl["A"], b)
+            got = paths[off[u]:off[u + 1]]
+            s_got, s_ref = path_score(got, mdl["pi"], mdl["A"], b), path_score(p_ref, mdl["pi"], mdl["A"], b)
+            assert abs(s_got - s_ref) < 1e-3, (s_got, s_ref)               # same path up to fp32 near-ties
+            assert abs(res.scores.cpu().numpy()[u, 0] - np.max(v[-1])) < 1e-3 * lens[u] / 100
+            lp_ref = O.lse(O.forward(mdl["pi"], mdl["A"], b)[-1])
+            assert abs(res.logprob.cpu().numpy()[u, 0] - lp_ref) < 1e-3 * max(1, lens[u] / 100)
