@@ -59,14 +59,14 @@ typedef struct lnasr_mfcc_tables {
     int32_t fft_n;            /* MFCC.fft_N; this build supports 512 only */
     int32_t n_mel;            /* MFCC.mfbank_num (40) ; <= 64 */
     int32_t n_ceps;           /* MFCC.cepstrum_num (12) ; < n_mel, <= 31 */
-    float   hpf_alpha;        /* MFCC.hpf_alpha (0.97) */
+    double  hpf_alpha;        /* MFCC.hpf_alpha (0.97) */
     int32_t fb_stride;        /* row stride of fb_weight (>= max filter width, <= 64) */
-    const float*   window;    /* [frame_len]  Hamming window */
-    const float*   twiddle;   /* [fft_n] pairs (cos, -sin)(2 pi m / fft_n) as float2 */
+    const double*  window;    /* [frame_len]  Hamming window (float64) */
+    const double*  twiddle;   /* [fft_n] pairs (cos, -sin)(2 pi m / fft_n) as double2 */
     const int32_t* fb_start;  /* [n_mel] first FFT bin with non-zero weight */
     const int32_t* fb_len;    /* [n_mel] number of consecutive non-zero bins */
     const float*   fb_weight; /* [n_mel, fb_stride] the non-zero weights of each triangular filter */
-    const float*   dct_t;     /* [n_mel(n), n_mel(k)] DCT-II ortho matrix, transposed: dct_t[n*n_mel+k] */
+    const double*  dct_t;     /* [n_mel(n), n_mel(k)] DCT-II ortho matrix (float64), transposed: dct_t[n*n_mel+k] */
 } lnasr_mfcc_tables;
 
 /* MFCC.calc_high_pass_filter (lnasr/mfcc.py:50-64) alone: y[0]=x[0]; y[t]=x[t]-alpha*x[t-1]; float64 out */
@@ -101,10 +101,12 @@ int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* sample_offse
  *   tc    : [x^2, x, 1] . [-1/(2 var), mu/var, c]^T as a 3xTF32 tcgen05 contraction with the log-sum-exp
  *           over mixtures fused into the TMEM epilogue -- large models (config 4).
  */
-/* packed exact model: per Gaussian 2*dim+2 doubles [ -1/(2 var_d) | mu_d | -1/2 (D ln 2pi + sum ln var) | log w ] */
+/* packed exact model: lnasr_gmm_exact_packed_doubles() float64 values -- chunks of 4 mixtures of one state
+ * (n_mix padded with log w = -inf), (dim+1) rows of [a_0..a_3 | b_0..b_3] per chunk (see csrc/gmm_exact.cu) */
+int64_t lnasr_gmm_exact_packed_doubles(int32_t n_states, int32_t n_mix, int32_t dim);
 int lnasr_gmm_pack_exact(const double* logw /*[n_states,n_mix]*/, const double* mu /*[n_states,n_mix,dim]*/,
                          const double* var /*[n_states,n_mix,dim]*/, int32_t n_states, int32_t n_mix, int32_t dim,
-                         double* packed /*[n_states*n_mix, 2*dim+2]*/, void* stream);
+                         double* packed, void* stream);
 int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype /*F32|F64*/, int32_t ld_feats, int64_t n_frames,
                            const double* packed, int32_t n_states, int32_t n_mix, int32_t dim,
                            void* b_out /*[n_frames, ld_b]*/, int b_dtype /*F32|F64*/, int64_t ld_b,

@@ -12,71 +12,127 @@
 
 namespace lnasr {
 
-constexpr int GX_THREADS = 128;   // one frame per thread
+constexpr int GX_THREADS = 128;                   // threads of one state group (and of the full-covariance kernel)
+constexpr int GX_FT = 2;                          // frames per thread (register tile: 2 frames x 4 Gaussians)
+constexpr int GX_TILE = GX_THREADS * GX_FT;       // frames per block
+constexpr int GX_SGROUPS = 4;                     // state groups per block: 512 threads share one x tile
 constexpr int GX_MAX_DIM = 64;
 
-// packed[g] = [ a_d = -1/(2 var_d) (D) | mu_d (D) | c = -1/2 (D ln 2pi + sum ln var) | logw ]   (2D+2 doubles)
+// Packed model: Gaussians in chunks of 4 mixtures of one state (n_mix padded with log w = -inf).  Per chunk
+// (dim+1) rows of 8 doubles:  row d < dim: [a_0..a_3 | b_0..b_3],  a = -1/(2 var_d), b = mu_d/var_d;
+// row dim: [c_0..c_3 | logw_0..logw_3],  c = -1/2 (D ln 2pi + sum ln var + sum mu^2/var).
+// log N(x) = sum_d (a_d x_d + b_d) x_d + c   -- two DFMA per (Gaussian, dim); float64 makes the expansion harmless.
+__host__ __device__ inline int gx_chunks(int n_mix) { return (n_mix + 3) / 4; }
+
 __global__ void gmm_pack_exact_kernel(const double* __restrict__ logw, const double* __restrict__ mu,
-                                      const double* __restrict__ var, int n_gauss, int dim,
+                                      const double* __restrict__ var, int n_states, int n_mix, int dim,
                                       double* __restrict__ packed) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_gauss) return;
-    double* o = packed + (int64_t)g * (2 * dim + 2);
-    double sumlog = 0.0;
-    for (int d = 0; d < dim; ++d) {
-        const double v = var[(int64_t)g * dim + d];
-        o[d] = -0.5 / v;
-        o[dim + d] = mu[(int64_t)g * dim + d];
-        sumlog += log(v);
+    const int nch = gx_chunks(n_mix);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // (state, chunk, g)
+    if (idx >= n_states * nch * 4) return;
+    const int g = idx & 3, ch = (idx >> 2) % nch, j = (idx >> 2) / nch;
+    const int m = ch * 4 + g;
+    double* o = packed + (int64_t)(j * nch + ch) * (dim + 1) * 8;
+    if (m >= n_mix) {
+        for (int d = 0; d < dim; ++d) { o[d * 8 + g] = 0.0; o[d * 8 + 4 + g] = 0.0; }
+        o[dim * 8 + g] = 0.0;
+        o[dim * 8 + 4 + g] = neg_inf();
+        return;
     }
-    o[2 * dim] = -0.5 * ((double)dim * 1.8378770664093453 /* ln(2 pi) */ + sumlog);
-    o[2 * dim + 1] = logw[g];
+    const int64_t gi = (int64_t)j * n_mix + m;
+    double c = (double)dim * 1.8378770664093453;  /* ln(2 pi) */
+    for (int d = 0; d < dim; ++d) {
+        const double v = var[gi * dim + d], mm = mu[gi * dim + d];
+        o[d * 8 + g] = -0.5 / v;
+        o[d * 8 + 4 + g] = mm / v;
+        c += log(v) + mm * mm / v;
+    }
+    o[dim * 8 + g] = -0.5 * c;
+    o[dim * 8 + 4 + g] = logw[gi];
+}
+
+__device__ __forceinline__ void lse_push(double v, double& mx, double& sum) {
+    if (v > mx) {
+        sum = sum * exp(mx - v) + 1.0;
+        mx = v;
+    } else if (v != neg_inf()) {
+        sum += exp(v - mx);
+    }
 }
 
 template <typename FeatT, typename OutT>
-__global__ void __launch_bounds__(GX_THREADS)
+__global__ void __launch_bounds__(GX_THREADS * GX_SGROUPS, 2)
 gmm_loglik_exact_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_frames,
                         const double* __restrict__ packed, int n_states, int n_mix, int dim,
                         OutT* __restrict__ b_out, int64_t ld_b, double* __restrict__ bm_out, int states_per_block) {
-    // x tile transposed: xs[d][thread] -> conflict-free column reads
+    // x tile transposed: xs[d][frame] -> conflict-free column reads
     extern __shared__ __align__(16) unsigned char gx_smem[];
-    double (*xs)[GX_THREADS + 1] = reinterpret_cast<double (*)[GX_THREADS + 1]>(gx_smem);
-    const int64_t t = (int64_t)blockIdx.x * GX_THREADS + threadIdx.x;
-    const int64_t t0 = (int64_t)blockIdx.x * GX_THREADS;
-    // coalesced load of the [128, dim] tile
-    const int rows = (int)min((int64_t)GX_THREADS, n_frames - t0);
-    for (int i = threadIdx.x; i < rows * dim; i += GX_THREADS) {
+    double (*xs)[GX_TILE] = reinterpret_cast<double (*)[GX_TILE]>(gx_smem);
+    const int tid = threadIdx.x & (GX_THREADS - 1);            // frame lane inside the state group
+    const int sgroup = threadIdx.x / GX_THREADS;              // states j = j_begin + sgroup, + GX_SGROUPS, ...
+    const int64_t t0 = (int64_t)blockIdx.x * GX_TILE;
+    const int rows = (int)min((int64_t)GX_TILE, n_frames - t0);
+    for (int i = threadIdx.x; i < GX_TILE * dim; i += GX_THREADS * GX_SGROUPS) {
         const int r = i / dim, d = i - r * dim;
-        xs[d][r] = (double)feats[(t0 + r) * ld_feats + d];
+        xs[d][r] = (r < rows) ? (double)feats[(t0 + r) * ld_feats + d] : 0.0;
     }
     __syncthreads();
-    if (t >= n_frames) return;
+    const int64_t tA = t0 + tid, tB = t0 + tid + GX_THREADS;
+    const bool okA = tA < n_frames, okB = tB < n_frames;
+    const int nch = gx_chunks(n_mix);
     const int j_begin = blockIdx.y * states_per_block;
     const int j_end = min(n_states, j_begin + states_per_block);
-    const int stride = 2 * dim + 2;
-    for (int j = j_begin; j < j_end; ++j) {
-        // online log-sum-exp over the mixtures
-        double mx = neg_inf(), sum = 0.0;
-        for (int m = 0; m < n_mix; ++m) {
-            const double* p = packed + (int64_t)(j * n_mix + m) * stride;
-            double q = 0.0;
-#pragma unroll 4
+    const int64_t n_gauss = (int64_t)n_states * n_mix;
+    for (int j = j_begin + sgroup; j < j_end; j += GX_SGROUPS) {
+        double mxA = neg_inf(), sumA = 0.0, mxB = neg_inf(), sumB = 0.0;
+        for (int ch = 0; ch < nch; ++ch) {
+            const double2* p = reinterpret_cast<const double2*>(packed + (int64_t)(j * nch + ch) * (dim + 1) * 8);
+            double qA[4] = {0.0, 0.0, 0.0, 0.0}, qB[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 3
             for (int d = 0; d < dim; ++d) {
-                const double diff = xs[d][threadIdx.x] - __ldg(p + dim + d);
-                q = fma(diff * diff, __ldg(p + d), q);
+                const double xA = xs[d][tid], xB = xs[d][tid + GX_THREADS];
+                const double2 a01 = __ldg(p + d * 4), a23 = __ldg(p + d * 4 + 1);
+                const double2 b01 = __ldg(p + d * 4 + 2), b23 = __ldg(p + d * 4 + 3);
+                qA[0] = fma(fma(a01.x, xA, b01.x), xA, qA[0]);
+                qA[1] = fma(fma(a01.y, xA, b01.y), xA, qA[1]);
+                qA[2] = fma(fma(a23.x, xA, b23.x), xA, qA[2]);
+                qA[3] = fma(fma(a23.y, xA, b23.y), xA, qA[3]);
+                qB[0] = fma(fma(a01.x, xB, b01.x), xB, qB[0]);
+                qB[1] = fma(fma(a01.y, xB, b01.y), xB, qB[1]);
+                qB[2] = fma(fma(a23.x, xB, b23.x), xB, qB[2]);
+                qB[3] = fma(fma(a23.y, xB, b23.y), xB, qB[3]);
             }
-            const double g = q + __ldg(p + 2 * dim);         // pure Gaussian log-density, gmm.py:59-68
-            if (bm_out) bm_out[t * ((int64_t)n_states * n_mix) + (int64_t)j * n_mix + m] = g;   // gmmhmm.py:66
-            const double bm = g + __ldg(p + 2 * dim + 1);    // + log w[j,m], gmmhmm.py:67
-            if (bm > mx) {
-                sum = sum * exp(mx - bm) + 1.0;
-                mx = bm;
-            } else if (bm != neg_inf()) {
-                sum += exp(bm - mx);
+            const double2 c01 = __ldg(p + dim * 4), c23 = __ldg(p + dim * 4 + 1);
+            const double2 w01 = __ldg(p + dim * 4 + 2), w23 = __ldg(p + dim * 4 + 3);
+            const double c[4] = {c01.x, c01.y, c23.x, c23.y}, lw[4] = {w01.x, w01.y, w23.x, w23.y};
+            double vA[4], vB[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int m = ch * 4 + g;
+                const double gA = qA[g] + c[g], gB = qB[g] + c[g];     // pure Gaussian log-density, gmm.py:59-68
+                if (bm_out && m < n_mix) {                              // gmmhmm.py:66
+                    if (okA) bm_out[tA * n_gauss + (int64_t)j * n_mix + m] = gA;
+                    if (okB) bm_out[tB * n_gauss + (int64_t)j * n_mix + m] = gB;
+                }
+                vA[g] = gA + lw[g];                                     // + log w[j,m], gmmhmm.py:67
+                vB[g] = gB + lw[g];
+            }
+            // branch-free streaming log-sum-exp over the chunk (exp(-inf) = 0 covers empty mixtures)
+            const double nA = fmax(fmax(fmax(vA[0], vA[1]), fmax(vA[2], vA[3])), mxA);
+            const double nB = fmax(fmax(fmax(vB[0], vB[1]), fmax(vB[2], vB[3])), mxB);
+            if (nA != neg_inf()) {
+                if (ch > 0) sumA *= exp(mxA - nA);
+                sumA += (exp(vA[0] - nA) + exp(vA[1] - nA)) + (exp(vA[2] - nA) + exp(vA[3] - nA));
+                mxA = nA;
+            }
+            if (nB != neg_inf()) {
+                if (ch > 0) sumB *= exp(mxB - nB);
+                sumB += (exp(vB[0] - nB) + exp(vB[1] - nB)) + (exp(vB[2] - nB) + exp(vB[3] - nB));
+                mxB = nB;
             }
         }
-        const double r = (mx == neg_inf()) ? mx : mx + log(sum);
-        b_out[t * ld_b + j] = (OutT)r;
+        if (okA) b_out[tA * ld_b + j] = (OutT)((mxA == neg_inf()) ? mxA : mxA + log(sumA));
+        if (okB) b_out[tB * ld_b + j] = (OutT)((mxB == neg_inf()) ? mxB : mxB + log(sumB));
     }
 }
 
@@ -135,12 +191,16 @@ __global__ void emit_gather_kernel(const double* __restrict__ logB, const int32_
 
 using namespace lnasr;
 
+extern "C" int64_t lnasr_gmm_exact_packed_doubles(int32_t n_states, int32_t n_mix, int32_t dim) {
+    return (int64_t)n_states * gx_chunks(n_mix) * (dim + 1) * 8;
+}
+
 extern "C" int lnasr_gmm_pack_exact(const double* logw, const double* mu, const double* var, int32_t n_states,
                                     int32_t n_mix, int32_t dim, double* packed, void* stream) {
     LNASR_CHECK_ARG(logw && mu && var && packed, "gmm_pack_exact: null pointer");
     LNASR_CHECK_ARG(n_states >= 1 && n_mix >= 1 && dim >= 1, "gmm_pack_exact: bad shape");
-    const int n = n_states * n_mix;
-    gmm_pack_exact_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n, dim, packed);
+    const int n = n_states * gx_chunks(n_mix) * 4;
+    gmm_pack_exact_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, packed);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }
@@ -148,18 +208,18 @@ extern "C" int lnasr_gmm_pack_exact(const double* logw, const double* mu, const 
 template <typename FeatT, typename OutT>
 static int launch_exact(const void* feats, int ld_feats, int64_t n_frames, const double* packed, int n_states,
                         int n_mix, int dim, void* b_out, int64_t ld_b, double* bm_out, cudaStream_t stream) {
-    const int64_t tiles = ceil_div(n_frames, GX_THREADS);
-    // split the states over blockIdx.y until the grid fills the machine twice
+    const int64_t tiles = ceil_div(n_frames, GX_TILE);
+    // split the states over blockIdx.y until the grid fills the machine a few times over
     int y = 1;
-    const int64_t want = 2LL * sm_count() * 4;
+    const int64_t want = 4LL * sm_count();
     while (tiles * y < want && y * 2 <= n_states) y *= 2;
     const int spb = (int)ceil_div(n_states, y);
     y = (int)ceil_div(n_states, spb);
     dim3 grid((unsigned)tiles, (unsigned)y);
-    const size_t smem = (size_t)dim * (GX_THREADS + 1) * sizeof(double);
+    const size_t smem = (size_t)dim * GX_TILE * sizeof(double);
     if (smem > 48 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(gmm_loglik_exact_kernel<FeatT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_loglik_exact_kernel<FeatT, OutT><<<grid, GX_THREADS, smem, stream>>>(
+    gmm_loglik_exact_kernel<FeatT, OutT><<<grid, GX_THREADS * GX_SGROUPS, smem, stream>>>(
         (const FeatT*)feats, ld_feats, n_frames, packed, n_states, n_mix, dim, (OutT*)b_out, ld_b, bm_out, spb);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
@@ -172,7 +232,7 @@ extern "C" int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype, int32_
     LNASR_CHECK_ARG(feats && packed && b_out, "gmm_loglik_exact: null pointer");
     LNASR_CHECK_ARG(dim >= 1 && dim <= GX_MAX_DIM, "gmm_loglik_exact: dim must be in [1,%d]", GX_MAX_DIM);
     LNASR_CHECK_ARG(ld_feats >= dim && ld_b >= n_states && n_states >= 1 && n_mix >= 1, "gmm_loglik_exact: bad shape");
-    LNASR_CHECK_ARG(n_frames < (1LL << 31) * GX_THREADS, "gmm_loglik_exact: too many frames");
+    LNASR_CHECK_ARG(n_frames < (1LL << 31) * GX_TILE, "gmm_loglik_exact: too many frames");
     if (n_frames == 0) return LNASR_OK;
     const bool f32 = feats_dtype == LNASR_DT_F32, f64 = feats_dtype == LNASR_DT_F64;
     const bool o32 = b_dtype == LNASR_DT_F32, o64 = b_dtype == LNASR_DT_F64;

@@ -177,9 +177,9 @@ static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     while (Mp < n_mix) Mp <<= 1;
     const int Kp = TC_KP;                                      // fixed K axis [x^2 (39) | x (39) | 1 | 0]; dims beyond `dim` are zero
     const int gran = 16 / Mp;                                  // states per 16 accumulator columns
-    // shared memory: W hi+lo = 2*NT*Kp*4, A ring = 4 * 128 * (Kp/2) * 4, barriers + slack 1 KB
+    // shared memory: W hi+lo = 2*NT*Kp*4, constants NT*4, A ring = 4 * 128 * (Kp/2) * 4, barriers + shift 1 KB
     const int ring = 4 * TC_BM * (Kp / 2) * 4;
-    int nt_max = (TC_SMEM_LIMIT - ring - 1024) / (2 * Kp * 4);
+    int nt_max = (TC_SMEM_LIMIT - ring - 1024) / (2 * Kp * 4 + 4);
     nt_max = std::min(nt_max, 256) / 16 * 16;
     if (nt_max < 16) return false;
     const int spt_max = nt_max / Mp;
@@ -188,7 +188,7 @@ static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     spt = (spt + gran - 1) / gran * gran;
     g->Mp = Mp; g->Kp = Kp; g->SPT = spt; g->NT = spt * Mp;
     g->n_wtiles = (n_states + spt - 1) / spt;
-    g->tile_bytes = (size_t)2 * g->NT * Kp * 4;
+    g->tile_bytes = (size_t)2 * g->NT * Kp * 4 + (size_t)g->NT * 4;      // W hi | W lo | per-column constant c
     g->total_bytes = sizeof(TcHeader) + g->tile_bytes * g->n_wtiles;
     g->smem_bytes = g->tile_bytes + ring + 1024;
     return true;
@@ -227,19 +227,28 @@ __global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double
                 const double sh = shift ? shift[d] : 0.0;
                 v = (mu[gi * dim + d] - sh) / var[gi * dim + d];
             }
-        } else if (k == 2 * TC_MAX_DIM) {
-            double c = (double)dim * 1.8378770664093453;
+        }
+        v *= 1.4426950408889634;                          // log2(e): the epilogue works in base 2
+    }
+    if (k == 2 * TC_MAX_DIM) {
+        // the constant of the Gaussian (+ log w) is added in the epilogue in fp32 with round-to-nearest: keeping it
+        // out of the tensor-core accumulator keeps the accumulated magnitudes -- and with them the truncation of
+        // the fp32 accumulation -- small.  Padded mixtures / states get -1e30 (exp2 -> 0).
+        double c = -1e30;
+        if (j < n_states && m < n_mix) {
+            const int64_t gi = (int64_t)j * n_mix + m;
+            c = (double)dim * 1.8378770664093453;
             for (int d = 0; d < dim; ++d) {
                 const double sh = shift ? shift[d] : 0.0;
                 const double mm = mu[gi * dim + d] - sh;
                 c += log(var[gi * dim + d]) + mm * mm / var[gi * dim + d];
             }
-            v = logw[gi] - 0.5 * c;
-            if (!(v > -1e30)) v = -1e30;                 // log w = -inf: keep the hi/lo split finite
+            c = (logw[gi] - 0.5 * c) * 1.4426950408889634;
+            if (!(c > -1e30)) c = -1e30;                  // log w = -inf
         }
-        v *= 1.4426950408889634;                          // log2(e): the epilogue works in base 2
-    } else if (k == 2 * TC_MAX_DIM) {
-        v = -1e30;                                        // padded mixture / state: contributes exp2(-huge) = 0
+        float* ctab = reinterpret_cast<float*>(packed + sizeof(TcHeader) + (size_t)tile * g.tile_bytes + (size_t)2 * g.NT * g.Kp * 4);
+        ctab[n] = (float)c;
+        v = 0.0;
     }
     const float hi = tf32_round((float)v);
     const float lo = (float)(v - (double)hi);
@@ -280,8 +289,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
     const int NT = a.NT;
     const uint32_t w_part = (uint32_t)NT * Kp * 4;
     const uint32_t slot_bytes = TC_BM * KH * 4;
-    uint8_t* s_w = tc_smem;                       // [hi | lo]
-    uint8_t* s_a = tc_smem + 2 * w_part;          // 4 slots
+    const uint32_t tile_bytes = 2 * w_part + (uint32_t)NT * 4;
+    uint8_t* s_w = tc_smem;                       // [W hi | W lo | c], the packed tile image verbatim
+    const float* s_c = reinterpret_cast<const float*>(tc_smem + 2 * w_part);
+    uint8_t* s_a = tc_smem + tile_bytes;          // 4 ring slots
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + 4 * slot_bytes);
     uint64_t* a_full = bars;                      // [4] producers -> MMA
     uint64_t* a_empty = bars + 4;                 // [4] MMA (commit) -> producers
@@ -322,9 +333,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
         if (wt != cur_wtile) {
             // (re)load the resident W tile: plain 16-byte copies, then make them visible to the tensor-core proxy
             __syncthreads();
-            const uint4* src = reinterpret_cast<const uint4*>(a.packed + sizeof(TcHeader) + (size_t)wt * 2 * w_part);
+            const uint4* src = reinterpret_cast<const uint4*>(a.packed + sizeof(TcHeader) + (size_t)wt * tile_bytes);
             uint4* dst = reinterpret_cast<uint4*>(s_w);
-            for (uint32_t i = tid; i < 2 * w_part / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+            for (uint32_t i = tid; i < tile_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
             fence_proxy_async();
             __syncthreads();
             cur_wtile = wt;
@@ -353,12 +364,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
                 }
 #pragma unroll
                 for (int d = 0; d < TC_MAX_DIM; ++d) x[d] = (valid && d < a.dim) ? x[d] - s_shift[d] : 0.f;
-                // ring slot s holds K half (s&1) of the hi (s<2) or lo (s>=2) image of [x^2 (39) | x (39) | 1 | 0]
+                // ring slot s holds K half (s&1) of the lo (s<2) or hi (s>=2) image of [x^2 (39) | x (39) | 0 0]
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     constexpr int dummy = 0; (void)dummy;
                     const int half = s & 1;
-                    const bool islo = (s >> 1) != 0;
+                    const bool islo = (s >> 1) == 0;
                     mbar_wait(a_empty + s, ((prod_cnt >> 2) & 1) ^ 1);
                     uint8_t* slot = s_a + s * slot_bytes + row_off;
 #pragma unroll
@@ -370,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
                             float v;
                             if (k < TC_MAX_DIM) v = x[k] * x[k];
                             else if (k < 2 * TC_MAX_DIM) v = x[k - TC_MAX_DIM];
-                            else v = (k == 2 * TC_MAX_DIM) ? 1.f : 0.f;
+                            else v = 0.f;
                             const float hi = tf32_round(v);
                             q[e] = islo ? (v - hi) : hi;
                         }
@@ -390,26 +401,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
                     mbar_wait(t_empty + stage, ((tile_cnt >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + stage * (uint32_t)NT;
+                    // Order: all correction products first (Al.Bh from slots 0,1; Ah.Bl from slots 2,3), the main
+                    // Ah.Bh products last.  The tensor core truncates when it aligns fp32 addends, so the fewer
+                    // accumulations happen at full magnitude the smaller the (systematic) error: 10 instead of 30.
                     uint32_t acc = 0;
-                    for (int s = 0; s < 4; ++s) {
-                        const int half = s & 1, islo = s >> 1;
-                        mbar_wait(a_full + s, (mma_cnt >> 2) & 1);
-                        tc_fence_after();
+                    const uint32_t kadv_a = 2 * (a.swap_lbo_sbo ? a_sbo : a_lbo), kadv_b = 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo);
+                    auto issue = [&](int s, uint32_t wbase) {
+                        const int half = s & 1;
                         const uint32_t sa = smem_u32(s_a + s * slot_bytes);
                         for (int j = 0; j < KH / 8; ++j) {
                             const int gk = half * (KH / 8) + j;
-                            const uint64_t ad = make_smem_desc(sa + j * 2 * (a.swap_lbo_sbo ? a_sbo : a_lbo), a_lbo, a_sbo, 0);
-                            const uint64_t bh = make_smem_desc(wh + gk * 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo), b_lbo, b_sbo, 0);
-                            umma_tf32(d_tmem, ad, bh, idesc, acc);
+                            umma_tf32(d_tmem, make_smem_desc(sa + j * kadv_a, a_lbo, a_sbo, 0),
+                                      make_smem_desc(wbase + gk * kadv_b, b_lbo, b_sbo, 0), idesc, acc);
                             acc = 1;
-                            if (!islo) {
-                                const uint64_t bl = make_smem_desc(wl + gk * 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo), b_lbo, b_sbo, 0);
-                                umma_tf32(d_tmem, ad, bl, idesc, 1u);
-                            }
                         }
-                        umma_commit(a_empty + s);       // slot free once these MMAs have read it
-                        ++mma_cnt;
+                    };
+                    for (int s = 0; s < 2; ++s) {                       // Al . Bh
+                        mbar_wait(a_full + s, (mma_cnt >> 2) & 1);
+                        tc_fence_after();
+                        issue(s, wh);
+                        umma_commit(a_empty + s);                       // lo slots are free again
                     }
+                    for (int s = 2; s < 4; ++s) {                       // Ah . Bl
+                        mbar_wait(a_full + s, (mma_cnt >> 2) & 1);
+                        tc_fence_after();
+                        issue(s, wl);
+                    }
+                    for (int s = 2; s < 4; ++s) {                       // Ah . Bh
+                        issue(s, wh);
+                        umma_commit(a_empty + s);
+                    }
+                    mma_cnt += 4;
                     umma_commit(t_full + stage);        // accumulator stage complete
                     ++tile_cnt;
                 }
@@ -431,6 +453,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
                 for (int c0 = 0; c0 < NT; c0 += 16) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += s_c[c0 + i];      // Gaussian constant + log w (base 2)
                     const int st0 = st_tile0 + c0 / a.Mp;
                     const int se = valid ? st_end : 0;
                     switch (a.Mp) {

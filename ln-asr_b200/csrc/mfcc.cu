@@ -27,203 +27,284 @@ constexpr int FRAMES_PER_RUN = 16;    // consecutive frames a warp handles befor
 
 struct MfccDev {
     int frame_len, frame_step, n_mel, n_ceps, fb_stride;
-    float hpf_alpha;
-    const float* window;
-    const float2* twiddle;
+    double hpf_alpha;
+    const double* window;
+    const double2* twiddle;
     const int* fb_start;
     const int* fb_len;
     const float* fb_weight;
-    const float* dct_t;
+    const double* dct_t;
 };
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-template <typename PcmT>
-__device__ __forceinline__ float load_pcm(const PcmT* p, int64_t i) { return (float)__ldg(p + i); }
+// compact per-stage twiddle tables of the radix-4 Stockham FFT: stage st (1..3, Ns = 4^st), factor r (1..3),
+// k < Ns  ->  W512^(r * k * 128 / Ns).  k is the fastest index, so a warp's loads are conflict-free.
+__host__ __device__ constexpr int tw_stage_off(int st) { return st == 1 ? 0 : (st == 2 ? 12 : 60); }
+constexpr int TW_STAGE_TOTAL = 252;              // 3*(4+16+64)
+constexpr int TW_SPLIT = HALF_N + 1;             // W512^k, k = 0..256, for the real-FFT split
 
-// shared memory carve-up (floats)
+// shared memory carve-up (in doubles)
 struct SmemLayout {
-    int window, twiddle, fb_w, dct, fb_meta, per_warp, total;
+    int tw_stage, tw_split, window, dct, fb_w, fb_meta, per_warp, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int frame_len, int n_mel, int fb_stride) {
+constexpr int PER_WARP_DOUBLES = 2 * 2 * HALF_N + MAX_MEL;   // two complex buffers (power aliases the 2nd), logmel[64]
+__host__ __device__ inline SmemLayout smem_layout(int frame_len, int n_mel, int fb_stride, int n_dct_cols) {
     SmemLayout L;
     int o = 0;
-    L.twiddle = o; o += 2 * FFT_N;
-    L.window = o;  o += (frame_len + 3) & ~3;
-    L.fb_w = o;    o += n_mel * fb_stride;
-    L.dct = o;     o += n_mel * n_mel;
-    L.fb_meta = o; o += 2 * MAX_MEL;
-    o = (o + 3) & ~3;
+    L.tw_stage = o; o += 2 * TW_STAGE_TOTAL;
+    L.tw_split = o; o += 2 * TW_SPLIT;
+    L.window = o;   o += (frame_len + 1) & ~1;
+    L.dct = o;      o += n_mel * n_dct_cols;             // [n][k < n_dct_cols]
+    L.fb_w = o;     o += (n_mel * fb_stride + 1) / 2;    // float weights
+    L.fb_meta = o;  o += MAX_MEL;                        // 2 * MAX_MEL ints
+    o = (o + 1) & ~1;
     L.per_warp = o;
-    // per warp: two complex buffers of 256 (1024 floats) + power[260] + logmel[64]
-    L.total = o + WARPS_PER_BLOCK * (2 * 2 * HALF_N + 260 + MAX_MEL);
+    L.total = o + WARPS_PER_BLOCK * PER_WARP_DOUBLES;
     return L;
 }
 
+// where a frame lives: utterance, its sample range, first sample of the frame
+struct FrameCtx {
+    int u;
+    int64_t u_f1;        // first frame of the next utterance
+    int64_t u_s0;        // first sample of the utterance in pcm
+    int64_t u_len;       // samples in the utterance
+    int64_t s_start;     // first sample of the frame, relative to the utterance
+};
+
+// The whole per-frame chain runs in float64.  The reference is float64 (mfcc.py), and the features are small
+// differences of ~200 dB log-mel values (mean normalisation, deltas) whose low-energy bands sit up to 90 dB below
+// the frame's peak: an fp32 FFT leaves ~1e-4 relative error in exactly those bands (measured), i.e. above the
+// 1e-4 parity bar after the DCT and the delta-deltas.  On B200 fp64 runs at half the fp32 rate and the kernel is
+// latency-, not ALU-bound, so exactness costs little.
 template <typename PcmT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sample_off,
                    const int64_t* __restrict__ frame_off, int n_utt, int64_t total_frames, MfccDev P,
                    float* __restrict__ raw, double* __restrict__ colsum, float* __restrict__ power_out,
                    float* __restrict__ ceps_raw_out) {
-    extern __shared__ __align__(16) float smem[];
-    const SmemLayout L = smem_layout(P.frame_len, P.n_mel, P.fb_stride);
-    float2* s_tw = (float2*)(smem + L.twiddle);
-    float* s_win = smem + L.window;
-    float* s_fbw = smem + L.fb_w;
-    float* s_dct = smem + L.dct;
-    int* s_fbs = (int*)(smem + L.fb_meta);
+    extern __shared__ __align__(16) double smem[];
+    const bool full_ceps = (ceps_raw_out != nullptr);
+    const int n_out = full_ceps ? P.n_mel : (P.n_ceps + 1);   // cepstral coefficients 0..n_out-1 computed
+    const SmemLayout L = smem_layout(P.frame_len, P.n_mel, P.fb_stride, n_out);
+    double2* s_tws = reinterpret_cast<double2*>(smem + L.tw_stage);
+    double2* s_twr = reinterpret_cast<double2*>(smem + L.tw_split);
+    double* s_win = smem + L.window;
+    double* s_dct = smem + L.dct;
+    float* s_fbw = reinterpret_cast<float*>(smem + L.fb_w);
+    int* s_fbs = reinterpret_cast<int*>(smem + L.fb_meta);
     int* s_fbl = s_fbs + MAX_MEL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < FFT_N; i += blockDim.x) s_tw[i] = P.twiddle[i];
+    for (int i = tid; i < TW_STAGE_TOTAL; i += blockDim.x) {
+        const int st = i < 12 ? 1 : (i < 60 ? 2 : 3);
+        const int Ns = 1 << (2 * st);
+        const int rel = i - tw_stage_off(st);
+        const int r = rel / Ns + 1, k = rel % Ns;
+        s_tws[i] = P.twiddle[r * k * (128 >> (2 * st))];
+    }
+    for (int i = tid; i < TW_SPLIT; i += blockDim.x) s_twr[i] = P.twiddle[i & (FFT_N - 1)];
     for (int i = tid; i < P.frame_len; i += blockDim.x) s_win[i] = P.window[i];
     for (int i = tid; i < P.n_mel * P.fb_stride; i += blockDim.x) s_fbw[i] = P.fb_weight[i];
-    for (int i = tid; i < P.n_mel * P.n_mel; i += blockDim.x) s_dct[i] = P.dct_t[i];
+    for (int i = tid; i < P.n_mel * n_out; i += blockDim.x) {
+        const int n = i / n_out, k = i - n * n_out;
+        s_dct[i] = P.dct_t[n * P.n_mel + k];
+    }
     for (int i = tid; i < P.n_mel; i += blockDim.x) { s_fbs[i] = P.fb_start[i]; s_fbl[i] = P.fb_len[i]; }
     __syncthreads();
 
-    float* wbase = smem + L.per_warp + warp * (2 * 2 * HALF_N + 260 + MAX_MEL);
-    float2* bufA = (float2*)wbase;
-    float2* bufB = bufA + HALF_N;
-    float* s_pow = wbase + 4 * HALF_N;
-    float* s_lm = s_pow + 260;
+    double* wbase = smem + L.per_warp + warp * PER_WARP_DOUBLES;
+    double2* bufA = reinterpret_cast<double2*>(wbase);
+    double2* bufB = bufA + HALF_N;
+    double* s_pow = reinterpret_cast<double*>(bufB);     // the spectrum ends in bufA; bufB is free for the power
+    double* s_lm = wbase + 4 * HALF_N;
 
-    const bool full_ceps = (ceps_raw_out != nullptr);
-    const int n_out = full_ceps ? P.n_mel : (P.n_ceps + 1);   // cepstral coefficients 0..n_out-1 computed
     const int64_t n_runs = (total_frames + FRAMES_PER_RUN - 1) / FRAMES_PER_RUN;
     const int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+    constexpr int NQ = HALF_N / 32;                      // sample pairs per lane
+
+    auto make_ctx = [&](int u, int64_t f) {
+        FrameCtx c;
+        c.u = u;
+        c.u_f1 = __ldg(frame_off + u + 1);
+        c.u_s0 = __ldg(sample_off + u);
+        c.u_len = __ldg(sample_off + u + 1) - c.u_s0;
+        c.s_start = (f - __ldg(frame_off + u)) * P.frame_step;
+        return c;
+    };
+    auto next_ctx = [&](const FrameCtx& c, int64_t f) {          // context of frame f = previous frame + 1
+        if (f < c.u_f1) { FrameCtx n = c; n.s_start += P.frame_step; return n; }
+        int u = c.u;
+        int64_t f1 = c.u_f1;
+        while (f >= f1) { ++u; f1 = __ldg(frame_off + u + 1); }
+        return make_ctx(u, f);
+    };
+    // raw samples of one frame: lane holds pairs (x[2m], x[2m+1]), m = lane + 32 q; out-of-range samples read as 0
+    auto fetch = [&](const FrameCtx& c, float* xe, float* xo, float& xlead) {
+        const PcmT* x = pcm + c.u_s0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int n0 = 2 * (lane + 32 * q);
+            const int64_t i0 = c.s_start + n0;
+            xe[q] = (n0 < P.frame_len && i0 < c.u_len) ? (float)__ldg(x + i0) : 0.f;
+            xo[q] = (n0 + 1 < P.frame_len && i0 + 1 < c.u_len) ? (float)__ldg(x + i0 + 1) : 0.f;
+        }
+        // the sample before the frame (needed by lane 0, q = 0)
+        xlead = (lane == 0 && c.s_start >= 1 && c.s_start - 1 < c.u_len) ? (float)__ldg(x + c.s_start - 1) : 0.f;
+    };
 
     for (int64_t run = warp_global; run < n_runs; run += warp_stride) {
         const int64_t f_begin = run * FRAMES_PER_RUN;
         const int64_t f_end = min(f_begin + (int64_t)FRAMES_PER_RUN, total_frames);
-        int u = find_utt(frame_off, n_utt, f_begin);
-        int64_t u_f0 = __ldg(frame_off + u), u_f1 = __ldg(frame_off + u + 1);
-        int64_t u_s0 = __ldg(sample_off + u), u_len = __ldg(sample_off + u + 1) - u_s0;
-        double acc0 = 0.0, acc1 = 0.0;    // running column sums of this utterance: lane k and k+32
+        FrameCtx nxt = make_ctx(find_utt(frame_off, n_utt, f_begin), f_begin);
+        float pe[NQ], po[NQ], plead;
+        fetch(nxt, pe, po, plead);
+        int acc_u = nxt.u;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};   // running column sums of utterance acc_u: coefficient (lane & 15) + 16 i
         for (int64_t f = f_begin; f < f_end; ++f) {
-            if (f >= u_f1) {              // crossed into the next utterance: flush sums
-                if (lane < n_out) atomicAdd(colsum + (int64_t)u * MAX_MEL + lane, acc0);
-                if (lane + 32 < n_out) atomicAdd(colsum + (int64_t)u * MAX_MEL + lane + 32, acc1);
-                acc0 = acc1 = 0.0;
-                while (f >= u_f1) { ++u; u_f1 = __ldg(frame_off + u + 1); }
-                u_f0 = __ldg(frame_off + u);
-                u_s0 = __ldg(sample_off + u);
-                u_len = __ldg(sample_off + u + 1) - u_s0;
-            }
-            const int64_t s_start = (f - u_f0) * P.frame_step;   // first sample of the frame inside the utterance
-            const PcmT* x = pcm + u_s0;
-            // ---- load + pre-emphasis + window, packed as z[m] = (xw[2m], xw[2m+1])
+            const FrameCtx cur = nxt;
+            float xe[NQ], xo[NQ];
 #pragma unroll
-            for (int q = 0; q < HALF_N / 32; ++q) {
+            for (int q = 0; q < NQ; ++q) { xe[q] = pe[q]; xo[q] = po[q]; }
+            const float xlead = plead;
+            if (f + 1 < f_end) {                      // software prefetch of the next frame's samples
+                nxt = next_ctx(cur, f + 1);
+                fetch(nxt, pe, po, plead);
+            }
+            if (cur.u != acc_u) {                     // crossed into another utterance: flush its column sums
+                if (lane < 16) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (lane + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + lane + 16 * i, acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = 0.0;
+                acc_u = cur.u;
+            }
+            // ---- pre-emphasis (mfcc.py:63) + window (mfcc.py:138), packed as z[m] = (xw[2m], xw[2m+1])
+            float carry = xlead;                      // x[2m - 1] for lane 0
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
                 const int m = lane + 32 * q;
-                float2 z = make_float2(0.f, 0.f);
                 const int n0 = 2 * m;
+                float xm1 = __shfl_up_sync(0xffffffffu, xo[q], 1);
+                if (lane == 0) xm1 = carry;
+                carry = __shfl_sync(0xffffffffu, xo[q], 31);
+                double2 z = make_double2(0.0, 0.0);
                 if (n0 < P.frame_len) {
-                    const int64_t i0 = s_start + n0;
-                    float xm1 = (i0 >= 1 && i0 - 1 < u_len) ? load_pcm(x, i0 - 1) : 0.f;
-                    float x0 = (i0 < u_len) ? load_pcm(x, i0) : 0.f;
-                    float x1 = (i0 + 1 < u_len) ? load_pcm(x, i0 + 1) : 0.f;
+                    const int64_t i0 = cur.s_start + n0;
                     // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
-                    float y0 = (i0 < u_len) ? ((i0 == 0) ? x0 : fmaf(-P.hpf_alpha, xm1, x0)) : 0.f;
-                    float y1 = (i0 + 1 < u_len) ? fmaf(-P.hpf_alpha, x0, x1) : 0.f;
+                    const double y0 = (i0 < cur.u_len) ? ((i0 == 0) ? (double)xe[q] : (double)xe[q] - P.hpf_alpha * (double)xm1) : 0.0;
+                    const double y1 = (i0 + 1 < cur.u_len) ? (double)xo[q] - P.hpf_alpha * (double)xe[q] : 0.0;
                     z.x = y0 * s_win[n0];
-                    z.y = (n0 + 1 < P.frame_len) ? y1 * s_win[n0 + 1] : 0.f;
+                    z.y = (n0 + 1 < P.frame_len) ? y1 * s_win[n0 + 1] : 0.0;
                 }
                 bufA[m] = z;
             }
             __syncwarp();
             // ---- 256-point complex FFT, radix-4 Stockham, 4 stages
-            float2* src = bufA;
-            float2* dst = bufB;
+            double2* src = bufA;
+            double2* dst = bufB;
 #pragma unroll
             for (int st = 0; st < 4; ++st) {
                 const int Ns = 1 << (2 * st);
-                const int tw_scale = 128 >> (2 * st);            // 512 / (4 Ns)
+                const double2* tw = s_tws + tw_stage_off(st);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int j = lane + 32 * h;
                     const int k = j & (Ns - 1);
-                    float2 v0 = src[j], v1 = src[j + 64], v2 = src[j + 128], v3 = src[j + 192];
+                    double2 v0 = src[j], v1 = src[j + 64], v2 = src[j + 128], v3 = src[j + 192];
                     if (st > 0) {
-                        v1 = cmul(v1, s_tw[k * tw_scale]);
-                        v2 = cmul(v2, s_tw[2 * k * tw_scale]);
-                        v3 = cmul(v3, s_tw[3 * k * tw_scale]);
+                        v1 = cmul(v1, tw[k]);
+                        v2 = cmul(v2, tw[Ns + k]);
+                        v3 = cmul(v3, tw[2 * Ns + k]);
                     }
-                    float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-                    float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-                    float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-                    float2 a3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));   // (v1-v3) * (-i)
+                    const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y);
+                    const double2 a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
+                    const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y);
+                    const double2 a3 = make_double2(v1.y - v3.y, -(v1.x - v3.x));   // (v1-v3) * (-i)
                     const int j0 = ((j - k) << 2) + k;
-                    dst[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                    dst[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                    dst[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                    dst[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                    dst[j0] = make_double2(a0.x + a2.x, a0.y + a2.y);
+                    dst[j0 + Ns] = make_double2(a1.x + a3.x, a1.y + a3.y);
+                    dst[j0 + 2 * Ns] = make_double2(a0.x - a2.x, a0.y - a2.y);
+                    dst[j0 + 3 * Ns] = make_double2(a1.x - a3.x, a1.y - a3.y);
                 }
                 __syncwarp();
-                float2* t = src; src = dst; dst = t;
+                double2* t = src; src = dst; dst = t;
             }
             // after 4 stages the spectrum Z is in `src` (== bufA)
-            // ---- real-FFT split + power spectrum |X|^2 / 512
-            float esum = 0.f;
+            // ---- real-FFT split + power spectrum |X|^2 / 512   (mfcc.py:141-142)
+            double esum = 0.0;
 #pragma unroll
-            for (int q = 0; q <= HALF_N / 32; ++q) {
+            for (int q = 0; q <= NQ; ++q) {
                 const int k = lane + 32 * q;
                 if (k <= HALF_N) {
-                    const float2 zk = src[k & (HALF_N - 1)];
-                    const float2 zr = src[(HALF_N - k) & (HALF_N - 1)];
-                    const float2 E = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));
-                    const float2 O = make_float2(0.5f * (zk.y + zr.y), -0.5f * (zk.x - zr.x));  // -(i/2)(zk - conj zr)
-                    const float2 X = make_float2(E.x, E.y);
-                    const float2 wo = cmul(s_tw[k], O);
-                    const float re = X.x + wo.x, im = X.y + wo.y;
-                    const float pw = (re * re + im * im) * (1.0f / FFT_N);
+                    const double2 zk = src[k & (HALF_N - 1)];
+                    const double2 zr = src[(HALF_N - k) & (HALF_N - 1)];
+                    const double2 E = make_double2(0.5 * (zk.x + zr.x), 0.5 * (zk.y - zr.y));
+                    const double2 O = make_double2(0.5 * (zk.y + zr.y), -0.5 * (zk.x - zr.x));  // -(i/2)(zk - conj zr)
+                    const double2 wo = cmul(s_twr[k], O);
+                    const double re = E.x + wo.x, im = E.y + wo.y;
+                    const double pw = (re * re + im * im) * (1.0 / FFT_N);
                     s_pow[k] = pw;
                     esum += pw;
-                    if (power_out) power_out[f * (HALF_N + 1) + k] = pw;
+                    if (power_out) power_out[f * (HALF_N + 1) + k] = (float)pw;
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
             __syncwarp();
-            // ---- mel filter bank (banded), eps substitution, 20 log10
-            for (int m = lane; m < P.n_mel; m += 32) {
-                const int s = s_fbs[m], len = s_fbl[m];
-                const float* w = s_fbw + m * P.fb_stride;
-                float e = 0.f;
-                for (int i = 0; i < len; ++i) e = fmaf(w[i], s_pow[s + i], e);
-                if (e == 0.f) e = 2.220446049250313e-16f;          // np.finfo(float).eps, mfcc.py:149
-                s_lm[m] = 8.685889638065035f * logf(e);            // 20 log10(e) = 20/ln(10) * ln(e)
-            }
-            __syncwarp();
-            // ---- DCT-II ortho: lane k computes coefficient k (and k+32)
-            float c0 = 0.f, c1 = 0.f;
+            // ---- mel filter bank (banded, mfcc.py:148): 4 lanes share a filter, eps substitution (mfcc.py:149),
+            //      20 log10 (mfcc.py:150) spread over the lanes
             {
-                const int k0 = lane, k1 = lane + 32;
-                const bool do1 = k1 < n_out;
-                if (k0 < n_out) {
-                    for (int n = 0; n < P.n_mel; ++n) {
-                        const float lm = s_lm[n];
-                        c0 = fmaf(s_dct[n * P.n_mel + k0], lm, c0);
-                        if (do1) c1 = fmaf(s_dct[n * P.n_mel + k1], lm, c1);
+                const int grp = lane >> 2, sub = lane & 3;
+                const unsigned gmask = 0xFu << (lane & ~3);          // trip counts differ between groups when n_mel % 8 != 0
+                for (int i = 0; grp + 8 * i < P.n_mel; ++i) {
+                    const int m = grp + 8 * i;
+                    const int s = s_fbs[m], len = s_fbl[m];
+                    const float* w = s_fbw + m * P.fb_stride;
+                    double e = 0.0;
+                    for (int t = sub; t < len; t += 4) e = fma((double)w[t], s_pow[s + t], e);
+                    e += __shfl_xor_sync(gmask, e, 1);
+                    e += __shfl_xor_sync(gmask, e, 2);
+                    if (sub == (i & 3)) {
+                        if (e == 0.0) e = 2.220446049250313e-16;          // np.finfo(float).eps
+                        s_lm[m] = 8.685889638065035 * log(e);             // 20 log10(e) = 20/ln(10) * ln(e)
                     }
                 }
             }
-            acc0 += (double)c0;
-            acc1 += (double)c1;
-            // raw static row: cepstra 1..n_ceps then ln(sum power)
-            if (lane >= 1 && lane <= P.n_ceps) raw[f * RAW_LD + (lane - 1)] = c0;
-            if (lane == 0) raw[f * RAW_LD + P.n_ceps] = logf(esum);
-            if (full_ceps) {
-                if (lane < P.n_mel) ceps_raw_out[f * P.n_mel + lane] = c0;
-                if (lane + 32 < P.n_mel) ceps_raw_out[f * P.n_mel + lane + 32] = c1;
+            __syncwarp();
+            // ---- DCT-II ortho (mfcc.py:152): lane = (half of n, coefficient k mod 16)
+            {
+                const int kk = lane & 15, part = lane >> 4;
+                const int nh = (P.n_mel + 1) >> 1;
+                const int n_lo = part * nh, n_hi = min(P.n_mel, n_lo + nh);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = kk + 16 * i;
+                    double c = 0.0;
+                    if (k < n_out)
+                        for (int n = n_lo; n < n_hi; ++n) c = fma(s_dct[n * n_out + k], s_lm[n], c);
+                    c += __shfl_xor_sync(0xffffffffu, c, 16);
+                    if (k < n_out && part == 0) {
+                        acc[i] += c;
+                        // raw static row: cepstra 1..n_ceps then ln(sum power) (mfcc.py:158-160)
+                        if (k >= 1 && k <= P.n_ceps) raw[f * RAW_LD + (k - 1)] = (float)c;
+                        if (full_ceps) ceps_raw_out[f * P.n_mel + k] = (float)c;
+                    }
+                }
             }
+            if (lane == 31) raw[f * RAW_LD + P.n_ceps] = (float)log(esum);
             __syncwarp();
         }
-        if (lane < n_out) atomicAdd(colsum + (int64_t)u * MAX_MEL + lane, acc0);
-        if (lane + 32 < n_out) atomicAdd(colsum + (int64_t)u * MAX_MEL + lane + 32, acc1);
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (lane + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + lane + 16 * i, acc[i]);
+        }
     }
 }
 
@@ -357,13 +438,14 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     MfccDev P;
     P.frame_len = tb->frame_len; P.frame_step = tb->frame_step; P.n_mel = tb->n_mel; P.n_ceps = tb->n_ceps;
     P.fb_stride = tb->fb_stride; P.hpf_alpha = tb->hpf_alpha; P.window = tb->window;
-    P.twiddle = (const float2*)tb->twiddle; P.fb_start = tb->fb_start; P.fb_len = tb->fb_len;
+    P.twiddle = (const double2*)tb->twiddle; P.fb_start = tb->fb_start; P.fb_len = tb->fb_len;
     P.fb_weight = tb->fb_weight; P.dct_t = tb->dct_t;
 
-    const SmemLayout L = smem_layout(P.frame_len, P.n_mel, P.fb_stride);
-    const size_t smem = (size_t)L.total * sizeof(float);
+    const SmemLayout L = smem_layout(P.frame_len, P.n_mel, P.fb_stride, ceps_out ? P.n_mel : P.n_ceps + 1);
+    const size_t smem = (size_t)L.total * sizeof(double);
     const int64_t n_runs = ceil_div(total_frames, FRAMES_PER_RUN);
-    int grid = (int)std::min<int64_t>(ceil_div(n_runs, WARPS_PER_BLOCK), (int64_t)sm_count() * 3);
+    const int blocks_per_sm = std::max(1, (int)((220 * 1024) / smem));
+    int grid = (int)std::min<int64_t>(ceil_div(n_runs, WARPS_PER_BLOCK), (int64_t)sm_count() * blocks_per_sm);
     if (grid < 1) grid = 1;
     if (pcm_dtype == LNASR_DT_I16) {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

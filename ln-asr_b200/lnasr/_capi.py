@@ -26,7 +26,7 @@ class MfccTables(C.Structure):
     """lnasr_mfcc_tables (include/lnasr_b200.h)."""
     _fields_ = [
         ("frame_len", i32), ("frame_step", i32), ("fft_n", i32), ("n_mel", i32), ("n_ceps", i32),
-        ("hpf_alpha", C.c_float), ("fb_stride", i32),
+        ("hpf_alpha", C.c_double), ("fb_stride", i32),
         ("window", vp), ("twiddle", vp), ("fb_start", vp), ("fb_len", vp), ("fb_weight", vp), ("dct_t", vp),
     ]
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "lnasr_mfcc_num_frames": (i64, [i64, i32, i32]),
     "lnasr_mfcc_workspace_bytes": (C.c_int, [i64, i32, C.POINTER(sz)]),
     "lnasr_mfcc_batch": (C.c_int, [vp, C.c_int, vp, vp, i32, i64, C.POINTER(MfccTables), vp, i32, vp, vp, vp, sz, vp]),
+    "lnasr_gmm_exact_packed_doubles": (i64, [i32, i32, i32]),
     "lnasr_gmm_pack_exact": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp]),
     "lnasr_gmm_loglik_exact": (C.c_int, [vp, C.c_int, i32, i64, vp, i32, i32, i32, vp, C.c_int, i64, vp, vp]),
     "lnasr_gmm_loglik_full": (C.c_int, [vp, C.c_int, i32, i64, vp, vp, vp, vp, i32, i32, i32, vp, C.c_int, i64, vp, vp]),

@@ -53,7 +53,7 @@ class PackedGmm:
         ng = self.n_states * self.n_mix
         if not self.full:
             self.var_d = _dev.to_dev(np.ascontiguousarray(var), t.float64)
-            self.packed = _dev.empty((ng, 2 * self.dim + 2), t.float64)
+            self.packed = _dev.empty((int(lib.lnasr_gmm_exact_packed_doubles(self.n_states, self.n_mix, self.dim)),), t.float64)
             _capi.check(lib.lnasr_gmm_pack_exact(_capi.ptr(self.logw_d), _capi.ptr(self.mu_d), _capi.ptr(self.var_d),
                                                  self.n_states, self.n_mix, self.dim, _capi.ptr(self.packed),
                                                  _capi.stream_ptr()), "gmm_pack_exact")

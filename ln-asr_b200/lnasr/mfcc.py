@@ -100,12 +100,12 @@ class MFCC:
         dct = 2.0 * np.cos(np.pi * k * (2 * n + 1) / (2 * Nm)) * np.sqrt(1.0 / (2 * Nm))
         dct[0] *= np.sqrt(0.5)
         keep = {
-            "window": _dev.to_dev(window, t.float32),
-            "twiddle": _dev.to_dev(twiddle, t.float32),
+            "window": _dev.to_dev(window, t.float64),
+            "twiddle": _dev.to_dev(twiddle, t.float64),
             "fb_start": _dev.to_dev(start.astype(np.int32), t.int32),
             "fb_len": _dev.to_dev(length.astype(np.int32), t.int32),
             "fb_weight": _dev.to_dev(weights, t.float32),
-            "dct_t": _dev.to_dev(dct.T, t.float32),
+            "dct_t": _dev.to_dev(dct.T, t.float64),
         }
         tb = _capi.MfccTables(
             frame_len=self.frame_L, frame_step=self.frame_step, fft_n=self.fft_N, n_mel=self.mfbank_num,

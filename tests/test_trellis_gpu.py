@@ -80,7 +80,7 @@ def test_trellis_batch_against_oracle(n, ltr):
     bs = [-5.0 * rng.random((n, T)) - 0.5 for T in lens]
     bs[3][rng.integers(0, n), 4] = -np.inf
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    b_cat = np.concatenate([b.T for b in bs], axis=0)
+    b_cat = np.ascontiguousarray(np.concatenate([b.T for b in bs], axis=0))
     bank = TransitionBank(A, pi)
     b_d = torch.from_numpy(np.ascontiguousarray(b_cat)).cuda()
     off_d = torch.from_numpy(off).cuda()
