@@ -202,7 +202,6 @@ def run_ours(args):
     n_utt = cfg["n_utt"]
     pcm_host = torch.from_numpy(pcm_np).pin_memory()
     pcm_dev = pcm_host.cuda()
-    pcm_stage = torch.empty_like(pcm_dev)
     want_paths = True
 
     def step_device():
@@ -210,11 +209,8 @@ def run_ours(args):
         return res, mb
 
     def step_e2e():
-        pcm_stage.copy_(pcm_host, non_blocking=True)
-        res, mb = pipe.recognize_batch(pcm_stage, off, want_paths=want_paths)
-        words = res.words.cpu()
-        best = res.best.cpu()
-        return words, best
+        # public host-facing API: pinned PCM in, decoded words + scores out; the H2D copy is chunked and overlapped
+        return pipe.recognize_batch_host(pcm_host, off, n_chunks=args.e2e_chunks, want_paths=want_paths)
 
     def barrier():
         if world > 1:
@@ -311,7 +307,8 @@ def stage_times(pipe, pcm_dev, off, want_paths, reps=5):
     from lnasr import _capi, _dev
     t = torch
     acc = {"mfcc": 0.0, "gmm": 0.0, "viterbi": 0.0}
-    for rep in range(reps + 1):
+    warm = 3                       # the caching allocator settles (no cudaMalloc inside a timed stage)
+    for rep in range(reps + warm):
         ev = [t.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         mb = pipe.mfcc.calc_mfcc_batch(pcm_dev, sample_offsets=off)
@@ -322,7 +319,8 @@ def stage_times(pipe, pcm_dev, off, want_paths, reps=5):
         r = pipe.bank.trans.viterbi(b, mb.frame_offsets, n_utt, total, want_path=want_paths, want_score=True)
         ev[3].record()
         t.cuda.synchronize()
-        if rep == 0:
+        del mb, b, r
+        if rep < warm:
             continue
         acc["mfcc"] += ev[0].elapsed_time(ev[1])
         acc["gmm"] += ev[1].elapsed_time(ev[2])
@@ -368,6 +366,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance groups the host->device copy is pipelined over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

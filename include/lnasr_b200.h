@@ -126,9 +126,12 @@ int lnasr_gmm_loglik_full(const void* feats, int feats_dtype, int32_t ld_feats, 
 int lnasr_gmm_tc_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes /*host out*/);
 int lnasr_gmm_pack_tc(const double* logw, const double* mu, const double* var, int32_t n_states, int32_t n_mix,
                       int32_t dim, const double* shift /*[dim] device, or NULL*/, void* packed, void* stream);
-/* feats [n_frames, ld_feats] float32 (ld_feats % 4 == 0 and >= 40 enables 16-byte loads); b_out [n_frames, ld_b] float32 */
+/* feats [n_frames, ld_feats] float32; b_out [n_frames, ld_b] float32; workspace: lnasr_gmm_tc_workspace_bytes(n_frames)
+ * bytes for the tile-transposed, centred copy of the features the main kernel streams */
+int lnasr_gmm_tc_workspace_bytes(int64_t n_frames, size_t* bytes /*host out*/);
 int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed,
-                        int32_t n_states, int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b, void* stream);
+                        int32_t n_states, int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* discrete emissions: HMM._map_b (lnasr/hmm.py:47-61): b[t, j] = B[j, obs[t]] */
 int lnasr_emit_gather(const double* logB /*[n_states, n_symbols]*/, const int32_t* obs /*[n_frames]*/,

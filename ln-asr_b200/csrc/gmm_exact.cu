@@ -60,6 +60,16 @@ __device__ __forceinline__ void lse_push(double v, double& mx, double& sum) {
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Block = 4 state groups x 128 threads sharing one x tile of 256 frames; thread = 2 frames x 4 Gaussians.
+// The parameters of the 4 states being scored (one chunk of 4 mixtures each) are staged in shared memory with
+// cp.async, double buffered, so the inner loop reads them as conflict-free broadcasts instead of waiting on L2.
 template <typename FeatT, typename OutT>
 __global__ void __launch_bounds__(GX_THREADS * GX_SGROUPS, 2)
 gmm_loglik_exact_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_frames,
@@ -68,31 +78,50 @@ gmm_loglik_exact_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n
     // x tile transposed: xs[d][frame] -> conflict-free column reads
     extern __shared__ __align__(16) unsigned char gx_smem[];
     double (*xs)[GX_TILE] = reinterpret_cast<double (*)[GX_TILE]>(gx_smem);
+    const int chunk_doubles = (dim + 1) * 8;
+    double* pbuf = reinterpret_cast<double*>(gx_smem) + (size_t)dim * GX_TILE;      // [2][GX_SGROUPS][chunk_doubles]
     const int tid = threadIdx.x & (GX_THREADS - 1);            // frame lane inside the state group
-    const int sgroup = threadIdx.x / GX_THREADS;              // states j = j_begin + sgroup, + GX_SGROUPS, ...
+    const int sgroup = threadIdx.x / GX_THREADS;              // scores state j_begin + 4*jg + sgroup
     const int64_t t0 = (int64_t)blockIdx.x * GX_TILE;
     const int rows = (int)min((int64_t)GX_TILE, n_frames - t0);
+    const int nch = gx_chunks(n_mix);
+    const int j_begin = blockIdx.y * states_per_block;
+    const int j_end = min(n_states, j_begin + states_per_block);
+    const int n_units = ((j_end - j_begin + GX_SGROUPS - 1) / GX_SGROUPS) * nch;
+    auto issue = [&](int u) {
+        const int jg = u / nch, ch = u - jg * nch;
+        double* dst = pbuf + (size_t)(u & 1) * GX_SGROUPS * chunk_doubles;
+        const int pieces = chunk_doubles / 2;                  // 16-byte pieces per chunk
+        for (int pidx = threadIdx.x; pidx < GX_SGROUPS * pieces; pidx += GX_THREADS * GX_SGROUPS) {
+            const int sg = pidx / pieces, off = pidx - sg * pieces;
+            const int j = j_begin + jg * GX_SGROUPS + sg;
+            if (j < j_end) cp_async16(dst + (size_t)sg * chunk_doubles + off * 2, packed + (int64_t)(j * nch + ch) * chunk_doubles + off * 2);
+        }
+        cp_async_commit();
+    };
+    if (n_units > 0) issue(0);
     for (int i = threadIdx.x; i < GX_TILE * dim; i += GX_THREADS * GX_SGROUPS) {
         const int r = i / dim, d = i - r * dim;
         xs[d][r] = (r < rows) ? (double)feats[(t0 + r) * ld_feats + d] : 0.0;
     }
-    __syncthreads();
     const int64_t tA = t0 + tid, tB = t0 + tid + GX_THREADS;
     const bool okA = tA < n_frames, okB = tB < n_frames;
-    const int nch = gx_chunks(n_mix);
-    const int j_begin = blockIdx.y * states_per_block;
-    const int j_end = min(n_states, j_begin + states_per_block);
     const int64_t n_gauss = (int64_t)n_states * n_mix;
-    for (int j = j_begin + sgroup; j < j_end; j += GX_SGROUPS) {
-        double mxA = neg_inf(), sumA = 0.0, mxB = neg_inf(), sumB = 0.0;
-        for (int ch = 0; ch < nch; ++ch) {
-            const double2* p = reinterpret_cast<const double2*>(packed + (int64_t)(j * nch + ch) * (dim + 1) * 8);
+    double mxA = neg_inf(), sumA = 0.0, mxB = neg_inf(), sumB = 0.0;
+    for (int u = 0; u < n_units; ++u) {
+        if (u + 1 < n_units) { issue(u + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                                       // unit u's parameters (and, first time, the x tile) are visible
+        const int jg = u / nch, ch = u - jg * nch;
+        const int j = j_begin + jg * GX_SGROUPS + sgroup;
+        if (j < j_end) {
+            const double2* p = reinterpret_cast<const double2*>(pbuf + ((size_t)(u & 1) * GX_SGROUPS + sgroup) * chunk_doubles);
+            if (ch == 0) { mxA = neg_inf(); sumA = 0.0; mxB = neg_inf(); sumB = 0.0; }
             double qA[4] = {0.0, 0.0, 0.0, 0.0}, qB[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 3
             for (int d = 0; d < dim; ++d) {
                 const double xA = xs[d][tid], xB = xs[d][tid + GX_THREADS];
-                const double2 a01 = __ldg(p + d * 4), a23 = __ldg(p + d * 4 + 1);
-                const double2 b01 = __ldg(p + d * 4 + 2), b23 = __ldg(p + d * 4 + 3);
+                const double2 a01 = p[d * 4], a23 = p[d * 4 + 1];
+                const double2 b01 = p[d * 4 + 2], b23 = p[d * 4 + 3];
                 qA[0] = fma(fma(a01.x, xA, b01.x), xA, qA[0]);
                 qA[1] = fma(fma(a01.y, xA, b01.y), xA, qA[1]);
                 qA[2] = fma(fma(a23.x, xA, b23.x), xA, qA[2]);
@@ -102,8 +131,8 @@ gmm_loglik_exact_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n
                 qB[2] = fma(fma(a23.x, xB, b23.x), xB, qB[2]);
                 qB[3] = fma(fma(a23.y, xB, b23.y), xB, qB[3]);
             }
-            const double2 c01 = __ldg(p + dim * 4), c23 = __ldg(p + dim * 4 + 1);
-            const double2 w01 = __ldg(p + dim * 4 + 2), w23 = __ldg(p + dim * 4 + 3);
+            const double2 c01 = p[dim * 4], c23 = p[dim * 4 + 1];
+            const double2 w01 = p[dim * 4 + 2], w23 = p[dim * 4 + 3];
             const double c[4] = {c01.x, c01.y, c23.x, c23.y}, lw[4] = {w01.x, w01.y, w23.x, w23.y};
             double vA[4], vB[4];
 #pragma unroll
@@ -130,9 +159,12 @@ gmm_loglik_exact_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n
                 sumB += (exp(vB[0] - nB) + exp(vB[1] - nB)) + (exp(vB[2] - nB) + exp(vB[3] - nB));
                 mxB = nB;
             }
+            if (ch == nch - 1) {
+                if (okA) b_out[tA * ld_b + j] = (OutT)((mxA == neg_inf()) ? mxA : mxA + log(sumA));
+                if (okB) b_out[tB * ld_b + j] = (OutT)((mxB == neg_inf()) ? mxB : mxB + log(sumB));
+            }
         }
-        if (okA) b_out[tA * ld_b + j] = (OutT)((mxA == neg_inf()) ? mxA : mxA + log(sumA));
-        if (okB) b_out[tB * ld_b + j] = (OutT)((mxB == neg_inf()) ? mxB : mxB + log(sumB));
+        __syncthreads();                                       // buffer u&1 is refilled by issue(u+2)
     }
 }
 
@@ -216,7 +248,7 @@ static int launch_exact(const void* feats, int ld_feats, int64_t n_frames, const
     const int spb = (int)ceil_div(n_states, y);
     y = (int)ceil_div(n_states, spb);
     dim3 grid((unsigned)tiles, (unsigned)y);
-    const size_t smem = (size_t)dim * GX_TILE * sizeof(double);
+    const size_t smem = ((size_t)dim * GX_TILE + (size_t)2 * GX_SGROUPS * (dim + 1) * 8) * sizeof(double);
     if (smem > 48 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(gmm_loglik_exact_kernel<FeatT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_loglik_exact_kernel<FeatT, OutT><<<grid, GX_THREADS * GX_SGROUPS, smem, stream>>>(

@@ -14,16 +14,17 @@
 // (= one frame) all mixtures of a state and the reduction needs no shuffles.  Weights are pre-scaled by
 // log2(e) so the epilogue is max / ex2 / lg2.
 //
-// CTA = 9 warps, one CTA per SM, each owning one W tile (NT <= 224 accumulator columns, resident in shared
+// CTA = 17 warps, one CTA per SM, each owning one W tile (NT <= 224 accumulator columns, resident in shared
 // memory for the whole pass) and streaming 128-frame tiles:
-//   warps 4-7  producers : thread = frame row; reads the 39 features, forms [x^2|x|1], splits hi/lo and writes
-//                          the UMMA canonical K-major (no-swizzle) layout straight into a 4-slot ring
-//                          (slot = half of K of the hi or lo image), fence.proxy.async, mbarrier arrive;
-//   warp 8     MMA       : one thread issues 30 tcgen05.mma (M=128, N=NT, K=8) per tile, tcgen05.commit frees
-//                          ring slots and publishes the accumulator stage (2 TMEM stages of NT columns);
-//   warps 0-3  epilogue  : tcgen05.ld 32x32b.x16, LSE over mixtures, b[frame, state] fp32 stores.
-// No tensor maps are needed: A never exists in global memory (156 B/frame are read instead of 640 B) and W
-// is a linear copy of a pre-packed image.
+//   warps 8-11  lo producers : thread = frame row; reads its 39 (centred) features from the tile-transposed staging
+//   warps 12-15 hi producers   copy (coalesced), forms [x^2|x|1], splits hi/lo and writes the UMMA canonical K-major
+//                              (no-swizzle) layout straight into a 4-slot ring (slot = half of K of the lo or hi
+//                              image), fence.proxy.async, mbarrier arrive;
+//   warp 16     MMA          : one thread issues 30 tcgen05.mma (M=128, N=NT, K=8) per tile, tcgen05.commit frees
+//                              ring slots and publishes the accumulator stage (2 TMEM stages of NT columns);
+//   warps 0-7   epilogue     : two warps per TMEM lane quadrant (half of the columns each): tcgen05.ld 32x32b.x16,
+//                              max / ex2 / lg2 over the mixtures, + per-state constant, b[frame, state] fp32 stores.
+// No tensor maps are needed: A never exists in global memory and W is a linear copy of a pre-packed image.
 #include <algorithm>
 #include "common.cuh"
 
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------ packed image
 constexpr uint32_t TC_MAGIC = 0x4c4e5443u;   // "LNTC"
 constexpr int TC_BM = 128;                    // frames per tile (UMMA M)
-constexpr int TC_THREADS = 288;               // 4 epilogue + 4 producer + 1 MMA warp
+constexpr int TC_THREADS = 544;               // 8 epilogue + 4 lo-producer + 4 hi-producer + 1 MMA warp
 constexpr int TC_MAX_DIM = 39;                // the K axis is laid out for 39 dims; smaller dims are zero-padded
 constexpr int TC_KP = 80;                     // 2*39 + 1 -> 80
 constexpr int TC_KH = TC_KP / 2;              // K values per ring slot
@@ -177,9 +178,9 @@ static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     while (Mp < n_mix) Mp <<= 1;
     const int Kp = TC_KP;                                      // fixed K axis [x^2 (39) | x (39) | 1 | 0]; dims beyond `dim` are zero
     const int gran = 16 / Mp;                                  // states per 16 accumulator columns
-    // shared memory: W hi+lo = 2*NT*Kp*4, constants NT*4, A ring = 4 * 128 * (Kp/2) * 4, barriers + shift 1 KB
+    // shared memory: W hi+lo = 2*NT*Kp*4, per-state constants, A ring = 4 * 128 * (Kp/2) * 4, barriers 1 KB
     const int ring = 4 * TC_BM * (Kp / 2) * 4;
-    int nt_max = (TC_SMEM_LIMIT - ring - 1024) / (2 * Kp * 4 + 4);
+    int nt_max = (TC_SMEM_LIMIT - ring - 2048) / (2 * Kp * 4);
     nt_max = std::min(nt_max, 256) / 16 * 16;
     if (nt_max < 16) return false;
     const int spt_max = nt_max / Mp;
@@ -188,7 +189,7 @@ static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     spt = (spt + gran - 1) / gran * gran;
     g->Mp = Mp; g->Kp = Kp; g->SPT = spt; g->NT = spt * Mp;
     g->n_wtiles = (n_states + spt - 1) / spt;
-    g->tile_bytes = (size_t)2 * g->NT * Kp * 4 + (size_t)g->NT * 4;      // W hi | W lo | per-column constant c
+    g->tile_bytes = (size_t)2 * g->NT * Kp * 4 + (size_t)((g->SPT * 4 + 15) / 16 * 16);   // W hi | W lo | per-state constant
     g->total_bytes = sizeof(TcHeader) + g->tile_bytes * g->n_wtiles;
     g->smem_bytes = g->tile_bytes + ring + 1024;
     return true;
@@ -231,24 +232,34 @@ __global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double
         v *= 1.4426950408889634;                          // log2(e): the epilogue works in base 2
     }
     if (k == 2 * TC_MAX_DIM) {
-        // the constant of the Gaussian (+ log w) is added in the epilogue in fp32 with round-to-nearest: keeping it
-        // out of the tensor-core accumulator keeps the accumulated magnitudes -- and with them the truncation of
-        // the fp32 accumulation -- small.  Padded mixtures / states get -1e30 (exp2 -> 0).
-        double c = -1e30;
-        if (j < n_states && m < n_mix) {
-            const int64_t gi = (int64_t)j * n_mix + m;
-            c = (double)dim * 1.8378770664093453;
+        // K column 78 multiplies the constant 1 of the A rows.  It carries the constant of the Gaussian (+ log w)
+        // RELATIVE to the largest constant of its state; that per-state maximum is added in the epilogue in fp32 with
+        // round-to-nearest.  Keeping the big common part (~ -55 in base 2) out of the tensor-core accumulator keeps
+        // the accumulated magnitudes -- and with them the truncation of the fp32 accumulation -- small, at the
+        // price of one add per state.  Padded mixtures / states get -1e30 (exp2 -> 0).
+        auto gconst = [&](int mm_) -> double {
+            const int64_t gi = (int64_t)j * n_mix + mm_;
+            double c = (double)dim * 1.8378770664093453;
             for (int d = 0; d < dim; ++d) {
                 const double sh = shift ? shift[d] : 0.0;
-                const double mm = mu[gi * dim + d] - sh;
-                c += log(var[gi * dim + d]) + mm * mm / var[gi * dim + d];
+                const double dm = mu[gi * dim + d] - sh;
+                c += log(var[gi * dim + d]) + dm * dm / var[gi * dim + d];
             }
             c = (logw[gi] - 0.5 * c) * 1.4426950408889634;
-            if (!(c > -1e30)) c = -1e30;                  // log w = -inf
+            return (c > -1e30) ? c : -1e30;               // log w = -inf
+        };
+        double cmax = -1e30;
+        if (j < n_states)
+            for (int mm_ = 0; mm_ < n_mix; ++mm_) cmax = fmax(cmax, gconst(mm_));
+        v = -1e30;
+        if (j < n_states && m < n_mix) {
+            const double c = gconst(m);
+            v = (c > -1e30) ? c - cmax : -1e30;
         }
-        float* ctab = reinterpret_cast<float*>(packed + sizeof(TcHeader) + (size_t)tile * g.tile_bytes + (size_t)2 * g.NT * g.Kp * 4);
-        ctab[n] = (float)c;
-        v = 0.0;
+        if (m == 0) {
+            float* ctab = reinterpret_cast<float*>(packed + sizeof(TcHeader) + (size_t)tile * g.tile_bytes + (size_t)2 * g.NT * g.Kp * 4);
+            ctab[n / g.Mp] = (float)cmax;
+        }
     }
     const float hi = tf32_round((float)v);
     const float lo = (float)(v - (double)hi);
@@ -258,17 +269,65 @@ __global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double
     *reinterpret_cast<float*>(base + (size_t)g.NT * g.Kp * 4 + off) = lo;
 }
 
+// ------------------------------------------------------------------------------------------------ feature staging
+// xt[tile][d < 40][row < 128] = feats[tile*128 + row][d] - shift[d]  (0 beyond n_frames / dim).  The W-resident main
+// kernel makes every CTA stream ALL frames; reading row-major 39-float rows with thread = row costs 8 sectors per
+// useful one out of L2.  One cheap pass to this tile-transposed copy (L2-resident: 160 B/frame) makes the
+// producers' loads perfectly coalesced.
+constexpr int TC_XT_D = 40;
+__global__ void __launch_bounds__(256) gmm_tc_stage_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
+                                                           const uint8_t* __restrict__ packed, float* __restrict__ xt) {
+    __shared__ float tile[TC_BM][TC_XT_D + 1];
+    const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
+    const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
+    const int rows = (int)min((int64_t)TC_BM, n_frames - f0);
+    for (int i = threadIdx.x; i < TC_BM * TC_XT_D; i += 256) {
+        const int r = i / TC_XT_D, d = i - r * TC_XT_D;
+        tile[r][d] = 0.f;
+    }
+    __syncthreads();
+    if (ld_feats == dim) {                                   // rows are contiguous: one flat coalesced copy
+        const float* src = feats + f0 * ld_feats;
+        for (int i = threadIdx.x; i < rows * dim; i += 256) {
+            const int r = i / dim, d = i - r * dim;
+            tile[r][d] = __ldg(src + i) - hdr->shift[d];
+        }
+    } else {
+        for (int i = threadIdx.x; i < rows * dim; i += 256) {
+            const int r = i / dim, d = i - r * dim;
+            tile[r][d] = __ldg(feats + (f0 + r) * ld_feats + d) - hdr->shift[d];
+        }
+    }
+    __syncthreads();
+    float* dst = xt + (int64_t)blockIdx.x * TC_XT_D * TC_BM;
+    for (int i = threadIdx.x; i < TC_XT_D * TC_BM; i += 256) {
+        const int d = i / TC_BM, r = i - d * TC_BM;
+        dst[i] = tile[r][d];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ main kernel
 struct TcArgs {
-    const float* feats; int ld_feats; int64_t n_frames;
+    const float* xt; int64_t n_frames;
     const uint8_t* packed; float* b_out; int64_t ld_b;
     int n_states, dim, Mp, Kp, SPT, NT, n_wtiles, n_fsplit;
     int64_t frames_per_split;
     uint32_t swap_lbo_sbo;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int MP>
-__device__ __forceinline__ void lse_store(const float* v, float* out_row, int st0, int st_end) {
+__device__ __forceinline__ void lse_store(const float* v, const float* c_state, float* out_row, int st_local0, int st_global0, int st_end) {
     // 16 accumulator columns = 16/MP states, MP mixtures each, base-2 domain
 #pragma unroll
     for (int g = 0; g < 16 / MP; ++g) {
@@ -277,11 +336,13 @@ __device__ __forceinline__ void lse_store(const float* v, float* out_row, int st
         for (int i = 1; i < MP; ++i) mx = fmaxf(mx, v[g * MP + i]);
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < MP; ++i) s += exp2f(v[g * MP + i] - mx);
-        const float r = (mx + __log2f(s)) * TC_LN2;
-        if (st0 + g < st_end) out_row[st0 + g] = r;
+        for (int i = 0; i < MP; ++i) s += ex2_approx(v[g * MP + i] - mx);
+        const float r = ((mx + lg2_approx(s)) + c_state[st_local0 + g]) * TC_LN2;
+        if (st_global0 + g < st_end) out_row[st_global0 + g] = r;
     }
 }
+
+constexpr int TC_EPI_WARPS = 8, TC_WARP_LO = 8, TC_WARP_HI = 12, TC_WARP_MMA = 16;
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -289,40 +350,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
     const int NT = a.NT;
     const uint32_t w_part = (uint32_t)NT * Kp * 4;
     const uint32_t slot_bytes = TC_BM * KH * 4;
-    const uint32_t tile_bytes = 2 * w_part + (uint32_t)NT * 4;
-    uint8_t* s_w = tc_smem;                       // [W hi | W lo | c], the packed tile image verbatim
+    const uint32_t tile_bytes = 2 * w_part + (uint32_t)((a.SPT * 4 + 15) / 16 * 16);
+    uint8_t* s_w = tc_smem;                       // [W hi | W lo | c_state], the packed tile image verbatim
     const float* s_c = reinterpret_cast<const float*>(tc_smem + 2 * w_part);
-    uint8_t* s_a = tc_smem + tile_bytes;          // 4 ring slots
+    uint8_t* s_a = tc_smem + tile_bytes;          // 4 ring slots: lo-half0, lo-half1, hi-half0, hi-half1
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + 4 * slot_bytes);
     uint64_t* a_full = bars;                      // [4] producers -> MMA
     uint64_t* a_empty = bars + 4;                 // [4] MMA (commit) -> producers
     uint64_t* t_full = bars + 8;                  // [2] MMA (commit) -> epilogue
     uint64_t* t_empty = bars + 10;                // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    float* s_shift = reinterpret_cast<float*>(bars + 13);          // [TC_MAX_DIM+1] feature centre
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, TC_EPI_WARPS * 32); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == TC_WARP_MMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const TcHeader* hdr = reinterpret_cast<const TcHeader*>(a.packed);
-    if (tid <= TC_MAX_DIM) s_shift[tid] = hdr->shift[tid];
     const uint32_t idesc = make_idesc_tf32(TC_BM, NT);
     // descriptor strides of the K-major no-swizzle images (kmajor_off): next K chunk 128 B, next 8 rows (K/4)*128 B
     uint32_t a_lbo = 128, a_sbo = (uint32_t)(KH / 4) * 128, b_lbo = 128, b_sbo = (uint32_t)(Kp / 4) * 128;
     if (a.swap_lbo_sbo) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
 
-    uint32_t prod_cnt = 0;      // ring-slot visits (producer view)
-    uint32_t mma_cnt = 0;       // ring-slot visits (MMA view)
-    uint32_t tile_cnt = 0;      // accumulator stages used (MMA and epilogue keep their own copies in lock step)
+    uint32_t tile_cnt = 0;      // tiles processed so far by this role (every role advances it identically)
     int cur_wtile = -1;
     const int n_items = a.n_wtiles * a.n_fsplit;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -342,35 +398,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
         }
         const int n_tiles = (int)((fe - fs + TC_BM - 1) / TC_BM);
 
-        if (warp >= 4 && warp < 8) {
-            // ===================== producers: thread = frame row
-            const int r = tid - 128;
+        if (warp >= TC_WARP_LO && warp < TC_WARP_MMA) {
+            // ===================== producers: thread = frame row; group 0 writes the lo slots (0,1), group 1 the hi slots (2,3)
+            const bool hi_group = warp >= TC_WARP_HI;
+            const int r = tid - (hi_group ? TC_WARP_HI : TC_WARP_LO) * 32;
             const uint32_t row_off = (uint32_t)((r >> 3) * (KH >> 2) * 128 + (r & 7) * 16);
             for (int t = 0; t < n_tiles; ++t) {
                 const int64_t f = fs + (int64_t)t * TC_BM + r;
-                float x[TC_MAX_DIM + 1];
-                const bool valid = f < fe;
-                const float* xr = a.feats + f * a.ld_feats;
-                if (valid && (a.ld_feats & 3) == 0 && a.ld_feats >= TC_MAX_DIM + 1 && ((uintptr_t)a.feats & 15) == 0) {
+                // coalesced: lane = row inside the tile-transposed staging copy (already centred, zero padded)
+                float x[TC_MAX_DIM];
+                const float* xr = a.xt + (f / TC_BM) * (int64_t)(TC_XT_D * TC_BM) + r;
 #pragma unroll
-                    for (int c = 0; c < (TC_MAX_DIM + 1) / 4; ++c) {
-                        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (c * 4 < a.dim) q = __ldg(reinterpret_cast<const float4*>(xr) + c);
-                        x[4 * c] = q.x; x[4 * c + 1] = q.y; x[4 * c + 2] = q.z; x[4 * c + 3] = q.w;
-                    }
-                } else {
+                for (int d = 0; d < TC_MAX_DIM; ++d) x[d] = __ldg(xr + d * TC_BM);
+                const uint32_t par = ((tile_cnt + t) & 1) ^ 1;
 #pragma unroll
-                    for (int d = 0; d < TC_MAX_DIM; ++d) x[d] = (valid && d < a.dim) ? __ldg(xr + d) : 0.f;
-                }
-#pragma unroll
-                for (int d = 0; d < TC_MAX_DIM; ++d) x[d] = (valid && d < a.dim) ? x[d] - s_shift[d] : 0.f;
-                // ring slot s holds K half (s&1) of the lo (s<2) or hi (s>=2) image of [x^2 (39) | x (39) | 0 0]
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    constexpr int dummy = 0; (void)dummy;
-                    const int half = s & 1;
-                    const bool islo = (s >> 1) == 0;
-                    mbar_wait(a_empty + s, ((prod_cnt >> 2) & 1) ^ 1);
+                for (int half = 0; half < 2; ++half) {
+                    const int s = (hi_group ? 2 : 0) + half;
+                    mbar_wait(a_empty + s, par);
                     uint8_t* slot = s_a + s * slot_bytes + row_off;
 #pragma unroll
                     for (int cc = 0; cc < KH / 4; ++cc) {
@@ -378,34 +422,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int k = half * KH + cc * 4 + e;          // compile-time after unrolling
-                            float v;
+                            float v;                                        // K axis: [x^2 (39) | x (39) | 1 | 0]
                             if (k < TC_MAX_DIM) v = x[k] * x[k];
                             else if (k < 2 * TC_MAX_DIM) v = x[k - TC_MAX_DIM];
-                            else v = 0.f;
+                            else v = (k == 2 * TC_MAX_DIM) ? 1.f : 0.f;
                             const float hi = tf32_round(v);
-                            q[e] = islo ? (v - hi) : hi;
+                            q[e] = hi_group ? hi : (v - hi);
                         }
                         *reinterpret_cast<float4*>(slot + cc * 128) = make_float4(q[0], q[1], q[2], q[3]);
                     }
                     fence_proxy_async();
                     mbar_arrive(a_full + s);
-                    ++prod_cnt;
                 }
             }
-        } else if (warp == 8) {
+        } else if (warp == TC_WARP_MMA) {
             // ===================== MMA issuer: one thread
             if (lane == 0) {
                 const uint32_t wh = smem_u32(s_w), wl = wh + w_part;
+                const uint32_t kadv_a = 2 * (a.swap_lbo_sbo ? a_sbo : a_lbo), kadv_b = 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo);
                 for (int t = 0; t < n_tiles; ++t) {
-                    const uint32_t stage = tile_cnt & 1;
-                    mbar_wait(t_empty + stage, ((tile_cnt >> 1) & 1) ^ 1);
+                    const uint32_t tc = tile_cnt + t;
+                    const uint32_t stage = tc & 1;
+                    mbar_wait(t_empty + stage, ((tc >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + stage * (uint32_t)NT;
                     // Order: all correction products first (Al.Bh from slots 0,1; Ah.Bl from slots 2,3), the main
                     // Ah.Bh products last.  The tensor core truncates when it aligns fp32 addends, so the fewer
                     // accumulations happen at full magnitude the smaller the (systematic) error: 10 instead of 30.
                     uint32_t acc = 0;
-                    const uint32_t kadv_a = 2 * (a.swap_lbo_sbo ? a_sbo : a_lbo), kadv_b = 2 * (a.swap_lbo_sbo ? b_sbo : b_lbo);
                     auto issue = [&](int s, uint32_t wbase) {
                         const int half = s & 1;
                         const uint32_t sa = smem_u32(s_a + s * slot_bytes);
@@ -417,13 +461,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
                         }
                     };
                     for (int s = 0; s < 2; ++s) {                       // Al . Bh
-                        mbar_wait(a_full + s, (mma_cnt >> 2) & 1);
+                        mbar_wait(a_full + s, tc & 1);
                         tc_fence_after();
                         issue(s, wh);
                         umma_commit(a_empty + s);                       // lo slots are free again
                     }
                     for (int s = 2; s < 4; ++s) {                       // Ah . Bl
-                        mbar_wait(a_full + s, (mma_cnt >> 2) & 1);
+                        mbar_wait(a_full + s, tc & 1);
                         tc_fence_after();
                         issue(s, wl);
                     }
@@ -431,49 +475,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
                         issue(s, wh);
                         umma_commit(a_empty + s);
                     }
-                    mma_cnt += 4;
                     umma_commit(t_full + stage);        // accumulator stage complete
-                    ++tile_cnt;
                 }
             }
             __syncwarp();
         } else {
-            // ===================== epilogue: warp w reads TMEM lanes 32w..32w+31 (= frame rows)
-            const int row = warp * 32 + lane;
+            // ===================== epilogue: warps w and w+4 read TMEM lanes 32(w&3).. (= frame rows), half of the columns each
+            const int quad = warp & 3, chalf = warp >> 2;
+            const int row = quad * 32 + lane;
             const int st_tile0 = wt * a.SPT;
             const int st_end = min(a.n_states, st_tile0 + a.SPT);
+            const int n16 = NT / 16;
+            const int c16_begin = chalf ? (n16 + 1) / 2 : 0, c16_end = chalf ? n16 : (n16 + 1) / 2;
             for (int t = 0; t < n_tiles; ++t) {
-                const uint32_t stage = tile_cnt & 1;
-                mbar_wait(t_full + stage, (tile_cnt >> 1) & 1);
+                const uint32_t tc = tile_cnt + t;
+                const uint32_t stage = tc & 1;
+                mbar_wait(t_full + stage, (tc >> 1) & 1);
                 tc_fence_after();
                 const int64_t f = fs + (int64_t)t * TC_BM + row;
                 float* out_row = a.b_out + f * a.ld_b;
-                const bool valid = f < fe;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * (uint32_t)NT;
-                for (int c0 = 0; c0 < NT; c0 += 16) {
+                const int se = (f < fe) ? st_end : 0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + stage * (uint32_t)NT;
+                for (int c16 = c16_begin; c16 < c16_end; ++c16) {
                     float v[16];
-                    tmem_ld16(taddr + c0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += s_c[c0 + i];      // Gaussian constant + log w (base 2)
-                    const int st0 = st_tile0 + c0 / a.Mp;
-                    const int se = valid ? st_end : 0;
+                    tmem_ld16(taddr + c16 * 16, v);
+                    const int sl0 = (c16 * 16) / a.Mp;
                     switch (a.Mp) {
-                        case 16: lse_store<16>(v, out_row, st0, se); break;
-                        case 8: lse_store<8>(v, out_row, st0, se); break;
-                        case 4: lse_store<4>(v, out_row, st0, se); break;
-                        case 2: lse_store<2>(v, out_row, st0, se); break;
-                        default: lse_store<1>(v, out_row, st0, se); break;
+                        case 16: lse_store<16>(v, s_c, out_row, sl0, st_tile0 + sl0, se); break;
+                        case 8: lse_store<8>(v, s_c, out_row, sl0, st_tile0 + sl0, se); break;
+                        case 4: lse_store<4>(v, s_c, out_row, sl0, st_tile0 + sl0, se); break;
+                        case 2: lse_store<2>(v, s_c, out_row, sl0, st_tile0 + sl0, se); break;
+                        default: lse_store<1>(v, s_c, out_row, sl0, st_tile0 + sl0, se); break;
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(t_empty + stage);
-                ++tile_cnt;
             }
         }
+        tile_cnt += n_tiles;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == TC_WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 static uint32_t g_umma_swap = 0;
@@ -518,18 +561,35 @@ extern "C" int lnasr_gmm_pack_tc(const double* logw, const double* mu, const dou
     return LNASR_OK;
 }
 
+extern "C" int lnasr_gmm_tc_workspace_bytes(int64_t n_frames, size_t* bytes) {
+    LNASR_CHECK_ARG(bytes && n_frames >= 0, "gmm_tc_workspace_bytes: bad arguments");
+    *bytes = (size_t)ceil_div(n_frames, TC_BM) * TC_BM * TC_XT_D * sizeof(float) + 256;
+    return LNASR_OK;
+}
+
 extern "C" int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed, int32_t n_states,
-                                   int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b, void* stream) {
+                                   int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b, void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
     TcGeom g;
     LNASR_CHECK_ARG(feats && packed && b_out, "gmm_loglik_tc: null pointer");
     LNASR_CHECK_ARG(tc_geometry(n_states, n_mix, dim, &g), "gmm_tc: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", TC_MAX_DIM, n_mix, dim);
     LNASR_CHECK_ARG(ld_feats >= dim && ld_b >= n_states, "gmm_loglik_tc: bad leading dimensions");
     if (n_frames == 0) return LNASR_OK;
+    size_t need = 0;
+    lnasr_gmm_tc_workspace_bytes(n_frames, &need);
+    if (!workspace || workspace_bytes < need) {
+        set_error("gmm_loglik_tc: workspace %zu < %zu bytes", workspace_bytes, need);
+        return LNASR_EWORKSPACE;
+    }
+    float* xt = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const int64_t frame_tiles = ceil_div(n_frames, TC_BM);
+    gmm_tc_stage_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, xt);
+    LNASR_LAUNCH_CHECK();
     TcArgs a{};
-    a.feats = feats; a.ld_feats = ld_feats; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
+    a.xt = xt; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
     a.n_states = n_states; a.dim = dim; a.Mp = g.Mp; a.Kp = g.Kp; a.SPT = g.SPT; a.NT = g.NT; a.n_wtiles = g.n_wtiles;
     const int sms = sm_count();
-    const int64_t frame_tiles = ceil_div(n_frames, TC_BM);
     int n_fsplit = (int)std::max<int64_t>(1, std::min<int64_t>(frame_tiles, sms / std::max(1, g.n_wtiles)));
     const int64_t tiles_per_split = ceil_div(frame_tiles, n_fsplit);
     n_fsplit = (int)ceil_div(frame_tiles, tiles_per_split);
@@ -538,7 +598,7 @@ extern "C" int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t
     a.swap_lbo_sbo = g_umma_swap;
     const int grid = std::min(sms, g.n_wtiles * n_fsplit);
     LNASR_CUDA(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    gmm_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, (cudaStream_t)stream>>>(a);
+    gmm_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, stream>>>(a);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }

@@ -143,33 +143,34 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         return make_ctx(u, f);
     };
     // raw samples of one frame: lane holds pairs (x[2m], x[2m+1]), m = lane + 32 q; out-of-range samples read as 0
-    auto fetch = [&](const FrameCtx& c, float* xe, float* xo, float& xlead) {
+    // (kept in the PCM type: converting here would make the prefetch wait for its own loads)
+    auto fetch = [&](const FrameCtx& c, PcmT* xe, PcmT* xo, PcmT& xlead) {
         const PcmT* x = pcm + c.u_s0;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int n0 = 2 * (lane + 32 * q);
             const int64_t i0 = c.s_start + n0;
-            xe[q] = (n0 < P.frame_len && i0 < c.u_len) ? (float)__ldg(x + i0) : 0.f;
-            xo[q] = (n0 + 1 < P.frame_len && i0 + 1 < c.u_len) ? (float)__ldg(x + i0 + 1) : 0.f;
+            xe[q] = (n0 < P.frame_len && i0 < c.u_len) ? __ldg(x + i0) : PcmT(0);
+            xo[q] = (n0 + 1 < P.frame_len && i0 + 1 < c.u_len) ? __ldg(x + i0 + 1) : PcmT(0);
         }
         // the sample before the frame (needed by lane 0, q = 0)
-        xlead = (lane == 0 && c.s_start >= 1 && c.s_start - 1 < c.u_len) ? (float)__ldg(x + c.s_start - 1) : 0.f;
+        xlead = (lane == 0 && c.s_start >= 1 && c.s_start - 1 < c.u_len) ? __ldg(x + c.s_start - 1) : PcmT(0);
     };
 
     for (int64_t run = warp_global; run < n_runs; run += warp_stride) {
         const int64_t f_begin = run * FRAMES_PER_RUN;
         const int64_t f_end = min(f_begin + (int64_t)FRAMES_PER_RUN, total_frames);
         FrameCtx nxt = make_ctx(find_utt(frame_off, n_utt, f_begin), f_begin);
-        float pe[NQ], po[NQ], plead;
+        PcmT pe[NQ], po[NQ], plead;
         fetch(nxt, pe, po, plead);
         int acc_u = nxt.u;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};   // running column sums of utterance acc_u: coefficient (lane & 15) + 16 i
         for (int64_t f = f_begin; f < f_end; ++f) {
             const FrameCtx cur = nxt;
-            float xe[NQ], xo[NQ];
+            float xe[NQ], xo[NQ];                    // int16 and float32 PCM are both exact in float
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) { xe[q] = pe[q]; xo[q] = po[q]; }
-            const float xlead = plead;
+            for (int q = 0; q < NQ; ++q) { xe[q] = (float)pe[q]; xo[q] = (float)po[q]; }
+            const float xlead = (float)plead;
             if (f + 1 < f_end) {                      // software prefetch of the next frame's samples
                 nxt = next_ctx(cur, f + 1);
                 fetch(nxt, pe, po, plead);
@@ -270,10 +271,13 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                     for (int t = sub; t < len; t += 4) e = fma((double)w[t], s_pow[s + t], e);
                     e += __shfl_xor_sync(gmask, e, 1);
                     e += __shfl_xor_sync(gmask, e, 2);
-                    if (sub == (i & 3)) {
-                        if (e == 0.0) e = 2.220446049250313e-16;          // np.finfo(float).eps
-                        s_lm[m] = 8.685889638065035 * log(e);             // 20 log10(e) = 20/ln(10) * ln(e)
-                    }
+                    if (sub == 0) s_lm[m] = e;
+                }
+                __syncwarp();
+                for (int m = lane; m < P.n_mel; m += 32) {                // all lanes take logs: 2 rounds instead of 5
+                    double e = s_lm[m];
+                    if (e == 0.0) e = 2.220446049250313e-16;              // np.finfo(float).eps
+                    s_lm[m] = 8.685889638065035 * log(e);                 // 20 log10(e) = 20/ln(10) * ln(e)
                 }
             }
             __syncwarp();

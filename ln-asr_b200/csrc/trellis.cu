@@ -226,6 +226,194 @@ trellis_small_kernel(TrellisArgs a) {
 // general kernel: one CTA per (utterance, model)
 constexpr int TG_THREADS = 256;
 
+// termination over the last column prev[0..N): max / first argmax (hmm.py:169) or log-sum-exp (hmm.py:274)
+template <int MODE>
+__device__ __forceinline__ void trellis_terminate(const double* prev, int N, const TrellisArgs& a, int64_t p, double* red_v, int* red_i) {
+    if (MODE == MODE_BACKWARD) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MODE == MODE_VITERBI) {
+        double best = neg_inf();
+        int arg = 0x7fffffff;
+        for (int j = threadIdx.x; j < N; j += TG_THREADS) {
+            const double c = prev[j];
+            if (c > best) { best = c; arg = j; }      // ascending j per thread -> first max per thread
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = shfl_d(best, lane ^ o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (lane == 0) { red_v[warp] = best; red_i[warp] = arg; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < TG_THREADS / 32; ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < arg)) { best = red_v[w]; arg = red_i[w]; }
+            if (arg == 0x7fffffff) arg = 0;           // all -inf: np.argmax gives 0
+            if (a.score_out) a.score_out[p] = best;
+            if (a.last_state) a.last_state[p] = arg;
+        }
+    } else {
+        double mx = neg_inf();
+        for (int j = threadIdx.x; j < N; j += TG_THREADS) mx = fmax(mx, prev[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_d(mx, lane ^ o));
+        if (lane == 0) red_v[warp] = mx;
+        __syncthreads();
+        mx = red_v[0];
+        for (int w = 1; w < TG_THREADS / 32; ++w) mx = fmax(mx, red_v[w]);
+        __syncthreads();
+        double sum = 0.0;
+        if (mx != neg_inf())
+            for (int j = threadIdx.x; j < N; j += TG_THREADS) sum += (prev[j] == neg_inf()) ? 0.0 : exp(prev[j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += shfl_d(sum, lane ^ o);
+        if (lane == 0) red_v[warp] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < TG_THREADS / 32; ++w) sum += red_v[w];
+            if (a.score_out) a.score_out[p] = (mx == neg_inf()) ? mx : mx + log(sum);
+        }
+    }
+}
+
+// Sparse-transition kernel for 32 < N <= 256*SPT with at most 4 finite predecessors (successors) per state: the
+// usual case for large acoustic models (left-to-right: self, next, skip).  One CTA per (utterance, model); every
+// thread OWNS states tid + 256 i for the whole utterance and keeps their transition lists in REGISTERS, so a time
+// step touches HBM only for the emission row (read, prefetched one step ahead) and the backpointer row (write):
+// 8N bytes per frame, the roofline of SURVEY.md 8(d).  The trellis column is double buffered in shared memory.
+constexpr int TR_DEG = 4;
+
+__device__ __forceinline__ void tr_cp_async(void* smem_dst, const void* gmem_src, int bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// PF emission rows are kept in flight with cp.async (global -> shared, no registers): at ~1 us of HBM latency and
+// ~0.3 us per time step a one-step register prefetch leaves the kernel latency-bound (measured: 11 % of HBM peak).
+template <int SPT, typename BT, int MODE, int PF>
+__global__ void __launch_bounds__(TG_THREADS, 2)
+trellis_reg_kernel(TrellisArgs a) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    const int N = a.N;
+    double* prev = (double*)tg_smem;
+    double* next = prev + N;
+    const int n_pad = (N + 3) & ~3;
+    BT* erow = reinterpret_cast<BT*>(next + N);            // [PF][n_pad]
+    __shared__ double red_v[TG_THREADS / 32];
+    __shared__ int red_i[TG_THREADS / 32];
+    const int64_t p = blockIdx.x;
+    const int u = (int)(p / a.n_models), k = (int)(p % a.n_models);
+    const int64_t f0 = __ldg(a.frame_off + u);
+    const int T = (int)(__ldg(a.frame_off + u + 1) - f0);
+    if (T == 0) return;
+    const int64_t ncol = (int64_t)a.n_models * N;
+    const int64_t cbase = (int64_t)k * N;
+    const BT* b = (const BT*)a.b;
+    const int deg = (MODE == MODE_BACKWARD) ? a.max_out : a.max_in;
+    const int* eidx = ((MODE == MODE_BACKWARD) ? a.succ_idx : a.pred_idx) + (int64_t)k * deg * N;
+    const double* eval = ((MODE == MODE_BACKWARD) ? a.succ_val : a.pred_val) + (int64_t)k * deg * N;
+    // emission row used at step s
+    auto erow_of = [&](int s) -> int64_t { return (MODE == MODE_BACKWARD) ? (f0 + T - 1 - s) : (f0 + s); };
+    const bool vec16 = (((size_t)a.ld_b * sizeof(BT)) % 16 == 0) && (((size_t)cbase * sizeof(BT)) % 16 == 0) &&
+                       (((size_t)N * sizeof(BT)) % 16 == 0) && (((uintptr_t)b) % 16 == 0);
+    auto issue_row = [&](int s) {
+        if (s < T) {
+            const BT* src = b + erow_of(s) * a.ld_b + cbase;
+            BT* dst = erow + (size_t)(s % PF) * n_pad;
+            if (vec16) {
+                constexpr int EPV = 16 / (int)sizeof(BT);
+                for (int i = threadIdx.x * EPV; i < N; i += TG_THREADS * EPV) tr_cp_async(dst + i, src + i, 16);
+            } else {
+                for (int i = threadIdx.x; i < N; i += TG_THREADS) tr_cp_async(dst + i, src + i, (int)sizeof(BT));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < PF - 1; ++s) issue_row(s);
+    int idx[SPT][TR_DEG];
+    double val[SPT][TR_DEG];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+        const int j = threadIdx.x + TG_THREADS * i;
+#pragma unroll
+        for (int d = 0; d < TR_DEG; ++d) {
+            const bool ok = j < N && d < deg;
+            idx[i][d] = ok ? __ldg(eidx + (int64_t)d * N + j) : 0;
+            val[i][d] = ok ? __ldg(eval + (int64_t)d * N + j) : neg_inf();
+        }
+    }
+    for (int s = 0; s < T; ++s) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");     // row s has landed (my copies) ...
+        __syncthreads();                                                       // ... and everyone's; step s-1's column is complete
+        issue_row(s + PF - 1);                                                 // its buffer was last read in step s-1
+        const BT* er = erow + (size_t)(s % PF) * n_pad;
+        const int64_t row = erow_of(s);
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) {
+            const int j = threadIdx.x + TG_THREADS * i;
+            if (j < N) {
+                const double e = (double)er[j];
+                if (s == 0) {
+                    double v;
+                    if (MODE == MODE_BACKWARD) {
+                        if (a.full_out) a.full_out[row * ncol + cbase + j] = 0.0;     // beta[T-1] = 0
+                        v = e;                                                        // buffer holds beta[t] + b[t]
+                    } else {
+                        v = __ldg(a.logpi + cbase + j) + e;
+                        if (a.full_out) a.full_out[row * ncol + cbase + j] = v;
+                        if (MODE == MODE_VITERBI) {
+                            if (a.bt_ws) a.bt_ws[row * ncol + cbase + j] = 0;
+                            if (a.bt_out) a.bt_out[row * ncol + cbase + j] = 0;
+                        }
+                    }
+                    next[j] = v;
+                    continue;
+                }
+                double c[TR_DEG];
+#pragma unroll
+                for (int d = 0; d < TR_DEG; ++d) c[d] = prev[idx[i][d]] + val[i][d];
+                if (MODE == MODE_VITERBI) {
+                    double best = neg_inf();
+                    int arg = 0;
+#pragma unroll
+                    for (int d = 0; d < TR_DEG; ++d)
+                        if (c[d] > best) { best = c[d]; arg = idx[i][d]; }        // ascending predecessor index: first max
+                    const double nv = best + e;
+                    if (a.bt_ws) a.bt_ws[row * ncol + cbase + j] = (uint16_t)arg;
+                    if (a.bt_out) a.bt_out[row * ncol + cbase + j] = (uint32_t)arg;
+                    if (a.full_out) a.full_out[row * ncol + cbase + j] = nv;
+                    next[j] = nv;
+                } else {
+                    double mx = fmax(fmax(c[0], c[1]), fmax(c[2], c[3]));
+                    double l = mx;
+                    if (mx != neg_inf()) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int d = 0; d < TR_DEG; ++d) sum += exp(c[d] - mx);     // exp(-inf) = 0 for the padding
+                        l = mx + log(sum);
+                    }
+                    if (MODE == MODE_FORWARD) {
+                        const double nv = l + e;
+                        if (a.full_out) a.full_out[row * ncol + cbase + j] = nv;
+                        next[j] = nv;
+                    } else {
+                        if (a.full_out) a.full_out[row * ncol + cbase + j] = l;    // beta[t, j]
+                        next[j] = l + e;                                            // beta[t] + b[t] for the next step
+                    }
+                }
+            }
+        }
+        double* t = prev; prev = next; next = t;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    trellis_terminate<MODE>(prev, N, a, p, red_v, red_i);
+}
+
 template <typename BT, int MODE>
 __global__ void __launch_bounds__(TG_THREADS)
 trellis_general_kernel(TrellisArgs a) {
@@ -312,53 +500,7 @@ trellis_general_kernel(TrellisArgs a) {
         __syncthreads();
         double* t = prev; prev = next; next = t;
     }
-    if (MODE == MODE_BACKWARD) return;
-    // termination over prev[0..N)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (MODE == MODE_VITERBI) {
-        double best = neg_inf();
-        int arg = 0x7fffffff;
-        for (int j = threadIdx.x; j < N; j += TG_THREADS) {
-            const double c = prev[j];
-            if (c > best) { best = c; arg = j; }      // ascending j per thread -> first max per thread
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = shfl_d(best, lane ^ o);
-            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-        }
-        if (lane == 0) { red_v[warp] = best; red_i[warp] = arg; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < TG_THREADS / 32; ++w)
-                if (red_v[w] > best || (red_v[w] == best && red_i[w] < arg)) { best = red_v[w]; arg = red_i[w]; }
-            if (arg == 0x7fffffff) arg = 0;           // all -inf: np.argmax gives 0
-            if (a.score_out) a.score_out[p] = best;
-            if (a.last_state) a.last_state[p] = arg;
-        }
-    } else {
-        double mx = neg_inf();
-        for (int j = threadIdx.x; j < N; j += TG_THREADS) mx = fmax(mx, prev[j]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_d(mx, lane ^ o));
-        if (lane == 0) red_v[warp] = mx;
-        __syncthreads();
-        mx = red_v[0];
-        for (int w = 1; w < TG_THREADS / 32; ++w) mx = fmax(mx, red_v[w]);
-        __syncthreads();
-        double sum = 0.0;
-        if (mx != neg_inf())
-            for (int j = threadIdx.x; j < N; j += TG_THREADS) sum += (prev[j] == neg_inf()) ? 0.0 : exp(prev[j] - mx);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += shfl_d(sum, lane ^ o);
-        if (lane == 0) red_v[warp] = sum;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < TG_THREADS / 32; ++w) sum += red_v[w];
-            if (a.score_out) a.score_out[p] = (mx == neg_inf()) ? mx : mx + log(sum);
-        }
-    }
+    trellis_terminate<MODE>(prev, N, a, p, red_v, red_i);
 }
 
 // path[T-1] = argmax v[T-1]; path[t] = bt[t+1, path[t+1]]                                  (hmm.py:168-171)
@@ -427,6 +569,19 @@ static int launch_general(const TrellisArgs& a, cudaStream_t stream) {
     return LNASR_OK;
 }
 
+template <int SPT, typename BT, int MODE>
+static int launch_reg(const TrellisArgs& a, cudaStream_t stream) {
+    constexpr int PF = (sizeof(BT) == 4) ? 8 : 4;            // emission rows in flight
+    const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
+    const size_t n_pad = ((size_t)a.N + 3) & ~(size_t)3;
+    const size_t smem = 2 * (size_t)a.N * sizeof(double) + (size_t)PF * n_pad * sizeof(BT);
+    if (smem > 48 * 1024)
+        LNASR_CUDA(cudaFuncSetAttribute(trellis_reg_kernel<SPT, BT, MODE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trellis_reg_kernel<SPT, BT, MODE, PF><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 template <int MODE>
 static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, cudaStream_t stream) {
     a.n_models = bank->n_models; a.N = bank->N; a.logA = bank->logA; a.logpi = bank->logpi;
@@ -436,6 +591,11 @@ static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, c
     if (a.N <= 32) return f32 ? launch_small<float, MODE>(a, stream) : launch_small<double, MODE>(a, stream);
     const bool have = (MODE == MODE_BACKWARD) ? (a.succ_idx && a.succ_val && a.max_out > 0) : (a.pred_idx && a.pred_val && a.max_in > 0);
     if (!have) { set_error("trellis: N=%d > 32 needs the packed transition lists (lnasr_trans_pack)", a.N); return LNASR_EINVAL; }
+    const int deg = (MODE == MODE_BACKWARD) ? a.max_out : a.max_in;
+    if (deg <= TR_DEG && a.N <= 4 * TG_THREADS)
+        return f32 ? launch_reg<4, float, MODE>(a, stream) : launch_reg<4, double, MODE>(a, stream);
+    if (deg <= TR_DEG && a.N <= 8 * TG_THREADS)
+        return f32 ? launch_reg<8, float, MODE>(a, stream) : launch_reg<8, double, MODE>(a, stream);
     return f32 ? launch_general<float, MODE>(a, stream) : launch_general<double, MODE>(a, stream);
 }
 

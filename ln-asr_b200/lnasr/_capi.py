@@ -54,7 +54,8 @@ SIGNATURES = {
     "lnasr_gmm_loglik_full": (C.c_int, [vp, C.c_int, i32, i64, vp, vp, vp, vp, i32, i32, i32, vp, C.c_int, i64, vp, vp]),
     "lnasr_gmm_tc_packed_bytes": (C.c_int, [i32, i32, i32, C.POINTER(sz)]),
     "lnasr_gmm_pack_tc": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
-    "lnasr_gmm_loglik_tc": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, vp, i64, vp]),
+    "lnasr_gmm_tc_workspace_bytes": (C.c_int, [i64, C.POINTER(sz)]),
+    "lnasr_gmm_loglik_tc": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, vp, i64, vp, sz, vp]),
     "lnasr_debug_set_umma_swap": (C.c_int, [C.c_int]),
     "lnasr_emit_gather": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
     "lnasr_trans_degree": (C.c_int, [vp, i32, i32, vp, vp]),

@@ -96,6 +96,54 @@ class AcousticPipeline:
         res = self.bank.score(mb.feats, mb.frame_offsets, n_utt, total, want_paths=want_paths, want_logprob=want_logprob)
         return res, mb
 
+    def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 4, want_paths: bool = False):
+        """End-to-end entry point for HOST audio: `pcm_host` is a pinned CPU tensor (int16 or float32) of concatenated
+        utterances, `sample_offsets` [n+1] host.  The batch is cut into `n_chunks` groups of whole utterances; the
+        host->device copy of group i+1 (copy stream) overlaps MFCC / GMM / Viterbi of group i (compute stream), two
+        staging buffers deep.  Returns (words int32 [n], best float64 [n]) as CPU tensors."""
+        t = _dev.torch()
+        off = np.asarray(sample_offsets, dtype=np.int64)
+        n_utt = len(off) - 1
+        n_chunks = max(1, min(n_chunks, n_utt))
+        # chunk boundaries at utterance borders, ~equal sample counts
+        targets = off[0] + (off[-1] - off[0]) * np.arange(1, n_chunks) / n_chunks
+        cuts = np.unique(np.concatenate([[0], np.searchsorted(off, targets), [n_utt]]))
+        bounds = [(int(cuts[i]), int(cuts[i + 1])) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+        max_samples = max(int(off[hi] - off[lo]) for lo, hi in bounds)
+        dev = _dev.device()
+        cur = t.cuda.current_stream()
+        if not hasattr(self, "_streams"):
+            self._streams = (t.cuda.Stream(), t.cuda.Stream())
+        copy_s, comp_s = self._streams
+        copy_s.wait_stream(cur)
+        comp_s.wait_stream(cur)
+        stage = [t.empty((max_samples,), dtype=pcm_host.dtype, device=dev) for _ in range(2)]
+        words = t.empty((n_utt,), dtype=t.int32, device=dev)
+        best = t.empty((n_utt,), dtype=t.float64, device=dev)
+        done = [None, None]
+        for i, (lo, hi) in enumerate(bounds):
+            s0, s1 = int(off[lo]), int(off[hi])
+            buf = stage[i & 1]
+            with t.cuda.stream(copy_s):
+                if done[i & 1] is not None:
+                    copy_s.wait_event(done[i & 1])            # the compute that last read this staging buffer
+                buf[:s1 - s0].copy_(pcm_host[s0:s1], non_blocking=True)
+                ev = t.cuda.Event()
+                ev.record(copy_s)
+            with t.cuda.stream(comp_s):
+                comp_s.wait_event(ev)
+                res, _ = self.recognize_batch(buf[:s1 - s0], off[lo:hi + 1] - s0, want_paths=want_paths)
+                words[lo:hi] = res.words
+                best[lo:hi] = res.best
+                d = t.cuda.Event()
+                d.record(comp_s)
+                done[i & 1] = d
+        cur.wait_stream(comp_s)
+        for x in stage + [words, best]:
+            x.record_stream(comp_s)
+            x.record_stream(copy_s)
+        return words.cpu(), best.cpu()
+
     def recognize(self, signals: Sequence[np.ndarray]):
         """Convenience: list of utterances -> numpy array of word indices."""
         arrs = [np.asarray(s) for s in signals]

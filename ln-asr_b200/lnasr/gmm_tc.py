@@ -40,7 +40,10 @@ class PackedGmmTC:
             raise _capi.LnasrError("the tensor-core GMM path takes float32 features")
         T = feats.shape[0]
         b = b_out if b_out is not None else _dev.empty((T, self.n_states), t.float32)
+        need = C.c_size_t(0)
+        _capi.check(_capi.lib().lnasr_gmm_tc_workspace_bytes(T, C.byref(need)), "gmm_tc_workspace_bytes")
+        ws = _dev.empty((need.value,), t.uint8)
         _capi.check(_capi.lib().lnasr_gmm_loglik_tc(_capi.ptr(feats), feats.stride(0), T, _capi.ptr(self.packed), self.n_states,
-                                                   self.n_mix, self.dim, _capi.ptr(b), b.stride(0), _capi.stream_ptr()),
-                    "gmm_loglik_tc")
+                                                   self.n_mix, self.dim, _capi.ptr(b), b.stride(0), _capi.ptr(ws), need.value,
+                                                   _capi.stream_ptr()), "gmm_loglik_tc")
         return b
