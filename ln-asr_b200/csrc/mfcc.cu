@@ -22,11 +22,17 @@ constexpr int FFT_N = 512;
 constexpr int HALF_N = 256;
 constexpr int MAX_MEL = 64;
 constexpr int RAW_LD = 16;            // raw static row: 12 cepstra + energy, padded to 16 floats
-constexpr int WARPS_PER_BLOCK = 8;
-constexpr int FRAMES_PER_RUN = 16;    // consecutive frames a warp handles before taking the next run
+constexpr int THREADS = 256;          // 8 warps = 16 half-warps; one frame per half-warp at a time
+constexpr int HW_PER_BLOCK = THREADS / 16;
+constexpr int FRAMES_PER_RUN = 32;    // consecutive frames a warp walks (its two halves take alternate frames)
+constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
+constexpr int P_LD = 264;             // power spectrum of one frame (257 doubles), aliases the transpose buffer
+constexpr int PER_HW_DOUBLES = 2 * 16 * TR_LD + MAX_MEL;     // transpose buffer | log-mel[64]
+constexpr int MAX_SLOTS = MAX_MEL / 16;
 
 struct MfccDev {
     int frame_len, frame_step, n_mel, n_ceps, fb_stride;
+    int hpf_q;                        // round(100 * hpf_alpha) when that is an integer (exact int16 pre-emphasis), else -1
     double hpf_alpha;
     const double* window;
     const double2* twiddle;
@@ -39,261 +45,279 @@ struct MfccDev {
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
-// compact per-stage twiddle tables of the radix-4 Stockham FFT: stage st (1..3, Ns = 4^st), factor r (1..3),
-// k < Ns  ->  W512^(r * k * 128 / Ns).  k is the fastest index, so a warp's loads are conflict-free.
-__host__ __device__ constexpr int tw_stage_off(int st) { return st == 1 ? 0 : (st == 2 ? 12 : 60); }
-constexpr int TW_STAGE_TOTAL = 252;              // 3*(4+16+64)
-constexpr int TW_SPLIT = HALF_N + 1;             // W512^k, k = 0..256, for the real-FFT split
+// 4-point forward DFT in place (W4 = -i)
+__device__ __forceinline__ void bfly4(double2& a0, double2& a1, double2& a2, double2& a3) {
+    const double2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = make_double2(d02.x + d13.y, d02.y - d13.x);     // d02 - i d13
+    a3 = make_double2(d02.x - d13.y, d02.y + d13.x);     // d02 + i d13
+}
+
+// 16-point forward DFT of v[0..15] (natural order in), fully in registers: two radix-4 passes with the W16 twiddles as
+// immediates.  Output Y[k] is left in v[NAT16(k)].
+#define NAT16(k) (4 * ((k) & 3) + ((k) >> 2))
+__device__ __forceinline__ void fft16(double2 (&v)[16]) {
+    constexpr double C1 = 0.92387953251128673848;    // cos(pi/8)
+    constexpr double S1 = 0.38268343236508978178;    // sin(pi/8)
+    constexpr double R2 = 0.70710678118654752440;    // sqrt(1/2)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bfly4(v[j], v[j + 4], v[j + 8], v[j + 12]);      // v[j + 4q] = T_j[q]
+    // v[j + 4q] *= W16^(j q),  W16^n = (cos(2 pi n/16), -sin(2 pi n/16))
+    v[5] = cmul(v[5], make_double2(C1, -S1));                                      // j=1,q=1 : n=1
+    v[9] = make_double2(R2 * (v[9].x + v[9].y), R2 * (v[9].y - v[9].x));           // j=1,q=2 : n=2
+    v[13] = cmul(v[13], make_double2(S1, -C1));                                    // j=1,q=3 : n=3
+    v[6] = make_double2(R2 * (v[6].x + v[6].y), R2 * (v[6].y - v[6].x));           // j=2,q=1 : n=2
+    v[10] = make_double2(v[10].y, -v[10].x);                                       // j=2,q=2 : n=4  (-i)
+    v[14] = make_double2(R2 * (v[14].y - v[14].x), -R2 * (v[14].x + v[14].y));     // j=2,q=3 : n=6  (-r,-r)
+    v[7] = cmul(v[7], make_double2(S1, -C1));                                      // j=3,q=1 : n=3
+    v[11] = make_double2(R2 * (v[11].y - v[11].x), -R2 * (v[11].x + v[11].y));     // j=3,q=2 : n=6
+    v[15] = cmul(v[15], make_double2(-C1, S1));                                    // j=3,q=3 : n=9
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bfly4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);   // v[4q + p] = Y[q + 4p]
+}
+
+__device__ __forceinline__ double2 shfl_c(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
 
 // shared memory carve-up (in doubles)
 struct SmemLayout {
-    int tw_stage, tw_split, window, dct, fb_w, fb_meta, per_warp, total;
+    int tw_mid, tw_split, window, dct, fb_w, fb_meta, per_hw, total;
 };
-constexpr int PER_WARP_DOUBLES = 2 * 2 * HALF_N + MAX_MEL;   // two complex buffers (power aliases the 2nd), logmel[64]
-__host__ __device__ inline SmemLayout smem_layout(int frame_len, int n_mel, int fb_stride, int n_dct_cols) {
+__host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int n_dct_cols) {
     SmemLayout L;
     int o = 0;
-    L.tw_stage = o; o += 2 * TW_STAGE_TOTAL;
-    L.tw_split = o; o += 2 * TW_SPLIT;
-    L.window = o;   o += (frame_len + 1) & ~1;
-    L.dct = o;      o += n_mel * n_dct_cols;             // [n][k < n_dct_cols]
-    L.fb_w = o;     o += (n_mel * fb_stride + 1) / 2;    // float weights
-    L.fb_meta = o;  o += MAX_MEL;                        // 2 * MAX_MEL ints
+    L.tw_mid = o;   o += 2 * 256;                         // W256^(b k1) at [k1*16 + b]
+    L.tw_split = o; o += 2 * 128;                         // W512^(b + 16 k2) at [k2*16 + b], k2 < 8
+    L.window = o;   o += FFT_N;                           // window (x 1/100 on the integer path), zero past frame_len
+    L.dct = o;      o += n_mel * n_dct_cols;              // [n][k < n_dct_cols]
+    L.fb_w = o;     o += n_mel * fb_stride;               // double weights
+    L.fb_meta = o;  o += (3 * MAX_MEL) / 2;               // ints: fb_start[64] | fb_len[64] | assign[MAX_SLOTS*16]
     o = (o + 1) & ~1;
-    L.per_warp = o;
-    L.total = o + WARPS_PER_BLOCK * PER_WARP_DOUBLES;
+    L.per_hw = o;
+    L.total = o + HW_PER_BLOCK * PER_HW_DOUBLES;
     return L;
 }
 
 // where a frame lives: utterance, its sample range, first sample of the frame
 struct FrameCtx {
     int u;
-    int64_t u_f1;        // first frame of the next utterance
+    int64_t u_f0, u_f1;  // first frame of this / of the next utterance
     int64_t u_s0;        // first sample of the utterance in pcm
     int64_t u_len;       // samples in the utterance
-    int64_t s_start;     // first sample of the frame, relative to the utterance
 };
 
 // The whole per-frame chain runs in float64.  The reference is float64 (mfcc.py), and the features are small
 // differences of ~200 dB log-mel values (mean normalisation, deltas) whose low-energy bands sit up to 90 dB below
 // the frame's peak: an fp32 FFT leaves ~1e-4 relative error in exactly those bands (measured), i.e. above the
-// 1e-4 parity bar after the DCT and the delta-deltas.  On B200 fp64 runs at half the fp32 rate and the kernel is
-// latency-, not ALU-bound, so exactness costs little.
+// 1e-4 parity bar after the DCT and the delta-deltas.
+//
+// Mapping: 16 threads (a half-warp) own one frame.  The 512-point real FFT is a 256-point complex FFT of the packed
+// signal z[m] = (xw[2m], xw[2m+1]), done as 16 x 16: thread b holds z[16a + b], a = 0..15, in registers, runs a
+// 16-point DFT over a, multiplies by W256^(b k1), transposes once through shared memory (the only shared-memory pass
+// of the FFT: 8 KB per frame instead of the ~70 KB of a stage-by-stage shared-memory FFT), runs the second 16-point
+// DFT over b.  Thread k1 then holds Z[k1 + 16 k2]; the real-FFT split pairs bin k with 256-k, which lives in lane
+// 16-k1 -> one shuffle per pair.
 template <typename PcmT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(THREADS, 2)
 mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sample_off,
                    const int64_t* __restrict__ frame_off, int n_utt, int64_t total_frames, MfccDev P,
                    float* __restrict__ raw, double* __restrict__ colsum, float* __restrict__ power_out,
                    float* __restrict__ ceps_raw_out) {
     extern __shared__ __align__(16) double smem[];
+    constexpr bool kIntPcm = (sizeof(PcmT) == 2);
     const bool full_ceps = (ceps_raw_out != nullptr);
     const int n_out = full_ceps ? P.n_mel : (P.n_ceps + 1);   // cepstral coefficients 0..n_out-1 computed
-    const SmemLayout L = smem_layout(P.frame_len, P.n_mel, P.fb_stride, n_out);
-    double2* s_tws = reinterpret_cast<double2*>(smem + L.tw_stage);
-    double2* s_twr = reinterpret_cast<double2*>(smem + L.tw_split);
+    const SmemLayout L = smem_layout(P.n_mel, P.fb_stride, n_out);
+    double2* s_twm = reinterpret_cast<double2*>(smem + L.tw_mid);
+    double2* s_tws = reinterpret_cast<double2*>(smem + L.tw_split);
     double* s_win = smem + L.window;
     double* s_dct = smem + L.dct;
-    float* s_fbw = reinterpret_cast<float*>(smem + L.fb_w);
+    double* s_fbw = smem + L.fb_w;
     int* s_fbs = reinterpret_cast<int*>(smem + L.fb_meta);
     int* s_fbl = s_fbs + MAX_MEL;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < TW_STAGE_TOTAL; i += blockDim.x) {
-        const int st = i < 12 ? 1 : (i < 60 ? 2 : 3);
-        const int Ns = 1 << (2 * st);
-        const int rel = i - tw_stage_off(st);
-        const int r = rel / Ns + 1, k = rel % Ns;
-        s_tws[i] = P.twiddle[r * k * (128 >> (2 * st))];
+    int* s_asg = s_fbl + MAX_MEL;
+    const int tid = threadIdx.x, lane = tid & 31, b = lane & 15, half = lane >> 4;
+    const bool int_path = kIntPcm && P.hpf_q >= 0;
+    const int n_slots = (P.n_mel + 15) >> 4;
+    for (int i = tid; i < 256; i += THREADS) {
+        const int k1 = i >> 4, bb = i & 15;
+        s_twm[i] = P.twiddle[2 * ((bb * k1) & 255)];                 // W256^n = W512^(2n)
     }
-    for (int i = tid; i < TW_SPLIT; i += blockDim.x) s_twr[i] = P.twiddle[i & (FFT_N - 1)];
-    for (int i = tid; i < P.frame_len; i += blockDim.x) s_win[i] = P.window[i];
-    for (int i = tid; i < P.n_mel * P.fb_stride; i += blockDim.x) s_fbw[i] = P.fb_weight[i];
-    for (int i = tid; i < P.n_mel * n_out; i += blockDim.x) {
+    for (int i = tid; i < 128; i += THREADS) s_tws[i] = P.twiddle[(i & 15) + 16 * (i >> 4)];
+    for (int i = tid; i < FFT_N; i += THREADS) s_win[i] = (i < P.frame_len) ? P.window[i] * (int_path ? 0.01 : 1.0) : 0.0;
+    for (int i = tid; i < P.n_mel * P.fb_stride; i += THREADS) s_fbw[i] = (double)P.fb_weight[i];
+    for (int i = tid; i < P.n_mel * n_out; i += THREADS) {
         const int n = i / n_out, k = i - n * n_out;
         s_dct[i] = P.dct_t[n * P.n_mel + k];
     }
-    for (int i = tid; i < P.n_mel; i += blockDim.x) { s_fbs[i] = P.fb_start[i]; s_fbl[i] = P.fb_len[i]; }
+    for (int i = tid; i < P.n_mel; i += THREADS) { s_fbs[i] = P.fb_start[i]; s_fbl[i] = P.fb_len[i]; }
+    for (int i = tid; i < MAX_SLOTS * 16; i += THREADS) s_asg[i] = -1;
+    __syncthreads();
+    if (tid == 0) {
+        // longest-processing-time assignment of the mel filters to the 16 threads of a frame (filter widths grow
+        // from 2 to ~31 bins, so a round-robin split would leave half of the lanes idle in the banded product)
+        int load[16], cnt[16];
+        unsigned long long done = 0ull;
+        for (int t = 0; t < 16; ++t) { load[t] = 0; cnt[t] = 0; }
+        for (int r = 0; r < P.n_mel; ++r) {
+            int best = -1;
+            for (int m = 0; m < P.n_mel; ++m)
+                if (!((done >> m) & 1ull) && (best < 0 || s_fbl[m] > s_fbl[best])) best = m;
+            done |= 1ull << best;
+            int tb = -1;
+            for (int t = 0; t < 16; ++t)
+                if (cnt[t] < n_slots && (tb < 0 || load[t] < load[tb])) tb = t;
+            s_asg[cnt[tb] * 16 + tb] = best;
+            load[tb] += s_fbl[best];
+            ++cnt[tb];
+        }
+    }
     __syncthreads();
 
-    double* wbase = smem + L.per_warp + warp * PER_WARP_DOUBLES;
-    double2* bufA = reinterpret_cast<double2*>(wbase);
-    double2* bufB = bufA + HALF_N;
-    double* s_pow = reinterpret_cast<double*>(bufB);     // the spectrum ends in bufA; bufB is free for the power
-    double* s_lm = wbase + 4 * HALF_N;
+    double* hbase = smem + L.per_hw + (tid >> 4) * PER_HW_DOUBLES;
+    double2* tr = reinterpret_cast<double2*>(hbase);     // [16][TR_LD] complex
+    double* s_pow = hbase;                               // aliases tr once the second DFT has read it
+    double* s_lm = hbase + 2 * 16 * TR_LD;
 
     const int64_t n_runs = (total_frames + FRAMES_PER_RUN - 1) / FRAMES_PER_RUN;
-    const int64_t warp_global = (int64_t)blockIdx.x * WARPS_PER_BLOCK + warp;
-    const int64_t warp_stride = (int64_t)gridDim.x * WARPS_PER_BLOCK;
-    constexpr int NQ = HALF_N / 32;                      // sample pairs per lane
+    const int64_t warp_global = (int64_t)blockIdx.x * (THREADS / 32) + (tid >> 5);
+    const int64_t warp_stride = (int64_t)gridDim.x * (THREADS / 32);
+    const int partner = ((16 - b) & 15) + 16 * half;     // lane holding Z[256 - k] for my Z[k]
+    const int n_a = (P.frame_len + 31) >> 5;             // rows a with at least one sample inside the frame
+    constexpr double PSCALE = 1.0 / (4.0 * FFT_N);       // the split below works on 2X
 
-    auto make_ctx = [&](int u, int64_t f) {
+    auto make_ctx = [&](int u) {
         FrameCtx c;
         c.u = u;
+        c.u_f0 = __ldg(frame_off + u);
         c.u_f1 = __ldg(frame_off + u + 1);
         c.u_s0 = __ldg(sample_off + u);
         c.u_len = __ldg(sample_off + u + 1) - c.u_s0;
-        c.s_start = (f - __ldg(frame_off + u)) * P.frame_step;
         return c;
-    };
-    auto next_ctx = [&](const FrameCtx& c, int64_t f) {          // context of frame f = previous frame + 1
-        if (f < c.u_f1) { FrameCtx n = c; n.s_start += P.frame_step; return n; }
-        int u = c.u;
-        int64_t f1 = c.u_f1;
-        while (f >= f1) { ++u; f1 = __ldg(frame_off + u + 1); }
-        return make_ctx(u, f);
-    };
-    // raw samples of one frame: lane holds pairs (x[2m], x[2m+1]), m = lane + 32 q; out-of-range samples read as 0
-    // (kept in the PCM type: converting here would make the prefetch wait for its own loads)
-    auto fetch = [&](const FrameCtx& c, PcmT* xe, PcmT* xo, PcmT& xlead) {
-        const PcmT* x = pcm + c.u_s0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int n0 = 2 * (lane + 32 * q);
-            const int64_t i0 = c.s_start + n0;
-            xe[q] = (n0 < P.frame_len && i0 < c.u_len) ? __ldg(x + i0) : PcmT(0);
-            xo[q] = (n0 + 1 < P.frame_len && i0 + 1 < c.u_len) ? __ldg(x + i0 + 1) : PcmT(0);
-        }
-        // the sample before the frame (needed by lane 0, q = 0)
-        xlead = (lane == 0 && c.s_start >= 1 && c.s_start - 1 < c.u_len) ? __ldg(x + c.s_start - 1) : PcmT(0);
     };
 
     for (int64_t run = warp_global; run < n_runs; run += warp_stride) {
         const int64_t f_begin = run * FRAMES_PER_RUN;
         const int64_t f_end = min(f_begin + (int64_t)FRAMES_PER_RUN, total_frames);
-        FrameCtx nxt = make_ctx(find_utt(frame_off, n_utt, f_begin), f_begin);
-        PcmT pe[NQ], po[NQ], plead;
-        fetch(nxt, pe, po, plead);
-        int acc_u = nxt.u;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};   // running column sums of utterance acc_u: coefficient (lane & 15) + 16 i
-        for (int64_t f = f_begin; f < f_end; ++f) {
-            const FrameCtx cur = nxt;
-            float xe[NQ], xo[NQ];                    // int16 and float32 PCM are both exact in float
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) { xe[q] = (float)pe[q]; xo[q] = (float)po[q]; }
-            const float xlead = (float)plead;
-            if (f + 1 < f_end) {                      // software prefetch of the next frame's samples
-                nxt = next_ctx(cur, f + 1);
-                fetch(nxt, pe, po, plead);
+        int64_t f = f_begin + half;
+        FrameCtx cur = make_ctx(find_utt(frame_off, n_utt, min(f, f_end - 1)));
+        int acc_u = cur.u;
+        double acc[MAX_SLOTS] = {0.0, 0.0, 0.0, 0.0};    // running column sums of utterance acc_u: coefficient b + 16 i
+        for (; f - half < f_end; f += 2) {                // warp-uniform trip count; `act` masks the odd tail
+            const bool act = f < f_end;
+            if (act && f >= cur.u_f1) {                   // walked into another utterance
+                int u = cur.u;
+                int64_t f1 = cur.u_f1;
+                while (f >= f1) { ++u; f1 = __ldg(frame_off + u + 1); }
+                cur = make_ctx(u);
             }
-            if (cur.u != acc_u) {                     // crossed into another utterance: flush its column sums
-                if (lane < 16) {
+            if (act && cur.u != acc_u) {                  // flush the column sums of the utterance just left
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (lane + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + lane + 16 * i, acc[i]);
+                for (int i = 0; i < MAX_SLOTS; ++i) {
+                    if (b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
+                    acc[i] = 0.0;
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = 0.0;
                 acc_u = cur.u;
             }
-            // ---- pre-emphasis (mfcc.py:63) + window (mfcc.py:138), packed as z[m] = (xw[2m], xw[2m+1])
-            float carry = xlead;                      // x[2m - 1] for lane 0
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const int m = lane + 32 * q;
-                const int n0 = 2 * m;
-                float xm1 = __shfl_up_sync(0xffffffffu, xo[q], 1);
-                if (lane == 0) xm1 = carry;
-                carry = __shfl_sync(0xffffffffu, xo[q], 31);
-                double2 z = make_double2(0.0, 0.0);
-                if (n0 < P.frame_len) {
-                    const int64_t i0 = cur.s_start + n0;
-                    // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
-                    const double y0 = (i0 < cur.u_len) ? ((i0 == 0) ? (double)xe[q] : (double)xe[q] - P.hpf_alpha * (double)xm1) : 0.0;
-                    const double y1 = (i0 + 1 < cur.u_len) ? (double)xo[q] - P.hpf_alpha * (double)xe[q] : 0.0;
-                    z.x = y0 * s_win[n0];
-                    z.y = (n0 + 1 < P.frame_len) ? y1 * s_win[n0 + 1] : 0.0;
-                }
-                bufA[m] = z;
-            }
-            __syncwarp();
-            // ---- 256-point complex FFT, radix-4 Stockham, 4 stages
-            double2* src = bufA;
-            double2* dst = bufB;
-#pragma unroll
-            for (int st = 0; st < 4; ++st) {
-                const int Ns = 1 << (2 * st);
-                const double2* tw = s_tws + tw_stage_off(st);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = lane + 32 * h;
-                    const int k = j & (Ns - 1);
-                    double2 v0 = src[j], v1 = src[j + 64], v2 = src[j + 128], v3 = src[j + 192];
-                    if (st > 0) {
-                        v1 = cmul(v1, tw[k]);
-                        v2 = cmul(v2, tw[Ns + k]);
-                        v3 = cmul(v3, tw[2 * Ns + k]);
-                    }
-                    const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y);
-                    const double2 a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
-                    const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y);
-                    const double2 a3 = make_double2(v1.y - v3.y, -(v1.x - v3.x));   // (v1-v3) * (-i)
-                    const int j0 = ((j - k) << 2) + k;
-                    dst[j0] = make_double2(a0.x + a2.x, a0.y + a2.y);
-                    dst[j0 + Ns] = make_double2(a1.x + a3.x, a1.y + a3.y);
-                    dst[j0 + 2 * Ns] = make_double2(a0.x - a2.x, a0.y - a2.y);
-                    dst[j0 + 3 * Ns] = make_double2(a1.x - a3.x, a1.y - a3.y);
-                }
-                __syncwarp();
-                double2* t = src; src = dst; dst = t;
-            }
-            // after 4 stages the spectrum Z is in `src` (== bufA)
-            // ---- real-FFT split + power spectrum |X|^2 / 512   (mfcc.py:141-142)
-            double esum = 0.0;
-#pragma unroll
-            for (int q = 0; q <= NQ; ++q) {
-                const int k = lane + 32 * q;
-                if (k <= HALF_N) {
-                    const double2 zk = src[k & (HALF_N - 1)];
-                    const double2 zr = src[(HALF_N - k) & (HALF_N - 1)];
-                    const double2 E = make_double2(0.5 * (zk.x + zr.x), 0.5 * (zk.y - zr.y));
-                    const double2 O = make_double2(0.5 * (zk.y + zr.y), -0.5 * (zk.x - zr.x));  // -(i/2)(zk - conj zr)
-                    const double2 wo = cmul(s_twr[k], O);
-                    const double re = E.x + wo.x, im = E.y + wo.y;
-                    const double pw = (re * re + im * im) * (1.0 / FFT_N);
-                    s_pow[k] = pw;
-                    esum += pw;
-                    if (power_out) power_out[f * (HALF_N + 1) + k] = (float)pw;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
-            __syncwarp();
-            // ---- mel filter bank (banded, mfcc.py:148): 4 lanes share a filter, eps substitution (mfcc.py:149),
-            //      20 log10 (mfcc.py:150) spread over the lanes
+            // ---- pre-emphasis (mfcc.py:63) + framing (utils.py:119-130) + window (mfcc.py:138): z[16a+b], a = 0..15
+            double2 v[16];
             {
-                const int grp = lane >> 2, sub = lane & 3;
-                const unsigned gmask = 0xFu << (lane & ~3);          // trip counts differ between groups when n_mel % 8 != 0
-                for (int i = 0; grp + 8 * i < P.n_mel; ++i) {
-                    const int m = grp + 8 * i;
-                    const int s = s_fbs[m], len = s_fbl[m];
-                    const float* w = s_fbw + m * P.fb_stride;
-                    double e = 0.0;
-                    for (int t = sub; t < len; t += 4) e = fma((double)w[t], s_pow[s + t], e);
-                    e += __shfl_xor_sync(gmask, e, 1);
-                    e += __shfl_xor_sync(gmask, e, 2);
-                    if (sub == 0) s_lm[m] = e;
+                const int64_t s_start = (f - cur.u_f0) * P.frame_step;          // first sample of the frame in its utterance
+                const PcmT* x = pcm + cur.u_s0 + s_start;
+                const int64_t rem = act ? (cur.u_len - s_start) : 0;            // samples from the frame origin on
+                const bool lead = s_start > 0;                                  // x[-1] exists
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    v[a] = make_double2(0.0, 0.0);
+                    if (a < n_a) {
+                        const int n0 = 32 * a + 2 * b;
+                        const bool ok0 = n0 < rem, ok1 = n0 + 1 < rem;
+                        PcmT xm = PcmT(0), x0 = PcmT(0), x1 = PcmT(0);
+                        if (ok0) {
+                            x0 = __ldg(x + n0);
+                            if (n0 > 0 || lead) xm = __ldg(x + n0 - 1);
+                        }
+                        if (ok1) x1 = __ldg(x + n0 + 1);
+                        double y0, y1;
+                        if (int_path) {
+                            // y = x[t] - (q/100) x[t-1] = (100 x[t] - q x[t-1]) / 100, exact in int32; 1/100 is in s_win
+                            const int i0 = 100 * (int)x0 - P.hpf_q * (int)xm;
+                            const int i1 = ok1 ? 100 * (int)x1 - P.hpf_q * (int)x0 : 0;
+                            y0 = (double)i0;
+                            y1 = (double)i1;
+                        } else {
+                            // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
+                            y0 = (double)x0 - P.hpf_alpha * (double)xm;
+                            y1 = ok1 ? (double)x1 - P.hpf_alpha * (double)x0 : 0.0;
+                        }
+                        v[a] = make_double2(y0 * s_win[n0], y1 * s_win[n0 + 1]);
+                    }
                 }
-                __syncwarp();
-                for (int m = lane; m < P.n_mel; m += 32) {                // all lanes take logs: 2 rounds instead of 5
-                    double e = s_lm[m];
+            }
+            // ---- 256-point complex FFT as 16 x 16 (mfcc.py:141)
+            fft16(v);                                                  // over a  -> Y_b[k1] in v[NAT16(k1)]
+            tr[b] = v[0];                                              // k1 = 0: twiddle 1
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) tr[k1 * TR_LD + b] = cmul(v[NAT16(k1)], s_twm[k1 * 16 + b]);
+            __syncwarp();
+#pragma unroll
+            for (int bb = 0; bb < 16; ++bb) v[bb] = tr[b * TR_LD + bb];
+            fft16(v);                                                  // over b  -> Z[b + 16 k2] in v[NAT16(k2)]
+            // ---- real-FFT split + power spectrum |X|^2 / 512 (mfcc.py:141-142), bins k = b + 16 k2 and 256 - k
+            double esum = 0.0;
+            __syncwarp();                                              // every lane has read its row of tr
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const double2 zk = v[NAT16(k2)];
+                double2 zr = shfl_c(v[NAT16(15 - k2)], partner);
+                if (b == 0) zr = v[NAT16((16 - k2) & 15)];             // lane 0 pairs 16 k2 with 256 - 16 k2, both its own
+                const double2 E = make_double2(zk.x + zr.x, zk.y - zr.y);        // 2 E[k]
+                const double2 O = make_double2(zk.y + zr.y, zr.x - zk.x);        // 2 O[k]
+                const double2 T = cmul(s_tws[k2 * 16 + b], O);
+                const double px = E.x + T.x, py = E.y + T.y;           // 2 X[k]
+                const double qx = E.x - T.x, qy = E.y - T.y;           // conj(2 X[256-k])
+                const double pk = px * px + py * py, pr = qx * qx + qy * qy;
+                s_pow[b + 16 * k2] = pk;
+                s_pow[HALF_N - b - 16 * k2] = pr;
+                esum += pk + pr;
+            }
+            {
+                const double2 z8 = v[NAT16(8)];                        // bin 128 (lane 0): X = conj(Z[128])
+                const double p8 = 4.0 * (z8.x * z8.x + z8.y * z8.y);
+                if (b == 0) { s_pow[128] = p8; esum += p8; }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+            __syncwarp();
+            if (power_out && act)
+                for (int k = b; k <= HALF_N; k += 16) power_out[f * (HALF_N + 1) + k] = (float)(s_pow[k] * PSCALE);
+            // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
+            for (int s = 0; s < n_slots; ++s) {
+                const int m = s_asg[s * 16 + b];
+                if (m >= 0) {
+                    const int k0 = s_fbs[m], len = s_fbl[m];
+                    const double* w = s_fbw + m * P.fb_stride;
+                    double e = 0.0;
+                    for (int t = 0; t < len; ++t) e = fma(w[t], s_pow[k0 + t], e);
+                    e *= PSCALE;
                     if (e == 0.0) e = 2.220446049250313e-16;              // np.finfo(float).eps
                     s_lm[m] = 8.685889638065035 * log(e);                 // 20 log10(e) = 20/ln(10) * ln(e)
                 }
             }
             __syncwarp();
-            // ---- DCT-II ortho (mfcc.py:152): lane = (half of n, coefficient k mod 16)
-            {
-                const int kk = lane & 15, part = lane >> 4;
-                const int nh = (P.n_mel + 1) >> 1;
-                const int n_lo = part * nh, n_hi = min(P.n_mel, n_lo + nh);
+            // ---- DCT-II ortho (mfcc.py:152): thread b produces coefficients b, b+16, ...
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int k = kk + 16 * i;
+            for (int i = 0; i < MAX_SLOTS; ++i) {
+                const int k = b + 16 * i;
+                if (k < n_out) {
                     double c = 0.0;
-                    if (k < n_out)
-                        for (int n = n_lo; n < n_hi; ++n) c = fma(s_dct[n * n_out + k], s_lm[n], c);
-                    c += __shfl_xor_sync(0xffffffffu, c, 16);
-                    if (k < n_out && part == 0) {
+                    for (int n = 0; n < P.n_mel; ++n) c = fma(s_dct[n * n_out + k], s_lm[n], c);
+                    if (act) {
                         acc[i] += c;
                         // raw static row: cepstra 1..n_ceps then ln(sum power) (mfcc.py:158-160)
                         if (k >= 1 && k <= P.n_ceps) raw[f * RAW_LD + (k - 1)] = (float)c;
@@ -301,14 +325,12 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                     }
                 }
             }
-            if (lane == 31) raw[f * RAW_LD + P.n_ceps] = (float)log(esum);
-            __syncwarp();
+            if (b == 15 && act) raw[f * RAW_LD + P.n_ceps] = (float)log(esum * PSCALE);
+            __syncwarp();                                              // s_pow / s_lm are rewritten by the next frame
         }
-        if (lane < 16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (lane + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + lane + 16 * i, acc[i]);
-        }
+        for (int i = 0; i < MAX_SLOTS; ++i)
+            if (b + 16 * i < n_out && acc[i] != 0.0) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
     }
 }
 
@@ -442,22 +464,27 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     MfccDev P;
     P.frame_len = tb->frame_len; P.frame_step = tb->frame_step; P.n_mel = tb->n_mel; P.n_ceps = tb->n_ceps;
     P.fb_stride = tb->fb_stride; P.hpf_alpha = tb->hpf_alpha; P.window = tb->window;
+    {
+        const double q = tb->hpf_alpha * 100.0;
+        const long qi = lround(q);
+        P.hpf_q = (fabs(q - (double)qi) < 1e-9 && qi >= 0 && qi <= 100) ? (int)qi : -1;
+    }
     P.twiddle = (const double2*)tb->twiddle; P.fb_start = tb->fb_start; P.fb_len = tb->fb_len;
     P.fb_weight = tb->fb_weight; P.dct_t = tb->dct_t;
 
-    const SmemLayout L = smem_layout(P.frame_len, P.n_mel, P.fb_stride, ceps_out ? P.n_mel : P.n_ceps + 1);
+    const SmemLayout L = smem_layout(P.n_mel, P.fb_stride, ceps_out ? P.n_mel : P.n_ceps + 1);
     const size_t smem = (size_t)L.total * sizeof(double);
     const int64_t n_runs = ceil_div(total_frames, FRAMES_PER_RUN);
-    const int blocks_per_sm = std::max(1, (int)((220 * 1024) / smem));
-    int grid = (int)std::min<int64_t>(ceil_div(n_runs, WARPS_PER_BLOCK), (int64_t)sm_count() * blocks_per_sm);
+    const int blocks_per_sm = std::max(1, std::min(2, (int)((226 * 1024) / (smem + 1024))));
+    int grid = (int)std::min<int64_t>(ceil_div(n_runs, THREADS / 32), (int64_t)sm_count() * blocks_per_sm);
     if (grid < 1) grid = 1;
     if (pcm_dtype == LNASR_DT_I16) {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mfcc_frames_kernel<int16_t><<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(
+        mfcc_frames_kernel<int16_t><<<grid, THREADS, smem, stream>>>(
             (const int16_t*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, power_out, ceps_out);
     } else {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mfcc_frames_kernel<float><<<grid, WARPS_PER_BLOCK * 32, smem, stream>>>(
+        mfcc_frames_kernel<float><<<grid, THREADS, smem, stream>>>(
             (const float*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, power_out, ceps_out);
     }
     LNASR_LAUNCH_CHECK();
