@@ -22,12 +22,10 @@ constexpr int FFT_N = 512;
 constexpr int HALF_N = 256;
 constexpr int MAX_MEL = 64;
 constexpr int RAW_LD = 16;            // raw static row: 12 cepstra + energy, padded to 16 floats
-constexpr int THREADS = 256;          // 8 warps = 16 half-warps; one frame per half-warp at a time
-constexpr int HW_PER_BLOCK = THREADS / 16;
+constexpr int MAX_THREADS = 512;      // 16 warps = 32 half-warps per SM (one block per SM); one frame per half-warp at a time
 constexpr int FRAMES_PER_RUN = 32;    // consecutive frames a warp walks (its two halves take alternate frames)
 constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
 constexpr int P_LD = 264;             // power spectrum of one frame (257 doubles), aliases the transpose buffer
-constexpr int PER_HW_DOUBLES = 2 * 16 * TR_LD + MAX_MEL;     // transpose buffer | log-mel[64]
 constexpr int MAX_SLOTS = MAX_MEL / 16;
 
 struct MfccDev {
@@ -86,24 +84,28 @@ __device__ __forceinline__ double2 shfl_c(double2 v, int src) {
 
 // shared memory carve-up (in doubles)
 struct SmemLayout {
-    int tw_mid, tw_split, window, dct, fb_w, fb_meta, per_hw, total;
+    int tw_mid, tw_split, window, logtab, dct, fb_w, fb_meta, per_hw, per_hw_doubles, stage_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int n_dct_cols) {
+constexpr int STAGE_SAMPLES = FFT_N + 8;      // x[-1 .. 32 n_a + 1) plus alignment slack
+__host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int n_dct_cols, int pcm_bytes, int n_hw) {
     SmemLayout L;
     int o = 0;
     L.tw_mid = o;   o += 2 * 256;                         // W256^(b k1) at [k1*16 + b]
     L.tw_split = o; o += 2 * 128;                         // W512^(b + 16 k2) at [k2*16 + b], k2 < 8
     L.window = o;   o += FFT_N;                           // window (x 1/100 on the integer path), zero past frame_len
+    L.logtab = o;   o += 2 * 128;                         // (1/c_i, log c_i) of the table-driven log
     L.dct = o;      o += n_mel * n_dct_cols;              // [n][k < n_dct_cols]
     L.fb_w = o;     o += n_mel * fb_stride;               // double weights
-    L.fb_meta = o;  o += (3 * MAX_MEL) / 2;               // ints: fb_start[64] | fb_len[64] | assign[MAX_SLOTS*16]
+    L.fb_meta = o;  o += (4 * MAX_MEL) / 2 + 2;           // ints: fb_start[64] | fb_len[64] | assign[64] | order[64] | flags
     o = (o + 1) & ~1;
     L.per_hw = o;
-    L.total = o + HW_PER_BLOCK * PER_HW_DOUBLES;
+    L.stage_off = 2 * 16 * TR_LD + MAX_MEL;               // transpose buffer | log-mel[64] | sample stage
+    L.per_hw_doubles = (L.stage_off + (STAGE_SAMPLES * pcm_bytes + 7) / 8 + 1) & ~1;
+    L.total = o + n_hw * L.per_hw_doubles;
     return L;
 }
 
-// where a frame lives: utterance, its sample range, first sample of the frame
+// where a frame lives: utterance, its sample range
 struct FrameCtx {
     int u;
     int64_t u_f0, u_f1;  // first frame of this / of the next utterance
@@ -111,85 +113,150 @@ struct FrameCtx {
     int64_t u_len;       // samples in the utterance
 };
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// ln(x) for the log-mel energies: x = 2^E m, m in [1,2); table entry i = top 7 mantissa bits holds c = 1/(1+(i+1/2)/128)
+// and -ln c; r = m c - 1 has |r| < 2^-8 and ln(1+r) is a degree-6 polynomial (error r^7/7 < 3e-18).  8 DFMA instead
+// of the ~25 of log().  Zero, subnormal, inf and NaN go through log().
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+    if (!(x >= 1e-300 && x <= 1e300)) return log(x);
+    const int hi = __double2hiint(x);
+    const int E = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 ct = tab[(hi >> 13) & 127];
+    const double r = fma(m, ct.x, -1.0);
+    double q = -1.0 / 6.0;
+    q = fma(q, r, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    q = fma(q, r, 1.0);
+    return fma(r, q, fma((double)E, 0.69314718055994530942, ct.y));
+}
+
 // The whole per-frame chain runs in float64.  The reference is float64 (mfcc.py), and the features are small
 // differences of ~200 dB log-mel values (mean normalisation, deltas) whose low-energy bands sit up to 90 dB below
 // the frame's peak: an fp32 FFT leaves ~1e-4 relative error in exactly those bands (measured), i.e. above the
 // 1e-4 parity bar after the DCT and the delta-deltas.
 //
-// Mapping: 16 threads (a half-warp) own one frame.  The 512-point real FFT is a 256-point complex FFT of the packed
-// signal z[m] = (xw[2m], xw[2m+1]), done as 16 x 16: thread b holds z[16a + b], a = 0..15, in registers, runs a
-// 16-point DFT over a, multiplies by W256^(b k1), transposes once through shared memory (the only shared-memory pass
-// of the FFT: 8 KB per frame instead of the ~70 KB of a stage-by-stage shared-memory FFT), runs the second 16-point
-// DFT over b.  Thread k1 then holds Z[k1 + 16 k2]; the real-FFT split pairs bin k with 256-k, which lives in lane
-// 16-k1 -> one shuffle per pair.
+// Mapping: 16 threads (a half-warp) own one frame; the two halves of a warp take alternate frames of a run of 32.
+// * Samples reach the SM by cp.async into a per-half-warp stage one frame ahead (no registers held across the
+//   latency), and are read back as three 2-byte loads per sample pair.
+// * The 512-point real FFT is a 256-point complex FFT of the packed signal z[m] = (xw[2m], xw[2m+1]), done as
+//   16 x 16: thread b holds z[16a + b], a = 0..15, in registers, runs a 16-point DFT over a, multiplies by
+//   W256^(b k1), transposes once through shared memory (the only shared-memory pass of the FFT: 8 KB per frame
+//   instead of the ~70 KB of a stage-by-stage shared-memory FFT), runs the second 16-point DFT over b.  Thread k1
+//   then holds Z[k1 + 16 k2]; the real-FFT split pairs bin k with 256-k, which lives in lane 16-k1 -> one shuffle
+//   per pair.
+// * Mel filters are dealt to the 16 threads longest-first (balanced banded product); each thread takes the log of
+//   its own filters; the DCT is one thread per coefficient.
 template <typename PcmT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sample_off,
                    const int64_t* __restrict__ frame_off, int n_utt, int64_t total_frames, MfccDev P,
                    float* __restrict__ raw, double* __restrict__ colsum, float* __restrict__ power_out,
                    float* __restrict__ ceps_raw_out) {
     extern __shared__ __align__(16) double smem[];
     constexpr bool kIntPcm = (sizeof(PcmT) == 2);
+    const int n_threads = blockDim.x;
     const bool full_ceps = (ceps_raw_out != nullptr);
     const int n_out = full_ceps ? P.n_mel : (P.n_ceps + 1);   // cepstral coefficients 0..n_out-1 computed
-    const SmemLayout L = smem_layout(P.n_mel, P.fb_stride, n_out);
+    const SmemLayout L = smem_layout(P.n_mel, P.fb_stride, n_out, (int)sizeof(PcmT), n_threads >> 4);
     double2* s_twm = reinterpret_cast<double2*>(smem + L.tw_mid);
     double2* s_tws = reinterpret_cast<double2*>(smem + L.tw_split);
     double* s_win = smem + L.window;
+    double2* s_log = reinterpret_cast<double2*>(smem + L.logtab);
     double* s_dct = smem + L.dct;
     double* s_fbw = smem + L.fb_w;
     int* s_fbs = reinterpret_cast<int*>(smem + L.fb_meta);
     int* s_fbl = s_fbs + MAX_MEL;
     int* s_asg = s_fbl + MAX_MEL;
+    int* s_ord = s_asg + MAX_MEL;
+    int* s_flag = s_ord + MAX_MEL;
     const int tid = threadIdx.x, lane = tid & 31, b = lane & 15, half = lane >> 4;
     const bool int_path = kIntPcm && P.hpf_q >= 0;
     const int n_slots = (P.n_mel + 15) >> 4;
-    for (int i = tid; i < 256; i += THREADS) {
+    for (int i = tid; i < 256; i += n_threads) {
         const int k1 = i >> 4, bb = i & 15;
         s_twm[i] = P.twiddle[2 * ((bb * k1) & 255)];                 // W256^n = W512^(2n)
     }
-    for (int i = tid; i < 128; i += THREADS) s_tws[i] = P.twiddle[(i & 15) + 16 * (i >> 4)];
-    for (int i = tid; i < FFT_N; i += THREADS) s_win[i] = (i < P.frame_len) ? P.window[i] * (int_path ? 0.01 : 1.0) : 0.0;
-    for (int i = tid; i < P.n_mel * P.fb_stride; i += THREADS) s_fbw[i] = (double)P.fb_weight[i];
-    for (int i = tid; i < P.n_mel * n_out; i += THREADS) {
+    for (int i = tid; i < 128; i += n_threads) {
+        s_tws[i] = P.twiddle[(i & 15) + 16 * (i >> 4)];
+        const double c = 1.0 / (1.0 + ((double)i + 0.5) / 128.0);
+        s_log[i] = make_double2(c, -log(c));
+    }
+    for (int i = tid; i < FFT_N; i += n_threads) s_win[i] = (i < P.frame_len) ? P.window[i] * (int_path ? 0.01 : 1.0) : 0.0;
+    for (int i = tid; i < P.n_mel * P.fb_stride; i += n_threads) s_fbw[i] = (double)P.fb_weight[i];
+    for (int i = tid; i < P.n_mel * n_out; i += n_threads) {
         const int n = i / n_out, k = i - n * n_out;
         s_dct[i] = P.dct_t[n * P.n_mel + k];
     }
-    for (int i = tid; i < P.n_mel; i += THREADS) { s_fbs[i] = P.fb_start[i]; s_fbl[i] = P.fb_len[i]; }
-    for (int i = tid; i < MAX_SLOTS * 16; i += THREADS) s_asg[i] = -1;
+    for (int i = tid; i < P.n_mel; i += n_threads) { s_fbs[i] = P.fb_start[i]; s_fbl[i] = P.fb_len[i]; }
+    for (int i = tid; i < MAX_MEL; i += n_threads) s_asg[i] = -1;
     __syncthreads();
-    if (tid == 0) {
-        // longest-processing-time assignment of the mel filters to the 16 threads of a frame (filter widths grow
-        // from 2 to ~31 bins, so a round-robin split would leave half of the lanes idle in the banded product)
-        int load[16], cnt[16];
-        unsigned long long done = 0ull;
-        for (int t = 0; t < 16; ++t) { load[t] = 0; cnt[t] = 0; }
-        for (int r = 0; r < P.n_mel; ++r) {
-            int best = -1;
-            for (int m = 0; m < P.n_mel; ++m)
-                if (!((done >> m) & 1ull) && (best < 0 || s_fbl[m] > s_fbl[best])) best = m;
-            done |= 1ull << best;
-            int tb = -1;
-            for (int t = 0; t < 16; ++t)
-                if (cnt[t] < n_slots && (tb < 0 || load[t] < load[tb])) tb = t;
-            s_asg[cnt[tb] * 16 + tb] = best;
-            load[tb] += s_fbl[best];
-            ++cnt[tb];
+    // longest-processing-time assignment of the mel filters to the 16 threads of a frame (filter widths grow from 2
+    // to ~31 bins, so a round-robin split would leave half of the lanes idle in the banded product).
+    // Step 1 (parallel): rank of every filter by descending width.
+    if (tid < P.n_mel) {
+        const int len = s_fbl[tid];
+        int r = 0;
+        for (int m = 0; m < P.n_mel; ++m) {
+            const int lm = s_fbl[m];
+            r += (lm > len) || (lm == len && m < tid);
         }
+        s_ord[r] = tid;
     }
     __syncthreads();
+    // Step 2 (one thread, keys = (full?, load, thread) packed in registers): greedy placement.
+    if (tid == 0) {
+        int key[16], cnt[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { key[t] = t; cnt[t] = 0; }
+        for (int r = 0; r < P.n_mel; ++r) {
+            const int m = s_ord[r];
+            int best = key[0];
+#pragma unroll
+            for (int t = 1; t < 16; ++t) best = min(best, key[t]);
+            const int tb = best & 15;
+            const int add = s_fbl[m] << 4;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (t == tb) {
+                    s_asg[cnt[t] * 16 + t] = m;
+                    ++cnt[t];
+                    key[t] += add;
+                    if (cnt[t] >= n_slots) key[t] |= 1 << 28;
+                }
+        }
+        // the log of the frame energy rides in a free position of the last slot when there is one
+        int epos = -1;
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+            if (epos < 0 && cnt[t] < n_slots) epos = (n_slots - 1) * 16 + t;
+        if (epos >= 0) s_asg[epos] = -2;
+        s_flag[0] = epos;
+    }
+    __syncthreads();
+    const bool energy_sep = s_flag[0] < 0;
 
-    double* hbase = smem + L.per_hw + (tid >> 4) * PER_HW_DOUBLES;
+    double* hbase = smem + L.per_hw + (tid >> 4) * L.per_hw_doubles;
     double2* tr = reinterpret_cast<double2*>(hbase);     // [16][TR_LD] complex
     double* s_pow = hbase;                               // aliases tr once the second DFT has read it
     double* s_lm = hbase + 2 * 16 * TR_LD;
+    PcmT* stage = reinterpret_cast<PcmT*>(hbase + L.stage_off);
 
     const int64_t n_runs = (total_frames + FRAMES_PER_RUN - 1) / FRAMES_PER_RUN;
-    const int64_t warp_global = (int64_t)blockIdx.x * (THREADS / 32) + (tid >> 5);
-    const int64_t warp_stride = (int64_t)gridDim.x * (THREADS / 32);
+    const int64_t warp_global = (int64_t)blockIdx.x * (n_threads >> 5) + (tid >> 5);
+    const int64_t warp_stride = (int64_t)gridDim.x * (n_threads >> 5);
     const int partner = ((16 - b) & 15) + 16 * half;     // lane holding Z[256 - k] for my Z[k]
     const int n_a = (P.frame_len + 31) >> 5;             // rows a with at least one sample inside the frame
     constexpr double PSCALE = 1.0 / (4.0 * FFT_N);       // the split below works on 2X
+    constexpr int SPW = 4 / (int)sizeof(PcmT);           // samples per 4-byte word
+    const int n_words = (32 * n_a + 2 + SPW) / SPW + 1;  // words covering x[-1 .. 32 n_a] at any alignment
+    const uintptr_t pcm_lo = (uintptr_t)pcm & ~(uintptr_t)3;
+    const uintptr_t pcm_hi = ((uintptr_t)(pcm + __ldg(sample_off + n_utt)) - 1) & ~(uintptr_t)3;
 
     auto make_ctx = [&](int u) {
         FrameCtx c;
@@ -200,137 +267,186 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         c.u_len = __ldg(sample_off + u + 1) - c.u_s0;
         return c;
     };
-
-    for (int64_t run = warp_global; run < n_runs; run += warp_stride) {
-        const int64_t f_begin = run * FRAMES_PER_RUN;
-        const int64_t f_end = min(f_begin + (int64_t)FRAMES_PER_RUN, total_frames);
-        int64_t f = f_begin + half;
-        FrameCtx cur = make_ctx(find_utt(frame_off, n_utt, min(f, f_end - 1)));
-        int acc_u = cur.u;
-        double acc[MAX_SLOTS] = {0.0, 0.0, 0.0, 0.0};    // running column sums of utterance acc_u: coefficient b + 16 i
-        for (; f - half < f_end; f += 2) {                // warp-uniform trip count; `act` masks the odd tail
-            const bool act = f < f_end;
-            if (act && f >= cur.u_f1) {                   // walked into another utterance
-                int u = cur.u;
-                int64_t f1 = cur.u_f1;
+    // step s of this warp = pair of frames  f_pair(s), f_pair(s)+1 ; returns false past the warp's last pair (uniform)
+    FrameCtx ctx;
+    ctx.u = -1; ctx.u_f0 = 0; ctx.u_f1 = -1; ctx.u_s0 = 0; ctx.u_len = 0;
+    int64_t f = 0;
+    bool act = false;
+    int par = 0;                                         // position of x[-1] inside its 4-byte word
+    auto locate = [&](int64_t step) -> bool {
+        const int64_t run = warp_global + (step >> 4) * warp_stride;
+        const int64_t f_pair = run * FRAMES_PER_RUN + 2 * (step & 15);
+        if (run >= n_runs || f_pair >= total_frames) return false;
+        f = f_pair + half;
+        act = f < total_frames;
+        if (act) {
+            if ((step & 15) == 0 || ctx.u < 0) ctx = make_ctx(find_utt(frame_off, n_utt, f));
+            else if (f >= ctx.u_f1) {                    // walked into another utterance
+                int u = ctx.u;
+                int64_t f1 = ctx.u_f1;
                 while (f >= f1) { ++u; f1 = __ldg(frame_off + u + 1); }
-                cur = make_ctx(u);
+                ctx = make_ctx(u);
             }
-            if (act && cur.u != acc_u) {                  // flush the column sums of the utterance just left
-#pragma unroll
-                for (int i = 0; i < MAX_SLOTS; ++i) {
-                    if (b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
-                    acc[i] = 0.0;
-                }
-                acc_u = cur.u;
+        }
+        return true;
+    };
+    // asynchronous copy of the samples x[-1 ..] of frame f into the stage (4-byte words, aligned down)
+    auto issue_copy = [&]() {
+        if (act) {
+            const uintptr_t first = (uintptr_t)(pcm + ctx.u_s0 + (f - ctx.u_f0) * P.frame_step - 1);
+            const uintptr_t w0 = first & ~(uintptr_t)3;
+            par = (int)((first - w0) / sizeof(PcmT));
+            for (int j = b; j < n_words; j += 16) {
+                uintptr_t src = w0 + 4u * (uintptr_t)j;
+                src = src < pcm_lo ? pcm_lo : (src > pcm_hi ? pcm_hi : src);      // clamped words are never consumed
+                cp_async4(reinterpret_cast<char*>(stage) + 4 * j, reinterpret_cast<const void*>(src));
             }
-            // ---- pre-emphasis (mfcc.py:63) + framing (utils.py:119-130) + window (mfcc.py:138): z[16a+b], a = 0..15
-            double2 v[16];
-            {
-                const int64_t s_start = (f - cur.u_f0) * P.frame_step;          // first sample of the frame in its utterance
-                const PcmT* x = pcm + cur.u_s0 + s_start;
-                const int64_t rem = act ? (cur.u_len - s_start) : 0;            // samples from the frame origin on
-                const bool lead = s_start > 0;                                  // x[-1] exists
-#pragma unroll
-                for (int a = 0; a < 16; ++a) {
-                    v[a] = make_double2(0.0, 0.0);
-                    if (a < n_a) {
-                        const int n0 = 32 * a + 2 * b;
-                        const bool ok0 = n0 < rem, ok1 = n0 + 1 < rem;
-                        PcmT xm = PcmT(0), x0 = PcmT(0), x1 = PcmT(0);
-                        if (ok0) {
-                            x0 = __ldg(x + n0);
-                            if (n0 > 0 || lead) xm = __ldg(x + n0 - 1);
-                        }
-                        if (ok1) x1 = __ldg(x + n0 + 1);
-                        double y0, y1;
-                        if (int_path) {
-                            // y = x[t] - (q/100) x[t-1] = (100 x[t] - q x[t-1]) / 100, exact in int32; 1/100 is in s_win
-                            const int i0 = 100 * (int)x0 - P.hpf_q * (int)xm;
-                            const int i1 = ok1 ? 100 * (int)x1 - P.hpf_q * (int)x0 : 0;
-                            y0 = (double)i0;
-                            y1 = (double)i1;
-                        } else {
-                            // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
-                            y0 = (double)x0 - P.hpf_alpha * (double)xm;
-                            y1 = ok1 ? (double)x1 - P.hpf_alpha * (double)x0 : 0.0;
-                        }
-                        v[a] = make_double2(y0 * s_win[n0], y1 * s_win[n0 + 1]);
-                    }
-                }
-            }
-            // ---- 256-point complex FFT as 16 x 16 (mfcc.py:141)
-            fft16(v);                                                  // over a  -> Y_b[k1] in v[NAT16(k1)]
-            tr[b] = v[0];                                              // k1 = 0: twiddle 1
-#pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) tr[k1 * TR_LD + b] = cmul(v[NAT16(k1)], s_twm[k1 * 16 + b]);
-            __syncwarp();
-#pragma unroll
-            for (int bb = 0; bb < 16; ++bb) v[bb] = tr[b * TR_LD + bb];
-            fft16(v);                                                  // over b  -> Z[b + 16 k2] in v[NAT16(k2)]
-            // ---- real-FFT split + power spectrum |X|^2 / 512 (mfcc.py:141-142), bins k = b + 16 k2 and 256 - k
-            double esum = 0.0;
-            __syncwarp();                                              // every lane has read its row of tr
-#pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2) {
-                const double2 zk = v[NAT16(k2)];
-                double2 zr = shfl_c(v[NAT16(15 - k2)], partner);
-                if (b == 0) zr = v[NAT16((16 - k2) & 15)];             // lane 0 pairs 16 k2 with 256 - 16 k2, both its own
-                const double2 E = make_double2(zk.x + zr.x, zk.y - zr.y);        // 2 E[k]
-                const double2 O = make_double2(zk.y + zr.y, zr.x - zk.x);        // 2 O[k]
-                const double2 T = cmul(s_tws[k2 * 16 + b], O);
-                const double px = E.x + T.x, py = E.y + T.y;           // 2 X[k]
-                const double qx = E.x - T.x, qy = E.y - T.y;           // conj(2 X[256-k])
-                const double pk = px * px + py * py, pr = qx * qx + qy * qy;
-                s_pow[b + 16 * k2] = pk;
-                s_pow[HALF_N - b - 16 * k2] = pr;
-                esum += pk + pr;
-            }
-            {
-                const double2 z8 = v[NAT16(8)];                        // bin 128 (lane 0): X = conj(Z[128])
-                const double p8 = 4.0 * (z8.x * z8.x + z8.y * z8.y);
-                if (b == 0) { s_pow[128] = p8; esum += p8; }
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
-            __syncwarp();
-            if (power_out && act)
-                for (int k = b; k <= HALF_N; k += 16) power_out[f * (HALF_N + 1) + k] = (float)(s_pow[k] * PSCALE);
-            // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
-            for (int s = 0; s < n_slots; ++s) {
-                const int m = s_asg[s * 16 + b];
-                if (m >= 0) {
-                    const int k0 = s_fbs[m], len = s_fbl[m];
-                    const double* w = s_fbw + m * P.fb_stride;
-                    double e = 0.0;
-                    for (int t = 0; t < len; ++t) e = fma(w[t], s_pow[k0 + t], e);
-                    e *= PSCALE;
-                    if (e == 0.0) e = 2.220446049250313e-16;              // np.finfo(float).eps
-                    s_lm[m] = 8.685889638065035 * log(e);                 // 20 log10(e) = 20/ln(10) * ln(e)
-                }
-            }
-            __syncwarp();
-            // ---- DCT-II ortho (mfcc.py:152): thread b produces coefficients b, b+16, ...
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    bool more = locate(0);
+    if (more) issue_copy();
+    int acc_u = -1;
+    double acc[MAX_SLOTS] = {0.0, 0.0, 0.0, 0.0};        // running column sums of utterance acc_u: coefficient b + 16 i
+    for (int64_t step = 0; more; ++step) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (act && ctx.u != acc_u) {                      // flush the column sums of the utterance just left
 #pragma unroll
             for (int i = 0; i < MAX_SLOTS; ++i) {
-                const int k = b + 16 * i;
-                if (k < n_out) {
-                    double c = 0.0;
-                    for (int n = 0; n < P.n_mel; ++n) c = fma(s_dct[n * n_out + k], s_lm[n], c);
-                    if (act) {
-                        acc[i] += c;
-                        // raw static row: cepstra 1..n_ceps then ln(sum power) (mfcc.py:158-160)
-                        if (k >= 1 && k <= P.n_ceps) raw[f * RAW_LD + (k - 1)] = (float)c;
-                        if (full_ceps) ceps_raw_out[f * P.n_mel + k] = (float)c;
+                if (acc_u >= 0 && b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
+                acc[i] = 0.0;
+            }
+            acc_u = ctx.u;
+        }
+        // ---- pre-emphasis (mfcc.py:63) + framing (utils.py:119-130) + window (mfcc.py:138): z[16a+b], a = 0..15
+        double2 v[16];
+        {
+            const int64_t s_start = (f - ctx.u_f0) * P.frame_step;          // first sample of the frame in its utterance
+            const int64_t rem64 = act ? (ctx.u_len - s_start) : 0;          // samples from the frame origin on
+            const int rem = (int)min(rem64, (int64_t)(2 * FFT_N));
+            const bool lead = s_start > 0;                                  // x[-1] exists
+            const PcmT* sx = stage + par + 1;                               // sx[n] = x[n]
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                v[a] = make_double2(0.0, 0.0);
+                if (a < n_a) {
+                    const int n0 = 32 * a + 2 * b;
+                    const bool ok0 = n0 < rem, ok1 = n0 + 1 < rem;
+                    PcmT xm = sx[n0 - 1], x0 = sx[n0], x1 = sx[n0 + 1];
+                    if (!ok0) x0 = PcmT(0);
+                    if (!ok0 || !(n0 > 0 || lead)) xm = PcmT(0);
+                    double y0, y1;
+                    if (int_path) {
+                        // y = x[t] - (q/100) x[t-1] = (100 x[t] - q x[t-1]) / 100, exact in int32; 1/100 is in s_win
+                        const int i0 = 100 * (int)x0 - P.hpf_q * (int)xm;
+                        const int i1 = ok1 ? 100 * (int)x1 - P.hpf_q * (int)x0 : 0;
+                        y0 = (double)i0;
+                        y1 = (double)i1;
+                    } else {
+                        // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
+                        y0 = (double)x0 - P.hpf_alpha * (double)xm;
+                        y1 = ok1 ? (double)x1 - P.hpf_alpha * (double)x0 : 0.0;
                     }
+                    v[a] = make_double2(y0 * s_win[n0], y1 * s_win[n0 + 1]);
                 }
             }
-            if (b == 15 && act) raw[f * RAW_LD + P.n_ceps] = (float)log(esum * PSCALE);
-            __syncwarp();                                              // s_pow / s_lm are rewritten by the next frame
+        }
+        const int64_t f_cur = f;
+        const bool act_cur = act;
+        __syncwarp();                                                      // the stage has been read by every lane
+        more = locate(step + 1);
+        if (more) issue_copy();                                            // next frame's samples fly during this frame's math
+        // ---- 256-point complex FFT as 16 x 16 (mfcc.py:141)
+        fft16(v);                                                          // over a  -> Y_b[k1] in v[NAT16(k1)]
+        tr[b] = v[0];                                                      // k1 = 0: twiddle 1
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) tr[k1 * TR_LD + b] = cmul(v[NAT16(k1)], s_twm[k1 * 16 + b]);
+        __syncwarp();
+#pragma unroll
+        for (int bb = 0; bb < 16; ++bb) v[bb] = tr[b * TR_LD + bb];
+        fft16(v);                                                          // over b  -> Z[b + 16 k2] in v[NAT16(k2)]
+        // ---- real-FFT split + power spectrum |X|^2 / 512 (mfcc.py:141-142), bins k = b + 16 k2 and 256 - k
+        double esum = 0.0;
+        __syncwarp();                                                      // every lane has read its row of tr
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+            const double2 zk = v[NAT16(k2)];
+            double2 zr = shfl_c(v[NAT16(15 - k2)], partner);
+            if (b == 0) zr = v[NAT16((16 - k2) & 15)];                     // lane 0 pairs 16 k2 with 256 - 16 k2, both its own
+            const double2 E = make_double2(zk.x + zr.x, zk.y - zr.y);      // 2 E[k]
+            const double2 O = make_double2(zk.y + zr.y, zr.x - zk.x);      // 2 O[k]
+            const double2 T = cmul(s_tws[k2 * 16 + b], O);
+            const double px = E.x + T.x, py = E.y + T.y;                   // 2 X[k]
+            const double qx = E.x - T.x, qy = E.y - T.y;                   // conj(2 X[256-k])
+            const double pk = px * px + py * py, pr = qx * qx + qy * qy;
+            s_pow[b + 16 * k2] = pk;
+            s_pow[HALF_N - b - 16 * k2] = pr;
+            esum += pk + pr;
+        }
+        {
+            const double2 z8 = v[NAT16(8)];                                // bin 128 (lane 0): X = conj(Z[128])
+            const double p8 = 4.0 * (z8.x * z8.x + z8.y * z8.y);
+            if (b == 0) { s_pow[128] = p8; esum += p8; }
         }
 #pragma unroll
+        for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+        __syncwarp();
+        if (power_out && act_cur)
+            for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = (float)(s_pow[k] * PSCALE);
+        // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
+        for (int s = 0; s < n_slots; ++s) {
+            const int m = s_asg[s * 16 + b];
+            double e = esum;                                               // m == -2: ln of the frame energy (mfcc.py:158-160)
+            if (m >= 0) {
+                const int k0 = s_fbs[m], len = s_fbl[m];
+                const double* w = s_fbw + m * P.fb_stride;
+                const double* pw = s_pow + k0;
+                double e0 = 0.0, e1 = 0.0;
+                int t = 0;
+                for (; t + 1 < len; t += 2) {
+                    e0 = fma(w[t], pw[t], e0);
+                    e1 = fma(w[t + 1], pw[t + 1], e1);
+                }
+                if (t < len) e0 = fma(w[t], pw[t], e0);
+                e = e0 + e1;
+            }
+            e *= PSCALE;
+            if (m >= 0 && e == 0.0) e = 2.220446049250313e-16;             // np.finfo(float).eps
+            const double lg = fast_log(m == -1 ? 1.0 : e, s_log);
+            if (m >= 0) s_lm[m] = 8.685889638065035 * lg;                  // 20 log10(e) = 20/ln(10) * ln(e)
+            else if (m == -2 && act_cur) raw[f_cur * RAW_LD + P.n_ceps] = (float)lg;
+        }
+        if (energy_sep && b == 15 && act_cur) raw[f_cur * RAW_LD + P.n_ceps] = (float)log(esum * PSCALE);
+        __syncwarp();
+        // ---- DCT-II ortho (mfcc.py:152): thread b produces coefficients b, b+16, ...
+#pragma unroll
+        for (int i = 0; i < MAX_SLOTS; ++i) {
+            const int k = b + 16 * i;
+            if (k < n_out) {
+                double c0 = 0.0, c1 = 0.0;
+                int n = 0;
+                for (; n + 1 < P.n_mel; n += 2) {
+                    c0 = fma(s_dct[n * n_out + k], s_lm[n], c0);
+                    c1 = fma(s_dct[(n + 1) * n_out + k], s_lm[n + 1], c1);
+                }
+                if (n < P.n_mel) c0 = fma(s_dct[n * n_out + k], s_lm[n], c0);
+                const double c = c0 + c1;
+                if (act_cur) {
+                    acc[i] += c;
+                    // raw static row: cepstra 1..n_ceps then ln(sum power) (mfcc.py:158-160)
+                    if (k >= 1 && k <= P.n_ceps) raw[f_cur * RAW_LD + (k - 1)] = (float)c;
+                    if (full_ceps) ceps_raw_out[f_cur * P.n_mel + k] = (float)c;
+                }
+            }
+        }
+        __syncwarp();                                                      // s_pow / s_lm are rewritten by the next frame
+    }
+    if (acc_u >= 0) {
+#pragma unroll
         for (int i = 0; i < MAX_SLOTS; ++i)
-            if (b + 16 * i < n_out && acc[i] != 0.0) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
+            if (b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
     }
 }
 
@@ -472,19 +588,25 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     P.twiddle = (const double2*)tb->twiddle; P.fb_start = tb->fb_start; P.fb_len = tb->fb_len;
     P.fb_weight = tb->fb_weight; P.dct_t = tb->dct_t;
 
-    const SmemLayout L = smem_layout(P.n_mel, P.fb_stride, ceps_out ? P.n_mel : P.n_ceps + 1);
-    const size_t smem = (size_t)L.total * sizeof(double);
+    // one block per SM, as many half-warps (frames in flight) as shared memory allows, at most 32
+    const int pcm_bytes = (pcm_dtype == LNASR_DT_I16) ? 2 : 4;
+    const int n_cols = ceps_out ? P.n_mel : P.n_ceps + 1;
+    int threads = MAX_THREADS;
+    size_t smem = 0;
+    for (;; threads -= 64) {
+        smem = (size_t)smem_layout(P.n_mel, P.fb_stride, n_cols, pcm_bytes, threads / 16).total * sizeof(double);
+        if (smem <= 226 * 1024 || threads <= 64) break;
+    }
     const int64_t n_runs = ceil_div(total_frames, FRAMES_PER_RUN);
-    const int blocks_per_sm = std::max(1, std::min(2, (int)((226 * 1024) / (smem + 1024))));
-    int grid = (int)std::min<int64_t>(ceil_div(n_runs, THREADS / 32), (int64_t)sm_count() * blocks_per_sm);
+    int grid = (int)std::min<int64_t>(ceil_div(n_runs, threads / 32), (int64_t)sm_count());
     if (grid < 1) grid = 1;
     if (pcm_dtype == LNASR_DT_I16) {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mfcc_frames_kernel<int16_t><<<grid, THREADS, smem, stream>>>(
+        mfcc_frames_kernel<int16_t><<<grid, threads, smem, stream>>>(
             (const int16_t*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, power_out, ceps_out);
     } else {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mfcc_frames_kernel<float><<<grid, THREADS, smem, stream>>>(
+        mfcc_frames_kernel<float><<<grid, threads, smem, stream>>>(
             (const float*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, power_out, ceps_out);
     }
     LNASR_LAUNCH_CHECK();
