@@ -310,8 +310,13 @@ def run_ours(args):
 
 
 def launches_per_step(pipe, want_paths):
-    # mfcc_frames, mfcc_finalize, gmm (exact or tc), trellis (viterbi), [backtrace], argmax_rows
-    return 5 + (1 if want_paths else 0)
+    """Kernels of liblnasr_b200.so launched by one device-resident step."""
+    n = 3                                   # mfcc_run_index, mfcc_frames, mfcc_finalize
+    n += 2 if pipe.bank.emission == "tc" else 1          # gmm_tc_stage + gmm_tc | gmm_loglik_exact
+    n += 1                                  # trellis (N <= 32: backtrace fused into the kernel)
+    if want_paths and pipe.bank.n > 32:
+        n += 1                              # backtrace
+    return n + 1                            # argmax_rows
 
 
 def stage_times(pipe, pcm_dev, off, want_paths, reps=5):
@@ -379,7 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance groups the host->device copy is pipelined over")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="utterance groups the host->device copy is pipelined over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -23,7 +23,9 @@ constexpr int HALF_N = 256;
 constexpr int MAX_MEL = 64;
 constexpr int RAW_LD = 16;            // raw static row: 12 cepstra + energy, padded to 16 floats
 constexpr int MAX_THREADS = 512;      // 16 warps = 32 half-warps per SM (one block per SM); one frame per half-warp at a time
-constexpr int FRAMES_PER_RUN = 32;    // consecutive frames a warp walks (its two halves take alternate frames)
+constexpr int FRAMES_PER_RUN = 8;     // consecutive frames a warp walks (its two halves take alternate frames); small runs
+                                      // keep the static schedule balanced for the few-ten-thousand-frame groups of the e2e path
+constexpr int STEPS_PER_RUN = FRAMES_PER_RUN / 2;
 constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
 constexpr int P_LD = 264;             // power spectrum of one frame (257 doubles), aliases the transpose buffer
 constexpr int MAX_SLOTS = MAX_MEL / 16;
@@ -156,8 +158,8 @@ template <typename PcmT>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sample_off,
                    const int64_t* __restrict__ frame_off, int n_utt, int64_t total_frames, MfccDev P,
-                   float* __restrict__ raw, double* __restrict__ colsum, float* __restrict__ power_out,
-                   float* __restrict__ ceps_raw_out) {
+                   float* __restrict__ raw, double* __restrict__ colsum, const int* __restrict__ run_utt,
+                   float* __restrict__ power_out, float* __restrict__ ceps_raw_out) {
     extern __shared__ __align__(16) double smem[];
     constexpr bool kIntPcm = (sizeof(PcmT) == 2);
     const int n_threads = blockDim.x;
@@ -274,14 +276,14 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     bool act = false;
     int par = 0;                                         // position of x[-1] inside its 4-byte word
     auto locate = [&](int64_t step) -> bool {
-        const int64_t run = warp_global + (step >> 4) * warp_stride;
-        const int64_t f_pair = run * FRAMES_PER_RUN + 2 * (step & 15);
+        const int64_t run = warp_global + (step / STEPS_PER_RUN) * warp_stride;
+        const int64_t f_pair = run * FRAMES_PER_RUN + 2 * (step % STEPS_PER_RUN);
         if (run >= n_runs || f_pair >= total_frames) return false;
         f = f_pair + half;
         act = f < total_frames;
         if (act) {
-            if ((step & 15) == 0 || ctx.u < 0) ctx = make_ctx(find_utt(frame_off, n_utt, f));
-            else if (f >= ctx.u_f1) {                    // walked into another utterance
+            if ((step % STEPS_PER_RUN) == 0 || ctx.u < 0) ctx = make_ctx(__ldg(run_utt + run));   // utterance of the run's first frame
+            if (f >= ctx.u_f1) {                         // walked into another utterance
                 int u = ctx.u;
                 int64_t f1 = ctx.u_f1;
                 while (f >= f1) { ++u; f1 = __ldg(frame_off + u + 1); }
@@ -450,6 +452,12 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     }
 }
 
+// utterance of the first frame of every run (so the frames kernel starts a run with one load instead of a binary search)
+__global__ void mfcc_run_index_kernel(const int64_t* __restrict__ frame_off, int n_utt, int64_t n_runs, int* __restrict__ run_utt) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_runs) run_utt[r] = find_utt(frame_off, n_utt, r * FRAMES_PER_RUN);
+}
+
 // Pass B.  One warp produces 30 consecutive frames (lanes 0,1 carry the two-frame halo); lane = frame so
 // delta / delta-delta are neighbour exchanges by __shfl_up_sync.  The 30x39 output block is contiguous in
 // HBM (rows of 39 floats back to back when ld_feats == 39) and is written through a shared-memory
@@ -547,7 +555,8 @@ extern "C" int lnasr_mfcc_workspace_bytes(int64_t total_frames, int32_t n_utt, s
     LNASR_CHECK_ARG(bytes && total_frames >= 0 && n_utt >= 0, "mfcc_workspace_bytes: bad arguments");
     size_t raw = (size_t)total_frames * RAW_LD * sizeof(float);
     raw = (raw + 255) & ~(size_t)255;
-    *bytes = raw + (size_t)n_utt * MAX_MEL * sizeof(double) + 256;
+    size_t col = ((size_t)n_utt * MAX_MEL * sizeof(double) + 255) & ~(size_t)255;
+    *bytes = raw + col + (size_t)ceil_div(total_frames, FRAMES_PER_RUN) * sizeof(int) + 256;
     return LNASR_OK;
 }
 
@@ -576,6 +585,13 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     size_t raw_bytes = ((size_t)total_frames * RAW_LD * sizeof(float) + 255) & ~(size_t)255;
     double* colsum = (double*)((char*)workspace + raw_bytes);
     LNASR_CUDA(cudaMemsetAsync(colsum, 0, (size_t)n_utt * MAX_MEL * sizeof(double), stream));
+    const size_t col_bytes = ((size_t)n_utt * MAX_MEL * sizeof(double) + 255) & ~(size_t)255;
+    int* run_utt = (int*)((char*)workspace + raw_bytes + col_bytes);
+    {
+        const int64_t nr = ceil_div(total_frames, FRAMES_PER_RUN);
+        mfcc_run_index_kernel<<<(unsigned)ceil_div(nr, 256), 256, 0, stream>>>(frame_offsets, n_utt, nr, run_utt);
+        LNASR_LAUNCH_CHECK();
+    }
 
     MfccDev P;
     P.frame_len = tb->frame_len; P.frame_step = tb->frame_step; P.n_mel = tb->n_mel; P.n_ceps = tb->n_ceps;
@@ -603,11 +619,11 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     if (pcm_dtype == LNASR_DT_I16) {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mfcc_frames_kernel<int16_t><<<grid, threads, smem, stream>>>(
-            (const int16_t*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, power_out, ceps_out);
+            (const int16_t*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, run_utt, power_out, ceps_out);
     } else {
         LNASR_CUDA(cudaFuncSetAttribute(mfcc_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mfcc_frames_kernel<float><<<grid, threads, smem, stream>>>(
-            (const float*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, power_out, ceps_out);
+            (const float*)pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, run_utt, power_out, ceps_out);
     }
     LNASR_LAUNCH_CHECK();
     const int64_t n_tiles = ceil_div(total_frames, FIN_FRAMES);

@@ -86,12 +86,15 @@ struct TrellisArgs {
     uint16_t* bt_ws;         // viterbi only, required when a path is wanted
     double* score_out;       // [n_utt, n_models]: max v[T-1] (viterbi) / lse alpha[T-1] (forward); unused for backward
     int32_t* last_state;     // [n_utt*n_models], viterbi only
+    uint32_t* path_out;      // [n_models, total_frames]; the small kernel backtraces in place when this is set
+    int64_t total_frames;
     int max_in, max_out;
     const int* pred_idx; const double* pred_val; const int* succ_idx; const double* succ_val;
 };
 
 constexpr int TS_WARPS = 4;
-constexpr int TS_PF = 4;     // emission prefetch depth (frames)
+constexpr int TS_PF = 12;    // emission prefetch depth (frames): a step is ~0.1 us of shuffles, an HBM/L2 miss ~0.8 us
+constexpr int TS_BT = 16;    // backpointer rows fetched per round of the in-kernel backtrace
 
 template <int G, typename BT, int MODE>
 __global__ void __launch_bounds__(TS_WARPS * 32)
@@ -206,6 +209,36 @@ trellis_small_kernel(TrellisArgs a) {
         if (pair_ok && j == 0) {
             if (a.score_out) a.score_out[p] = best;
             if (a.last_state) a.last_state[p] = arg;
+        }
+        // Backtrace (hmm.py:168-171), fused: path[T-1] = argmax v[T-1]; path[t] = bt[t+1, path[t+1]].  Lane j re-reads
+        // ITS OWN column of the uint16 backpointers (its own stores, so program order makes them visible), TS_BT rows per
+        // round and all in flight together; the pointer chase itself then runs on registers through shuffles instead
+        // of one dependent global load per frame.
+        if (a.path_out && a.bt_ws) {
+            uint32_t* out = a.path_out + (int64_t)k * a.total_frames + f0;
+            int st = arg;                                          // state at frame t_hi (same in every lane of the group)
+            if (pair_ok && j == 0 && T > 0) out[T - 1] = (uint32_t)st;
+            // rows t+1 = T-1 .. 1 are consumed; round r covers rows hi .. hi-TS_BT+1 with hi = Tmax-1 - r*TS_BT
+            for (int hi = Tmax - 1; hi >= 1; hi -= TS_BT) {
+                uint16_t q[TS_BT];
+#pragma unroll
+                for (int i = 0; i < TS_BT; ++i) {
+                    const int row = hi - i;
+                    q[i] = (active && row >= 1 && row < T) ? a.bt_ws[(f0 + row) * ncol + col] : (uint16_t)0;
+                }
+                int mine = 0;                                      // state of frame hi-1-j, kept by lane j for a coalesced store
+#pragma unroll
+                for (int i = 0; i < TS_BT; ++i) {
+                    const int row = hi - i;
+                    const int nx = __shfl_sync(0xffffffffu, (int)q[i], (lane & ~(G - 1)) + st);
+                    if (row >= 1 && row < T) st = nx;              // uniform inside the group
+                    if ((i % G) == j) mine = st;
+                    if ((i % G) == G - 1 || i == TS_BT - 1) {      // flush G results: lane j holds frame (hi-1) - (i - i%G) - j
+                        const int t = hi - 1 - (i - (i % G)) - j;
+                        if (pair_ok && (i - (i % G)) + j <= i && t >= 0 && t < T - 1) out[t] = (uint32_t)mine;
+                    }
+                }
+            }
         }
     } else if (MODE == MODE_FORWARD) {
         double mx = neg_inf();
@@ -662,10 +695,12 @@ extern "C" int lnasr_viterbi_batch(const void* b, int b_dtype, int64_t ld_b, con
         }
         a.bt_ws = (uint16_t*)workspace;
         a.last_state = (int32_t*)((char*)workspace + bt_bytes);
+        a.path_out = path_out;
+        a.total_frames = total_frames;
     }
     rc = run_trellis<MODE_VITERBI>(a, b_dtype, bank, stream);
     if (rc) return rc;
-    if (path_out) {
+    if (path_out && bank->N > 32) {        // the small kernel (N <= 32) backtraces in place
         backtrace_kernel<<<(unsigned)ceil_div(n_pairs, 64), 64, 0, stream>>>(a.bt_ws, a.last_state, frame_offsets, n_utt,
                                                                           bank->n_models, bank->N, total_frames, path_out);
         LNASR_LAUNCH_CHECK();

@@ -104,11 +104,18 @@ def check(rc: int, what: str = ""):
         raise LnasrError(f"{what or 'lnasr'} failed (code {rc}): {msg}")
 
 
+_torch = None
+
+
 def require_cuda():
-    import torch
-    if not torch.cuda.is_available():
-        raise LnasrError("lnasr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-    return torch
+    """torch, after checking once that a CUDA device exists (the check costs microseconds per call otherwise)."""
+    global _torch
+    if _torch is None:
+        import torch
+        if not torch.cuda.is_available():
+            raise LnasrError("lnasr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _torch = torch
+    return _torch
 
 
 def ptr(t):
@@ -117,5 +124,4 @@ def ptr(t):
 
 
 def stream_ptr():
-    import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(require_cuda().cuda.current_stream().cuda_stream)

@@ -9,6 +9,7 @@ Viterbi score max_j v[T-1, j], lowest index on ties.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import NamedTuple, Optional, Sequence
 
 import numpy as np
@@ -68,12 +69,12 @@ class ModelBank:
         return self.gmm.loglik(feats, b_out=b_out)[0]
 
     def score(self, feats, f_off_d, n_utt: int, total: int, want_paths=False, want_logprob=False,
-              workspace=None) -> BankResult:
+              workspace=None, words_out=None, best_out=None) -> BankResult:
         t = _dev.torch()
         b = self.emissions(feats)
         r = self.trans.viterbi(b, f_off_d, n_utt, total, want_path=want_paths, want_score=True, workspace=workspace)
-        words = _dev.empty((n_utt,), t.int32)
-        best = _dev.empty((n_utt,), t.float64)
+        words = words_out if words_out is not None else _dev.empty((n_utt,), t.int32)
+        best = best_out if best_out is not None else _dev.empty((n_utt,), t.float64)
         _capi.check(_capi.lib().lnasr_argmax_rows(_capi.ptr(r["score"]), n_utt, self.K, _capi.ptr(words), _capi.ptr(best),
                                                  _capi.stream_ptr()), "argmax_rows")
         lp = self.trans.forward(b, f_off_d, n_utt, total)[1] if want_logprob else None
@@ -96,11 +97,13 @@ class AcousticPipeline:
         res = self.bank.score(mb.feats, mb.frame_offsets, n_utt, total, want_paths=want_paths, want_logprob=want_logprob)
         return res, mb
 
-    def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 4, want_paths: bool = False):
+    def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 8, want_paths: bool = False):
         """End-to-end entry point for HOST audio: `pcm_host` is a pinned CPU tensor (int16 or float32) of concatenated
-        utterances, `sample_offsets` [n+1] host.  The batch is cut into `n_chunks` groups of whole utterances; the
-        host->device copy of group i+1 (copy stream) overlaps MFCC / GMM / Viterbi of group i (compute stream), two
-        staging buffers deep.  Returns (words int32 [n], best float64 [n]) as CPU tensors."""
+        utterances, `sample_offsets` [n+1] host.  The batch is cut into `n_chunks` groups of whole utterances.  All
+        host->device copies are queued up front on a copy stream (one event per group), so the copy engine streams
+        the PCM without waiting for the host; MFCC / GMM / Viterbi of group i (compute stream) start when its copy
+        has landed and overlap the copies of the later groups.  Offsets of every group travel in ONE pinned upload.
+        Returns (words int32 [n], best float64 [n]) as CPU tensors."""
         t = _dev.torch()
         off = np.asarray(sample_offsets, dtype=np.int64)
         n_utt = len(off) - 1
@@ -109,7 +112,17 @@ class AcousticPipeline:
         targets = off[0] + (off[-1] - off[0]) * np.arange(1, n_chunks) / n_chunks
         cuts = np.unique(np.concatenate([[0], np.searchsorted(off, targets), [n_utt]]))
         bounds = [(int(cuts[i]), int(cuts[i + 1])) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
-        max_samples = max(int(off[hi] - off[lo]) for lo, hi in bounds)
+        n_fr = self.mfcc.frame_counts(off)
+        # per-group offsets relative to the group's first sample / frame, all groups in one array: [s_off | f_off] per group
+        meta, plan = [], []
+        pos = 0
+        for lo, hi in bounds:
+            s_rel = off[lo:hi + 1] - off[lo]
+            f_rel = _dev.offsets_from_lengths(n_fr[lo:hi])
+            meta += [s_rel, f_rel]
+            plan.append((pos, pos + len(s_rel), f_rel))
+            pos += 2 * len(s_rel)
+        meta_host = t.from_numpy(np.concatenate(meta)).pin_memory()
         dev = _dev.device()
         cur = t.cuda.current_stream()
         if not hasattr(self, "_streams"):
@@ -117,32 +130,45 @@ class AcousticPipeline:
         copy_s, comp_s = self._streams
         copy_s.wait_stream(cur)
         comp_s.wait_stream(cur)
-        stage = [t.empty((max_samples,), dtype=pcm_host.dtype, device=dev) for _ in range(2)]
-        words = t.empty((n_utt,), dtype=t.int32, device=dev)
-        best = t.empty((n_utt,), dtype=t.float64, device=dev)
-        done = [None, None]
-        for i, (lo, hi) in enumerate(bounds):
-            s0, s1 = int(off[lo]), int(off[hi])
-            buf = stage[i & 1]
-            with t.cuda.stream(copy_s):
-                if done[i & 1] is not None:
-                    copy_s.wait_event(done[i & 1])            # the compute that last read this staging buffer
-                buf[:s1 - s0].copy_(pcm_host[s0:s1], non_blocking=True)
+        total_samples = int(off[-1] - off[0])
+        max_frames = max(int(p[2][-1]) for p in plan)
+        with t.cuda.stream(copy_s):
+            pcm_dev = t.empty((total_samples,), dtype=pcm_host.dtype, device=dev)
+            meta_dev = t.empty((meta_host.numel(),), dtype=t.int64, device=dev)
+            meta_dev.copy_(meta_host, non_blocking=True)
+            events = []
+            for lo, hi in bounds:
+                s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
+                pcm_dev[s0:s1].copy_(pcm_host[int(off[lo]):int(off[hi])], non_blocking=True)
                 ev = t.cuda.Event()
                 ev.record(copy_s)
-            with t.cuda.stream(comp_s):
+                events.append(ev)
+        with t.cuda.stream(comp_s):
+            words = t.empty((n_utt,), dtype=t.int32, device=dev)
+            best = t.empty((n_utt,), dtype=t.float64, device=dev)
+            need = C.c_size_t(0)
+            _capi.check(_capi.lib().lnasr_mfcc_workspace_bytes(max_frames, max(h - l for l, h in bounds), C.byref(need)),
+                        "mfcc_workspace_bytes")
+            ws = t.empty((need.value,), dtype=t.uint8, device=dev)
+            for (lo, hi), (p0, p1, f_rel), ev in zip(bounds, plan, events):
                 comp_s.wait_event(ev)
-                res, _ = self.recognize_batch(buf[:s1 - s0], off[lo:hi + 1] - s0, want_paths=want_paths)
-                words[lo:hi] = res.words
-                best[lo:hi] = res.best
-                d = t.cuda.Event()
-                d.record(comp_s)
-                done[i & 1] = d
+                s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
+                nu = hi - lo
+                mb = self.mfcc.calc_mfcc_batch(pcm_dev[s0:s1], sample_offsets=off[lo:hi + 1],
+                                               _plan=(meta_dev[p0:p1], meta_dev[p1:p1 + nu + 1], f_rel, ws))
+                res = self.bank.score(mb.feats, mb.frame_offsets, nu, int(f_rel[-1]), want_paths=want_paths,
+                                      words_out=words[lo:hi], best_out=best[lo:hi])
+            out_w = t.empty((n_utt,), dtype=t.int32, pin_memory=True)
+            out_b = t.empty((n_utt,), dtype=t.float64, pin_memory=True)
+            out_w.copy_(words, non_blocking=True)
+            out_b.copy_(best, non_blocking=True)
         cur.wait_stream(comp_s)
-        for x in stage + [words, best]:
+        for x in (pcm_dev, meta_dev):
             x.record_stream(comp_s)
-            x.record_stream(copy_s)
-        return words.cpu(), best.cpu()
+        for x in (words, best, ws):
+            x.record_stream(cur)
+        comp_s.synchronize()
+        return out_w, out_b
 
     def recognize(self, signals: Sequence[np.ndarray]):
         """Convenience: list of utterances -> numpy array of word indices."""

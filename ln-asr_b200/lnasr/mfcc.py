@@ -140,11 +140,24 @@ class MFCC:
         return (res.power.double().cpu().numpy(), res.ceps.double().cpu().numpy(), res.feats.double().cpu().numpy())
 
     # ------------------------------------------------------------------ batched, device-resident
-    def calc_mfcc_batch(self, signals, sample_offsets=None, want_power=False, want_ceps=False, feats_out=None) -> MfccBatch:
+    def frame_counts(self, sample_offsets) -> np.ndarray:
+        """Frames per utterance from host sample offsets [n+1]: ceil(|S-(L-step)|/step) (utils.py:118), vectorised."""
+        lens = np.diff(np.asarray(sample_offsets, dtype=np.int64))
+        step = self.frame_step
+        n_fr = (np.abs(lens - (self.frame_L - step)) + step - 1) // step
+        if len(n_fr) and n_fr.min() < 2:
+            # the reference indexes row 1 of the feature matrix (mfcc.py:164): fewer than 2 frames is an IndexError there
+            raise IndexError("calc_mfcc needs at least 2 frames per utterance (index 1 is out of bounds)")
+        return n_fr
+
+    def calc_mfcc_batch(self, signals, sample_offsets=None, want_power=False, want_ceps=False, feats_out=None,
+                        _plan=None) -> MfccBatch:
         """MFCC of a ragged batch.
 
         signals: a list of 1-D arrays (numpy, int16 or float), or one concatenated 1-D CUDA/CPU tensor / array
-        together with `sample_offsets` ([n_utt+1], host).  Returns device tensors (see MfccBatch)."""
+        together with `sample_offsets` ([n_utt+1], host).  Returns device tensors (see MfccBatch).
+        `_plan` = (sample_offsets_dev, frame_offsets_dev, frame_offsets_host, workspace) skips the host-side
+        offset arithmetic and uploads (used by AcousticPipeline.recognize_batch_host)."""
         t = _dev.torch()
         lib = _capi.lib()
         if sample_offsets is None:
@@ -153,35 +166,35 @@ class MFCC:
             pcm_host, s_off = _dev.pack_ragged(arrs, np.int16 if all_i16 else np.float32)
             pcm = _dev.to_dev(pcm_host, t.int16 if all_i16 else t.float32)
         else:
-            s_off = np.asarray(sample_offsets, dtype=np.int64)
+            s_off = sample_offsets if _plan is not None else np.asarray(sample_offsets, dtype=np.int64)
             if isinstance(signals, t.Tensor):
                 pcm = signals if signals.dtype in (t.int16, t.float32) else signals.to(t.float32)
                 pcm = _dev.to_dev(pcm)
             else:
                 a = np.asarray(signals)
                 pcm = _dev.to_dev(a if a.dtype == np.int16 else a.astype(np.float32))
-        n_utt = len(s_off) - 1
-        lens = np.diff(s_off)
-        step = self.frame_step
-        n_fr = (np.abs(lens - (self.frame_L - step)) + step - 1) // step          # utils.py:118, vectorised
-        if n_utt and n_fr.min() < 2:
-            # the reference indexes row 1 of the feature matrix (mfcc.py:164): fewer than 2 frames is an IndexError there
-            raise IndexError("calc_mfcc needs at least 2 frames per utterance (index 1 is out of bounds)")
-        f_off = _dev.offsets_from_lengths(n_fr)
+        ws = None
+        if _plan is not None:
+            s_off_d, f_off_d, f_off, ws = _plan
+            n_utt = len(f_off) - 1
+        else:
+            n_utt = len(s_off) - 1
+            f_off = _dev.offsets_from_lengths(self.frame_counts(s_off))
+            s_off_d = _dev.to_dev(s_off, t.int64)
+            f_off_d = _dev.to_dev(f_off, t.int64)
         total = int(f_off[-1])
         ncol = 3 * (self.cepstrum_num + 1)
         feats = feats_out if feats_out is not None else _dev.empty((total, ncol), t.float32)
         power = _dev.empty((total, self.fft_size), t.float32) if want_power else None
         ceps = _dev.empty((total, self.mfbank_num), t.float32) if want_ceps else None
-        s_off_d = _dev.to_dev(s_off, t.int64)
-        f_off_d = _dev.to_dev(f_off, t.int64)
         if total:
             need = C.c_size_t(0)
             _capi.check(lib.lnasr_mfcc_workspace_bytes(total, n_utt, C.byref(need)), "mfcc_workspace_bytes")
-            ws = _dev.empty((need.value,), t.uint8)
+            if ws is None or ws.numel() < need.value:
+                ws = _dev.empty((need.value,), t.uint8)
             tb = self._device_tables()
             _capi.check(lib.lnasr_mfcc_batch(
                 _capi.ptr(pcm), _dev.np_dtype_code(pcm.dtype), _capi.ptr(s_off_d), _capi.ptr(f_off_d), n_utt, total,
                 C.byref(tb), _capi.ptr(feats), feats.stride(0), _capi.ptr(power), _capi.ptr(ceps),
-                _capi.ptr(ws), need.value, _capi.stream_ptr()), "mfcc_batch")
+                _capi.ptr(ws), ws.numel(), _capi.stream_ptr()), "mfcc_batch")
         return MfccBatch(feats, f_off_d, f_off, power, ceps)
