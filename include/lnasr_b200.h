@@ -101,8 +101,10 @@ int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* sample_offse
  *   tc    : [x^2, x, 1] . [-1/(2 var), mu/var, c]^T as a 3xTF32 tcgen05 contraction with the log-sum-exp
  *           over mixtures fused into the TMEM epilogue -- large models (config 4).
  */
-/* packed exact model: lnasr_gmm_exact_packed_doubles() float64 values -- chunks of 4 mixtures of one state
- * (n_mix padded with log w = -inf), (dim+1) rows of [a_0..a_3 | b_0..b_3] per chunk (see csrc/gmm_exact.cu) */
+/* packed exact model: lnasr_gmm_exact_packed_doubles() float64 values -- the SIMT image (chunks of 4 mixtures of one
+ * state, n_mix padded with log w = -inf, (dim+1) rows of [a_0..a_3 | b_0..b_3] per chunk) followed, when n_mix <= 8 and
+ * dim <= 39, by the FP64 tensor-core image ([groups*40][84] rows of [-1/(2 var) , mu/var interleaved | c | log w]);
+ * lnasr_gmm_loglik_exact runs the DMMA kernel on the latter where it exists (see csrc/gmm_exact.cu) */
 int64_t lnasr_gmm_exact_packed_doubles(int32_t n_states, int32_t n_mix, int32_t dim);
 int lnasr_gmm_pack_exact(const double* logw /*[n_states,n_mix]*/, const double* mu /*[n_states,n_mix,dim]*/,
                          const double* var /*[n_states,n_mix,dim]*/, int32_t n_states, int32_t n_mix, int32_t dim,
@@ -226,6 +228,8 @@ int lnasr_baumwelch_xi(const double* alpha, const double* beta, const double* b,
 int lnasr_debug_umma_probe(const float* a_image /*[a_bytes/4]*/, int32_t a_bytes, const float* b_image, int32_t b_bytes,
                            uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout_type,
                            uint32_t idesc, float* d_out /*[128,128]*/, void* stream);
+/* bring-up / test switch: 1 = lnasr_gmm_loglik_exact keeps the SIMT kernel even where the FP64 tensor-core (DMMA) kernel applies */
+int lnasr_debug_set_gmm_simt(int on);
 /* bring-up switch: exchange the LBO / SBO fields of the descriptors lnasr_gmm_loglik_tc builds (0 = as documented) */
 int lnasr_debug_set_umma_swap(int swap);
 

@@ -73,4 +73,54 @@ __device__ __forceinline__ double logaddexp_d(double a, double b) {
     return mx + log1p(exp(mn - mx));
 }
 
+// ln(x), table driven (used for log-mel energies and the mixture log-sum-exp): x = 2^E m, m in [1,2); table entry i = top 7 mantissa bits holds c = 1/(1+(i+1/2)/128)
+// and -ln c; r = m c - 1 has |r| < 2^-8 and ln(1+r) is a degree-6 polynomial (error r^7/7 < 3e-18).  8 DFMA instead
+// of the ~25 of log().  Zero, subnormal, inf and NaN go through log().
+__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
+    if (!(x >= 1e-300 && x <= 1e300)) return log(x);
+    const int hi = __double2hiint(x);
+    const int E = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 ct = tab[(hi >> 13) & 127];
+    const double r = fma(m, ct.x, -1.0);
+    double q = -1.0 / 6.0;
+    q = fma(q, r, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    q = fma(q, r, 1.0);
+    return fma(r, q, fma((double)E, 0.69314718055994530942, ct.y));
+}
+
+
+// exp(d) for d <= 0 (the terms of a log-sum-exp after subtracting the maximum): d = (n/64) ln2 + r, |r| <= ln2/128,
+// exp(d) = 2^(n>>6) * T[n & 63] * P5(r); relative error ~2e-16, 10 DFMA instead of the ~20 of exp().  T = 2^(i/64).
+__device__ __forceinline__ double fast_exp_neg(double d, const double* __restrict__ t64) {
+    if (!(d > -700.0)) return (d != d) ? d : 0.0;                   // -inf and anything below e^-700: 0 ; NaN stays NaN
+    const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52: the integer lands in the low word
+    double nf = fma(d, 92.33248261689366, MAGIC);                   // 64 / ln 2
+    const int n = __double2loint(nf);
+    nf -= MAGIC;
+    double r = fma(nf, -0.01083042469326756, d);                    // ln2/64, high part (32 significant bits)
+    r = fma(nf, -2.9815858269852933e-12, r);                        //         low part
+    double p = 1.0 / 120.0;
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = t64[n & 63] * p;
+    return __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+}
+
+// block-wide set-up of the two tables above: log_tab[128] = (1/c_i, -ln c_i), exp_tab[64] = 2^(i/64)
+__device__ __forceinline__ void fill_log_exp_tables(double2* log_tab, double* exp_tab, int tid, int n_threads) {
+    for (int i = tid; i < 128; i += n_threads) {
+        const double c = 1.0 / (1.0 + ((double)i + 0.5) / 128.0);
+        log_tab[i] = make_double2(c, -log(c));
+    }
+    if (exp_tab)
+        for (int i = tid; i < 64; i += n_threads) exp_tab[i] = exp2((double)i / 64.0);
+}
+
 }  // namespace lnasr

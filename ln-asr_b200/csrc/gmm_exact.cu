@@ -168,6 +168,183 @@ gmm_loglik_exact_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core variant: the contraction [x^2 | x | 1] . [-1/(2 var) | mu/var | c]^T as
+// mma.sync.m8n8k4.f64 (DMMA).  On B200 DMMA and DFMA both sustain 64 FMA/clk/SM (measured, tools/ubench/fp64_pipes.cu)
+// but one DMMA carries 256 FMA per warp instruction and its operands arrive as one conflict-free LDS.64 per fragment
+// that is reused MT x NT times, so the kernel leaves the shared-memory / issue limits of the SIMT kernel above and runs at
+// the FP64 pipe.  Everything stays float64, so the expansion costs ~1e-13 absolute (K = 2D+1 <= 80 terms of magnitude
+// <= 1e3) -- same bar as the SIMT kernel.
+//
+// Block = 8 warps x 16 frames (two blocks per SM: 16 warps hide the latency of the serial exp / log chains of the epilogue).  x tile in shared memory as doubles [128][LDX] with x[D] = 1 (the constant column); the A
+// fragment of k-step j is x or x*x of dims 2j, 2j+1, formed in registers.  Gaussians are processed in groups of 40
+// (5 n-blocks of 8); the group's parameter rows ([40][84] doubles: k < 80 weights, k = 80 log w) are streamed through a
+// double buffer with cp.async.  The mixture log-sum-exp (gmmhmm.py:67) runs on the accumulator fragments: a thread holds
+// 2 adjacent Gaussians of one frame, so the n_mix (padded to MP = 1, 2, 4 or 8) mixtures of a state are reached with
+// 0, 0, 1 or 2 quad shuffles.
+constexpr int GM_WARPS = 8;
+constexpr int GM_MT = 2;                            // m-blocks (8 frames each) per warp
+constexpr int GM_TILE = GM_WARPS * GM_MT * 8;       // 128 frames per block
+constexpr int GM_NT = 5;                            // n-blocks (8 Gaussians each) per group
+constexpr int GM_GROUP = GM_NT * 8;                 // 40 Gaussians per group
+constexpr int GM_LDB = 84;                          // parameter row: 80 weights | log w | pad  (84 = 4 mod 16: conflict-free B fragments)
+constexpr int GM_MAX_DIM = 39;                      // K = 2 dim + 1 <= 80
+
+__host__ __device__ inline int gm_mpad(int n_mix) { return n_mix <= 1 ? 1 : (n_mix <= 2 ? 2 : (n_mix <= 4 ? 4 : 8)); }
+__host__ __device__ inline int gm_ksteps(int dim) { return (2 * dim + 1 + 3) / 4; }
+__host__ __device__ inline int gm_ldx(int dim) {   // x row stride: >= 2*ksteps slots, = 2 mod 4 (conflict-free A fragments)
+    int l = 2 * gm_ksteps(dim);
+    while ((l & 3) != 2) ++l;
+    return l;
+}
+__host__ __device__ inline int64_t gm_groups(int n_states, int n_mix) {
+    return ((int64_t)n_states * gm_mpad(n_mix) + GM_GROUP - 1) / GM_GROUP;
+}
+__host__ __device__ inline bool gm_supported(int n_mix, int dim) { return n_mix <= 8 && dim <= GM_MAX_DIM; }
+
+// image: [n_groups*40][84] doubles, Gaussian (state j, mixture m) at row j*MP + m
+__global__ void gmm_pack_mma_kernel(const double* __restrict__ logw, const double* __restrict__ mu,
+                                    const double* __restrict__ var, int n_states, int n_mix, int dim,
+                                    double* __restrict__ img) {
+    const int MP = gm_mpad(n_mix);
+    const int64_t rows = gm_groups(n_states, n_mix) * GM_GROUP;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    double* o = img + row * GM_LDB;
+    for (int k = 0; k < GM_LDB; ++k) o[k] = 0.0;
+    const int64_t j = row / MP;
+    const int m = (int)(row % MP);
+    if (j >= n_states || m >= n_mix) { o[80] = neg_inf(); return; }
+    const int64_t gi = j * n_mix + m;
+    double c = (double)dim * 1.8378770664093453;  /* ln(2 pi) */
+    for (int d = 0; d < dim; ++d) {
+        const double v = var[gi * dim + d], mm = mu[gi * dim + d];
+        o[2 * d] = -0.5 / v;
+        o[2 * d + 1] = mm / v;
+        c += log(v) + mm * mm / v;
+    }
+    o[2 * dim] = -0.5 * c;
+    o[80] = logw[gi];
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int MP, typename FeatT, typename OutT>
+__global__ void __launch_bounds__(GM_WARPS * 32, 2)
+gmm_loglik_mma_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_frames, const double* __restrict__ img,
+                      int n_states, int n_mix, int dim, int n_groups, OutT* __restrict__ b_out, int64_t ld_b,
+                      double* __restrict__ bm_out) {
+    extern __shared__ __align__(16) unsigned char gx_smem[];
+    const int ldx = gm_ldx(dim), ks = gm_ksteps(dim);
+    double* xs = reinterpret_cast<double*>(gx_smem);                         // [GM_TILE][ldx]
+    double* wb = xs + (size_t)GM_TILE * ldx;                                 // [2][GM_GROUP][GM_LDB]
+    double2* log_tab = reinterpret_cast<double2*>(wb + 2 * GM_GROUP * GM_LDB);
+    double* exp_tab = reinterpret_cast<double*>(log_tab + 128);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, c = lane & 3;
+    const int64_t t0 = (int64_t)blockIdx.x * GM_TILE;
+    auto issue = [&](int g) {
+        double* dst = wb + (size_t)(g & 1) * GM_GROUP * GM_LDB;
+        const double* src = img + (int64_t)g * GM_GROUP * GM_LDB;
+        for (int i = tid; i < GM_GROUP * GM_LDB / 2; i += GM_WARPS * 32) cp_async16(dst + 2 * i, src + 2 * i);
+        cp_async_commit();
+    };
+    issue(0);
+    for (int i = tid; i < GM_TILE * ldx; i += GM_WARPS * 32) {
+        const int row = i / ldx, col = i - row * ldx;
+        double v = (col == dim) ? 1.0 : 0.0;
+        if (col < dim && t0 + row < n_frames) v = (double)feats[(t0 + row) * ld_feats + col];
+        xs[i] = v;
+    }
+    fill_log_exp_tables(log_tab, exp_tab, tid, GM_WARPS * 32);
+    const double* xrow = xs + (size_t)(warp * GM_MT * 8 + r) * ldx + (c >> 1);   // + mb*8*ldx + 2j
+    const bool sq = (c & 1) == 0;                                               // even k: x^2, odd k: x
+    const int64_t n_gauss = (int64_t)n_states * n_mix;
+    for (int g = 0; g < n_groups; ++g) {
+        if (g + 1 < n_groups) { issue(g + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                                       // group g's rows (and, first time, the x tile + tables) are visible
+        const double* W = wb + (size_t)(g & 1) * GM_GROUP * GM_LDB;
+        const double* wrow = W + (size_t)r * GM_LDB + c;        // + nb*8*GM_LDB + 4j
+        double acc[GM_MT][GM_NT][2];
+#pragma unroll
+        for (int mb = 0; mb < GM_MT; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < GM_NT; ++nb) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+#pragma unroll 2
+        for (int j = 0; j < ks; ++j) {
+            double a[GM_MT], bf[GM_NT];
+#pragma unroll
+            for (int mb = 0; mb < GM_MT; ++mb) {
+                const double xv = xrow[(size_t)mb * 8 * ldx + 2 * j];
+                a[mb] = sq ? xv * xv : xv;
+            }
+#pragma unroll
+            for (int nb = 0; nb < GM_NT; ++nb) bf[nb] = wrow[(size_t)nb * 8 * GM_LDB + 4 * j];
+#pragma unroll
+            for (int mb = 0; mb < GM_MT; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < GM_NT; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bf[nb]);
+        }
+        // ---- epilogue: + log w, log-sum-exp over the MP (padded) mixtures of a state, stores
+#pragma unroll
+        for (int nb = 0; nb < GM_NT; ++nb) {
+            const int gl = nb * 8 + 2 * c;                                   // my first Gaussian inside the group
+            const int64_t gp = (int64_t)g * GM_GROUP + gl;                   // padded global Gaussian index (row of the image)
+            const double lw0 = W[(size_t)gl * GM_LDB + 80], lw1 = W[(size_t)(gl + 1) * GM_LDB + 80];
+            const int64_t st0 = gp / MP, st1 = (gp + 1) / MP;
+            const int mx0 = (int)(gp % MP), mx1 = (int)((gp + 1) % MP);
+            double mxv[GM_MT], sum[GM_MT];
+#pragma unroll
+            for (int mb = 0; mb < GM_MT; ++mb) {
+                const int64_t t = t0 + (warp * GM_MT + mb) * 8 + r;
+                const bool ok = t < n_frames;
+                const double g0 = acc[mb][nb][0], g1 = acc[mb][nb][1];       // pure Gaussian log-densities (gmm.py:59-68)
+                if (bm_out && ok) {                                          // gmmhmm.py:66
+                    if (st0 < n_states && mx0 < n_mix) bm_out[t * n_gauss + st0 * n_mix + mx0] = g0;
+                    if (st1 < n_states && mx1 < n_mix) bm_out[t * n_gauss + st1 * n_mix + mx1] = g1;
+                }
+                const double v0 = g0 + lw0, v1 = g1 + lw1;                   // + log w[j,m] (gmmhmm.py:67)
+                if (MP == 1) {
+                    if (ok && st0 < n_states) b_out[t * ld_b + st0] = (OutT)v0;
+                    if (ok && st1 < n_states) b_out[t * ld_b + st1] = (OutT)v1;
+                } else {
+                    double mx = fmax(v0, v1);
+                    if (MP >= 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    if (MP >= 8) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    double sm = 0.0;
+                    if (mx != neg_inf()) sm = fast_exp_neg(v0 - mx, exp_tab) + fast_exp_neg(v1 - mx, exp_tab);
+                    if (MP >= 4) sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+                    if (MP >= 8) sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                    mxv[mb] = mx;
+                    sum[mb] = sm;
+                }
+            }
+            if (MP == 2) {
+#pragma unroll
+                for (int mb = 0; mb < GM_MT; ++mb) {
+                    const int64_t t = t0 + (warp * GM_MT + mb) * 8 + r;
+                    if (t < n_frames && st0 < n_states)
+                        b_out[t * ld_b + st0] = (OutT)((mxv[mb] == neg_inf()) ? mxv[mb] : mxv[mb] + fast_log(sum[mb], log_tab));
+                }
+            } else if (MP >= 4) {
+                // the 2 (MP=4) or 4 (MP=8) lanes that share a state hold identical (max, sum) for every m-block: each of
+                // them finishes a different m-block, so the log is taken once per result instead of once per lane
+                static_assert(GM_MT == 2, "the m-block hand-out below assumes two m-blocks per warp");
+                const int mb = c & 1;
+                const double mx = mb ? mxv[1] : mxv[0], sm = mb ? sum[1] : sum[0];
+                const int64_t t = t0 + (warp * GM_MT + mb) * 8 + r;
+                const bool writer = (MP == 4) || (c < 2);
+                if (writer && t < n_frames && st0 < n_states)
+                    b_out[t * ld_b + st0] = (OutT)((mx == neg_inf()) ? mx : mx + fast_log(sm, log_tab));
+            }
+        }
+        __syncthreads();                                       // buffer g&1 is refilled by issue(g+2)
+    }
+}
+
 // Full-covariance variant (the reference's gaussian_multi_distribution_log takes a full Sigma, gmm.py:59-68):
 // Sigma = L L^T is factorised on the host at model-pack time; here quad = | Linv x - nu |^2 with nu = Linv mu,
 // c = -1/2 (D ln 2pi + 2 sum ln L_ii).  One thread per frame, parameters are warp-uniform loads.
@@ -223,8 +400,13 @@ __global__ void emit_gather_kernel(const double* __restrict__ logB, const int32_
 
 using namespace lnasr;
 
+// packed buffer = SIMT image (chunks of 4 mixtures) followed by the DMMA image ([groups*40][84]) when the shape allows it
+static inline int64_t gx_simt_doubles(int n_states, int n_mix, int dim) { return (int64_t)n_states * gx_chunks(n_mix) * (dim + 1) * 8; }
+
 extern "C" int64_t lnasr_gmm_exact_packed_doubles(int32_t n_states, int32_t n_mix, int32_t dim) {
-    return (int64_t)n_states * gx_chunks(n_mix) * (dim + 1) * 8;
+    int64_t n = gx_simt_doubles(n_states, n_mix, dim);
+    if (gm_supported(n_mix, dim)) n += gm_groups(n_states, n_mix) * GM_GROUP * GM_LDB;
+    return n;
 }
 
 extern "C" int lnasr_gmm_pack_exact(const double* logw, const double* mu, const double* var, int32_t n_states,
@@ -234,6 +416,12 @@ extern "C" int lnasr_gmm_pack_exact(const double* logw, const double* mu, const 
     const int n = n_states * gx_chunks(n_mix) * 4;
     gmm_pack_exact_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, packed);
     LNASR_LAUNCH_CHECK();
+    if (gm_supported(n_mix, dim)) {
+        const int64_t rows = gm_groups(n_states, n_mix) * GM_GROUP;
+        gmm_pack_mma_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, (cudaStream_t)stream>>>(
+            logw, mu, var, n_states, n_mix, dim, packed + gx_simt_doubles(n_states, n_mix, dim));
+        LNASR_LAUNCH_CHECK();
+    }
     return LNASR_OK;
 }
 
@@ -257,6 +445,35 @@ static int launch_exact(const void* feats, int ld_feats, int64_t n_frames, const
     return LNASR_OK;
 }
 
+
+template <typename FeatT, typename OutT>
+static int launch_mma(const void* feats, int ld_feats, int64_t n_frames, const double* packed, int n_states,
+                      int n_mix, int dim, void* b_out, int64_t ld_b, double* bm_out, cudaStream_t stream) {
+    const double* img = packed + gx_simt_doubles(n_states, n_mix, dim);
+    const int n_groups = (int)gm_groups(n_states, n_mix);
+    const size_t smem = ((size_t)GM_TILE * gm_ldx(dim) + 2 * GM_GROUP * GM_LDB + 256 + 64) * sizeof(double);
+    const unsigned grid = (unsigned)ceil_div(n_frames, GM_TILE);
+#define LNASR_GM_LAUNCH(MPV)                                                                                              \
+    do {                                                                                                                  \
+        LNASR_CUDA(cudaFuncSetAttribute(gmm_loglik_mma_kernel<MPV, FeatT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gmm_loglik_mma_kernel<MPV, FeatT, OutT><<<grid, GM_WARPS * 32, smem, stream>>>(                                  \
+            (const FeatT*)feats, ld_feats, n_frames, img, n_states, n_mix, dim, n_groups, (OutT*)b_out, ld_b, bm_out);    \
+    } while (0)
+    switch (gm_mpad(n_mix)) {
+        case 1: LNASR_GM_LAUNCH(1); break;
+        case 2: LNASR_GM_LAUNCH(2); break;
+        case 4: LNASR_GM_LAUNCH(4); break;
+        default: LNASR_GM_LAUNCH(8); break;
+    }
+#undef LNASR_GM_LAUNCH
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+static bool g_force_simt = false;     // bring-up / test switch: lnasr_debug_set_gmm_simt(1) keeps the SIMT kernel
+
+extern "C" int lnasr_debug_set_gmm_simt(int on) { g_force_simt = (on != 0); return LNASR_OK; }
+
 extern "C" int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype, int32_t ld_feats, int64_t n_frames,
                                       const double* packed, int32_t n_states, int32_t n_mix, int32_t dim,
                                       void* b_out, int b_dtype, int64_t ld_b, double* bm_out, void* stream_) {
@@ -269,6 +486,12 @@ extern "C" int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype, int32_
     const bool f32 = feats_dtype == LNASR_DT_F32, f64 = feats_dtype == LNASR_DT_F64;
     const bool o32 = b_dtype == LNASR_DT_F32, o64 = b_dtype == LNASR_DT_F64;
     LNASR_CHECK_ARG((f32 || f64) && (o32 || o64), "gmm_loglik_exact: dtypes must be float32 or float64");
+    if (gm_supported(n_mix, dim) && !g_force_simt) {
+        if (f32 && o32) return launch_mma<float, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        if (f32 && o64) return launch_mma<float, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        if (f64 && o32) return launch_mma<double, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        return launch_mma<double, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+    }
     if (f32 && o32) return launch_exact<float, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
     if (f32 && o64) return launch_exact<float, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
     if (f64 && o32) return launch_exact<double, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);

@@ -119,25 +119,6 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-// ln(x) for the log-mel energies: x = 2^E m, m in [1,2); table entry i = top 7 mantissa bits holds c = 1/(1+(i+1/2)/128)
-// and -ln c; r = m c - 1 has |r| < 2^-8 and ln(1+r) is a degree-6 polynomial (error r^7/7 < 3e-18).  8 DFMA instead
-// of the ~25 of log().  Zero, subnormal, inf and NaN go through log().
-__device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
-    if (!(x >= 1e-300 && x <= 1e300)) return log(x);
-    const int hi = __double2hiint(x);
-    const int E = (hi >> 20) - 1023;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    const double2 ct = tab[(hi >> 13) & 127];
-    const double r = fma(m, ct.x, -1.0);
-    double q = -1.0 / 6.0;
-    q = fma(q, r, 0.2);
-    q = fma(q, r, -0.25);
-    q = fma(q, r, 1.0 / 3.0);
-    q = fma(q, r, -0.5);
-    q = fma(q, r, 1.0);
-    return fma(r, q, fma((double)E, 0.69314718055994530942, ct.y));
-}
-
 // The whole per-frame chain runs in float64.  The reference is float64 (mfcc.py), and the features are small
 // differences of ~200 dB log-mel values (mean normalisation, deltas) whose low-energy bands sit up to 90 dB below
 // the frame's peak: an fp32 FFT leaves ~1e-4 relative error in exactly those bands (measured), i.e. above the
