@@ -93,19 +93,23 @@ struct TrellisArgs {
 };
 
 constexpr int TS_WARPS = 4;
-constexpr int TS_PF = 12;    // emission prefetch depth (frames): a step is ~0.1 us of shuffles, an HBM/L2 miss ~0.8 us
 constexpr int TS_BT = 16;    // backpointer rows fetched per round of the in-kernel backtrace
 
-template <int G, typename BT, int MODE>
+// G lanes per (utterance, model) pair.  G = N exactly for N <= 8 (so 5-state word models pack 6 pairs into a warp and the
+// predecessor loops run N, not 8, iterations), else 16 or 32 with the surplus lanes idle.  PF = emission rows in flight per
+// lane: a trellis step is ~0.1 us of shuffles and adds, an HBM / L2 miss ~0.8 us.
+template <int G, typename BT, int MODE, int PF>
 __global__ void __launch_bounds__(TS_WARPS * 32)
 trellis_small_kernel(TrellisArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PPW = 32 / G;                                   // pairs per warp
     const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
-    const int64_t p = ((int64_t)blockIdx.x * TS_WARPS + warp) * PPW + lane / G;
-    const int j = lane % G;
+    const int slot = lane / G;
+    const int gbase = slot * G;                                   // first lane of my group
+    const int64_t p = ((int64_t)blockIdx.x * TS_WARPS + warp) * PPW + slot;
+    const int j = lane - gbase;
     const int N = a.N;
-    const bool pair_ok = p < n_pairs;
+    const bool pair_ok = slot < PPW && p < n_pairs;
     const bool active = pair_ok && j < N;
     const int u = pair_ok ? (int)(p / a.n_models) : 0;
     const int k = pair_ok ? (int)(p % a.n_models) : 0;
@@ -115,6 +119,7 @@ trellis_small_kernel(TrellisArgs a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
     if (Tmax == 0) return;
+    auto grp = [&](double v, int q) { return __shfl_sync(0xffffffffu, v, gbase + q); };   // value of state q of my pair
 
     // transition column (forward/viterbi: A[:, j]) or row (backward: A[j, :]) in registers
     double tr[G];
@@ -133,17 +138,18 @@ trellis_small_kernel(TrellisArgs a) {
         if (MODE == MODE_BACKWARD) return f0 + (s == 0 ? T - 1 : T - s);
         return f0 + s;
     };
-    BT bq[TS_PF];
+    BT bq[PF];
 #pragma unroll
-    for (int i = 0; i < TS_PF; ++i) bq[i] = (active && i < T) ? __ldg(bcol + emis_row(i) * a.ld_b) : BT(0);
+    for (int i = 0; i < PF; ++i) bq[i] = (active && i < T) ? __ldg(bcol + emis_row(i) * a.ld_b) : BT(0);
+    const double pi_j = (MODE != MODE_BACKWARD && active) ? __ldg(a.logpi + (int64_t)k * N + j) : neg_inf();
 
     double cur = neg_inf();       // trellis value of my state
-    for (int s0 = 0; s0 < Tmax; s0 += TS_PF) {
+    for (int s0 = 0; s0 < Tmax; s0 += PF) {
 #pragma unroll
-        for (int i = 0; i < TS_PF; ++i) {
+        for (int i = 0; i < PF; ++i) {
             const int s = s0 + i;
             const double e = (double)bq[i];
-            bq[i] = (active && s + TS_PF < T) ? __ldg(bcol + emis_row(s + TS_PF) * a.ld_b) : BT(0);
+            bq[i] = (active && s + PF < T) ? __ldg(bcol + emis_row(s + PF) * a.ld_b) : BT(0);
             const bool live = active && s < T;
             double nv;
             int arg = 0;
@@ -154,7 +160,7 @@ trellis_small_kernel(TrellisArgs a) {
                 double mx = neg_inf();
 #pragma unroll
                 for (int q = 0; q < G; ++q) {
-                    cand[q] = shfl_d(uj, q, G) + tr[q];
+                    cand[q] = grp(uj, q) + tr[q];
                     mx = fmax(mx, cand[q]);
                 }
                 double sum = 0.0;
@@ -167,23 +173,23 @@ trellis_small_kernel(TrellisArgs a) {
                 double mx = neg_inf();
 #pragma unroll
                 for (int q = 0; q < G; ++q) {
-                    cand[q] = shfl_d(cur, q, G) + tr[q];
+                    cand[q] = grp(cur, q) + tr[q];
                     mx = fmax(mx, cand[q]);
                 }
                 double sum = 0.0;
 #pragma unroll
                 for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
                 const double l = (mx == neg_inf()) ? mx : mx + log(sum);
-                nv = (s == 0) ? (active ? __ldg(a.logpi + (int64_t)k * N + j) + e : neg_inf()) : l + e;
+                nv = (s == 0) ? pi_j + e : l + e;
             } else {
                 // v[0] = pi + b[:,0] ; v[t,j] = max_i (v[t-1,i] + A[i,j]) + b[j,t] ; bt = first argmax (hmm.py:160-166)
                 double best = neg_inf();
 #pragma unroll
                 for (int q = 0; q < G; ++q) {
-                    const double c = shfl_d(cur, q, G) + tr[q];
+                    const double c = grp(cur, q) + tr[q];
                     if (c > best) { best = c; arg = q; }
                 }
-                nv = (s == 0) ? (active ? __ldg(a.logpi + (int64_t)k * N + j) + e : neg_inf()) : best + e;
+                nv = (s == 0) ? pi_j + e : best + e;
                 if (s == 0) arg = 0;
             }
             if (live) {
@@ -203,7 +209,7 @@ trellis_small_kernel(TrellisArgs a) {
         int arg = 0;
 #pragma unroll
         for (int q = 0; q < G; ++q) {
-            const double c = shfl_d(cur, q, G);
+            const double c = grp(cur, q);
             if (q < N && c > best) { best = c; arg = q; }
         }
         if (pair_ok && j == 0) {
@@ -230,7 +236,7 @@ trellis_small_kernel(TrellisArgs a) {
 #pragma unroll
                 for (int i = 0; i < TS_BT; ++i) {
                     const int row = hi - i;
-                    const int nx = __shfl_sync(0xffffffffu, (int)q[i], (lane & ~(G - 1)) + st);
+                    const int nx = __shfl_sync(0xffffffffu, (int)q[i], gbase + st);
                     if (row >= 1 && row < T) st = nx;              // uniform inside the group
                     if ((i % G) == j) mine = st;
                     if ((i % G) == G - 1 || i == TS_BT - 1) {      // flush G results: lane j holds frame (hi-1) - (i - i%G) - j
@@ -245,7 +251,7 @@ trellis_small_kernel(TrellisArgs a) {
         double cand[G];
 #pragma unroll
         for (int q = 0; q < G; ++q) {
-            cand[q] = (q < N) ? shfl_d(cur, q, G) : neg_inf();
+            cand[q] = (q < N) ? grp(cur, q) : neg_inf();
             mx = fmax(mx, cand[q]);
         }
         double sum = 0.0;
@@ -575,17 +581,23 @@ __global__ void argmax_rows_kernel(const double* __restrict__ score, int n_rows,
 template <typename BT, int MODE>
 static int launch_small(const TrellisArgs& a, cudaStream_t stream) {
     const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
-    int G = 1;
-    while (G < a.N) G <<= 1;
-    if (G < 4) G = 4;
+    const int G = a.N <= 8 ? a.N : (a.N <= 16 ? 16 : 32);
     const int ppw = 32 / G;
     const unsigned grid = (unsigned)ceil_div(n_pairs, (int64_t)TS_WARPS * ppw);
+#define LNASR_TS(GV, PFV) trellis_small_kernel<GV, BT, MODE, PFV><<<grid, TS_WARPS * 32, 0, stream>>>(a)
     switch (G) {
-        case 4:  trellis_small_kernel<4, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
-        case 8:  trellis_small_kernel<8, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
-        case 16: trellis_small_kernel<16, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
-        default: trellis_small_kernel<32, BT, MODE><<<grid, TS_WARPS * 32, 0, stream>>>(a); break;
+        case 1:  LNASR_TS(1, 12); break;
+        case 2:  LNASR_TS(2, 12); break;
+        case 3:  LNASR_TS(3, 12); break;
+        case 4:  LNASR_TS(4, 12); break;
+        case 5:  LNASR_TS(5, 12); break;
+        case 6:  LNASR_TS(6, 12); break;
+        case 7:  LNASR_TS(7, 12); break;
+        case 8:  LNASR_TS(8, 12); break;
+        case 16: LNASR_TS(16, 4); break;
+        default: LNASR_TS(32, 4); break;
     }
+#undef LNASR_TS
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }
