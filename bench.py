@@ -1,13 +1,15 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the acoustic hot path (MFCC -> GMM emissions -> Viterbi word decision).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
 
 Metric (BASELINE.json): frames/sec through MFCC + GMM log-likelihood + Viterbi.  One "step" = one pass of the hot
 path over one batch of synthetic 16 kHz utterances with random-init GMM-HMMs:
   c2 (default, BASELINE configs[1]): isolated-word models, 10 words x 5 states x 4 mixtures x 39 dims, 4096
       utterances of 0.5-1.5 s per GPU; the word is the argmax over models of the Viterbi score.
   c4 (BASELINE configs[3] shape): one 2000-state x 16-mixture x 39-dim left-to-right model, tensor-core emissions.
+  c3 (BASELINE configs[2]): one Baum-Welch EM iteration, 3 states x 8 mixtures x 39 dims, 1000 utterances per GPU,
+      accumulators all-reduced over NCCL (lnasr.em.EmTrainer).
 `value` is timed with the PCM already in HBM; `e2e` goes through the public API from pinned host buffers with the
 host->device copy and the device->host read of the decoded words inside the timed region.  Multi-GPU: one process
 per GPU (torchrun), utterances sharded by rank, no data-path collective ("weak" scaling: per-GPU batch fixed).
@@ -72,6 +74,9 @@ def make_models(workload: str, seed: int = 1234):
 WORKLOADS = {
     "c2": dict(desc="isolated-word GMM-HMM: 10 words x 5 states x 4 mixtures x 39 dims, batched Viterbi",
                n_utt=4096, min_s=8000, max_s=24000, emission="exact"),
+    "c3": dict(desc="Baum-Welch EM: 3-state x 8-mixture x 39-dim monophone, 1000 utterances of 200-400 frames per GPU, "
+                    "one EM iteration (emissions + forward + fused backward/accumulate + all-reduce + M-step)",
+               n_utt=1000, min_t=200, max_t=400),
     "c4": dict(desc="large-vocab acoustic scoring: 2000 states x 16 mixtures x 39 dims (left-to-right), TC emissions",
                n_utt=1250, min_s=48000, max_s=48000, emission="tc"),
 }
@@ -157,11 +162,55 @@ def cpu_arm(workload: str, n_utt_sample: int, cores: int):
     return frames / dt, frames, dt
 
 
+def _em_cpu_worker(job):
+    from oracle import lnasr_oracle as O
+    x, mdl = job
+    acc = O.em_accumulate_diag(x, mdl["pi"], mdl["A"], mdl["w"], mdl["mu"], mdl["var"])
+    return x.shape[0], acc
+
+
+def run_reference_em(args):
+    """CPU restatement of one EM iteration of c3 (per-utterance statistics summed + M-step), one process per core."""
+    import multiprocessing as mp
+    from oracle import lnasr_oracle as O
+    cores = os.cpu_count() or 1
+    cfg = WORKLOADS["c3"]
+    mdl = O.random_gmmhmm(3, 8, 39, np.random.default_rng(7))
+    n_s = 2 * cores
+    x, off = synth_feats(99, n_s, cfg["min_t"], cfg["max_t"])
+    jobs = [(x[off[u]:off[u + 1]].astype(np.float64), mdl) for u in range(n_s)]
+    vals = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_em_cpu_worker, jobs, chunksize=1)
+            tot = None
+            for _, acc in res:
+                tot = acc if tot is None else {k: tot[k] + acc[k] for k in tot}
+            O.em_finalize_diag(tot)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                vals.append((sum(r[0] for r in res), dt))
+    frames, dt = sum(v[0] for v in vals), sum(v[1] for v in vals)
+    value = frames / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "frames/sec (Baum-Welch EM iteration)", "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, len(vals)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "c3: " + cfg["desc"], "sample_utts_per_step": n_s},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_s} utterances/step x {len(vals)} steps, one single-threaded process per core"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    return 0
+
+
 def run_reference(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.workload == "c3":
+        return run_reference_em(args)
     cores = os.cpu_count() or 1
     per_step = max(32 * cores, 64) if args.workload == "c2" else cores
     vals = []
@@ -275,11 +324,20 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        fp64 = fp64_peaks()
         top = max(stages, key=lambda k: stages[k]["ms"])
-        roof = roofline_for(top, stages[top], frames, cfg, models, hbm_peak, peaks)
+        roof = roofline_for(top, stages[top], frames, cfg, models, hbm_peak, peaks, fp64)
         roof["kernel"] = top
         roof["peak_source"] = peak_src
         roof["stage_ms"] = {k: round(v["ms"], 4) for k, v in stages.items()}
+        roof["all_stages"] = {}
+        for k in stages:
+            r = roofline_for(k, stages[k], frames, cfg, models, hbm_peak, peaks, fp64)
+            roof["all_stages"][k] = {"bound": r["bound"], "achieved": round(r["achieved"], 3), "peak": round(r["peak"], 1),
+                                     "unit": r["unit"], "frac": round(r["frac"], 4)}
+            if "fp64_alu" in r:
+                roof["all_stages"][k]["fp64_alu_frac"] = round(r["fp64_alu"]["frac"], 4)
+        roof["fp64_peaks_measured"] = {k: round(v, 2) for k, v in fp64.items()}
         cores = os.cpu_count() or 1
         cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "skipped (--no-cpu)"}
         if world == 1 and not args.no_cpu:
@@ -291,7 +349,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 MFCC / f64 emissions+trellis" if cfg["emission"] == "exact" else "f32 MFCC / 3xTF32 emissions / f64 trellis",
+            "dtype": "f64" if cfg["emission"] == "exact" else "f64 MFCC + trellis / 3xTF32 emissions",
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + cfg["desc"], "utts_per_gpu": n_utt, "frames_per_gpu_step": frames,
                        "pcm_bytes_per_gpu_step": int(pcm_np.nbytes), "l2": "inputs larger than L2 (PCM + intermediates > 126 MB per step)",
@@ -308,6 +366,111 @@ def run_ours(args):
         dist.destroy_process_group()
     return 0
 
+
+
+# ------------------------------------------------------------------------------------------------ EM arm (c3)
+def synth_feats(seed, n_utt, min_t, max_t, d=39):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(min_t, max_t + 1, size=n_utt)
+    off = np.zeros(n_utt + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    x = (0.5 * rng.standard_normal((int(off[-1]), d))).astype(np.float32)
+    return x, off
+
+
+def run_em(args):
+    """BASELINE configs[2]: one Baum-Welch iteration over the rank's shard of utterances; the packed float64 accumulator is
+    all-reduced over NCCL; every rank finalises the same M-step.  value = frames of ALL ranks / time of one iteration."""
+    import torch
+    import torch.distributed as dist
+    from lnasr.dist import make_reduce_fn
+    from lnasr.em import EmTrainer
+    from oracle import lnasr_oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = WORKLOADS["c3"]
+    mdl = O.random_gmmhmm(3, 8, 39, np.random.default_rng(7))
+    x_np, off = synth_feats(2000 + rank, cfg["n_utt"], cfg["min_t"], cfg["max_t"])
+    x_host = torch.from_numpy(x_np).pin_memory()
+    tr = EmTrainer(mdl).load_batch(x_host.cuda(), off)
+    reduce_fn = make_reduce_fn() if world > 1 else None
+    frames = int(off[-1])
+
+    def step():
+        return tr.iterate(reduce_fn)
+
+    def step_e2e():
+        tr._x.copy_(x_host, non_blocking=True)            # features from pinned host memory every iteration
+        return float(tr.iterate(reduce_fn).item())       # log-likelihood read back
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    ms_dev = timed(step, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, 3)
+    while time.perf_counter() - t0 < 1.5:
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+    total_frames = float(fr.item())
+    if rank == 0:
+        n, m, d = 3, 8, 39
+        per = 16 * n + 4 * d + 8 * n * m          # SURVEY.md 8(d): b fwd + alpha w/r + b bwd + x + bm
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sec = ms_dev / 1e3 / args.steps
+        ach = per * frames / sec / 1e9
+        line = {
+            "metric": "frames/sec (Baum-Welch EM iteration)", "value": total_frames / sec, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c3: " + cfg["desc"], "utts_per_gpu": cfg["n_utt"], "frames_per_gpu_step": frames,
+                       "l2": "x + b + bm + alpha = %.0f MB per step" % (frames * (4 * d + 8 * (2 * n + n * m)) / 1e6),
+                       "parallelism": f"utterance-sharded x{world}, one all-reduce of {tr.acc.numel()} float64 per iteration"},
+            "clocks": clocks,
+            "e2e": {"value": total_frames / (ms_e2e / 1e3 / args.steps), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": 8},
+            "gpu_launches": 7 * args.steps,       # pack x2 (SIMT + DMMA image), loglik, forward, fb_accumulate, mstep (+ memset)
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_frame": per, "kernel": "whole iteration"},
+            "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "not run for c3"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 def launches_per_step(pipe, want_paths):
     """Kernels of liblnasr_b200.so launched by one device-resident step."""
@@ -346,7 +509,25 @@ def stage_times(pipe, pcm_dev, off, want_paths, reps=5):
     return {k: {"ms": v / reps} for k, v in acc.items()}
 
 
-def roofline_for(name, st, frames, cfg, models, hbm_peak, peaks):
+def fp64_peaks():
+    """FP64 peaks of this GPU measured now (TFLOP/s): DFMA and mma.sync m8n8k4 f64 (csrc/capi.cu probes)."""
+    import ctypes as C
+    import torch
+    from lnasr import _capi
+    lib = _capi.lib()
+    scratch = torch.empty(int(lib.lnasr_debug_fp64_peak_scratch_doubles()), dtype=torch.float64, device="cuda")
+    out = {}
+    for kind, name in ((0, "fp64_fma_tflops"), (1, "fp64_mma_tflops")):
+        v = C.c_double(0.0)
+        _capi.check(lib.lnasr_debug_fp64_peak(kind, _capi.ptr(scratch), C.byref(v), _capi.stream_ptr()), "fp64_peak")
+        out[name] = v.value
+    return out
+
+
+MFCC_FP64_FLOPS_PER_FRAME = 18300     # 256-pt complex FFT 10.2k + split/power 4.1k + pre-emphasis/window 1.2k + mel 0.9k + log 0.8k + DCT 1.0k
+
+
+def roofline_for(name, st, frames, cfg, models, hbm_peak, peaks, fp64):
     """Algorithmic bytes / flops per frame x frames per launch / measured duration."""
     K = len(models)
     n, m = models[0]["w"].shape
@@ -355,25 +536,32 @@ def roofline_for(name, st, frames, cfg, models, hbm_peak, peaks):
     if name == "mfcc":
         per = 160 * 2 + 39 * 4                    # new int16 samples in + 39 fp32 features out (476 B)
         ach = per * frames / sec / 1e9
+        alu = MFCC_FP64_FLOPS_PER_FRAME * frames / sec / 1e12
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                "algorithmic_bytes_per_frame": per, "note": "front end is fp32-ALU bound (~35 kFLOP/frame), see DESIGN.md"}
+                "algorithmic_bytes_per_frame": per,
+                "fp64_alu": {"achieved_tflops": alu, "peak_tflops": fp64["fp64_fma_tflops"], "frac": alu / fp64["fp64_fma_tflops"],
+                             "algorithmic_flops_per_frame": MFCC_FP64_FLOPS_PER_FRAME},
+                "note": "nominally HBM-bound (476 B/frame) but the float64 chain (parity, DESIGN.md 5) makes it FP64-ALU / "
+                        "shared-memory bound: the fp64_alu entry is the roofline that binds"}
     if name == "viterbi":
         per = 8 * N                               # read b (4N as fp32-equivalent) + write backpointers (4N): SURVEY.md 8(d)
         ach = per * frames / sec / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                 "algorithmic_bytes_per_frame": per}
     # gmm
+    flops = 2 * 79 * N * m                        # 2 (2D+1) N M: the dense contraction of SURVEY.md 8(d)
     if cfg["emission"] == "tc":
-        flops = 2 * 79 * N * m                    # algorithmic; executed = 3x (3xTF32), K padded to 80
-        ach = flops * frames / sec / 1e12
+        ach = flops * frames / sec / 1e12         # executed = 3x (3xTF32), K padded to 80
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
         return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "algorithmic_flops_per_frame": flops, "executed_over_algorithmic": 3.04,
                 "note": "peak = 1/2 of measured sustained bf16 (TF32 runs at half the bf16 rate); no TF32 figure is measured"}
-    per = 39 * 4 + 8 * N                          # fp32 features in + float64 emissions out
-    ach = per * frames / sec / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-            "algorithmic_bytes_per_frame": per, "note": "float64 SIMT: 2*39*N*m fp64 FMA-pairs per frame, FP64-pipe bound"}
+    ach = flops * frames / sec / 1e12
+    peak = fp64["fp64_mma_tflops"]
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_flops_per_frame": flops, "executed_over_algorithmic": 80.0 / 79.0,
+            "note": "FP64 tensor cores (mma.sync m8n8k4 f64); peak = the same instruction measured in this run "
+                    "(lnasr_debug_fp64_peak), not in MEASURED_PEAKS.json which has no FP64 figure"}
 
 
 def main():
@@ -384,12 +572,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="utterance groups the host->device copy is pipelined over")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="utterance groups the host->device copy is pipelined over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload == "c3":
+        return run_em(args)
     return run_ours(args)
 
 

@@ -228,6 +228,10 @@ int lnasr_baumwelch_xi(const double* alpha, const double* beta, const double* b,
 int lnasr_debug_umma_probe(const float* a_image /*[a_bytes/4]*/, int32_t a_bytes, const float* b_image, int32_t b_bytes,
                            uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout_type,
                            uint32_t idesc, float* d_out /*[128,128]*/, void* stream);
+/* measured FP64 peak of the current device in TFLOP/s: kind 0 = DFMA, 1 = mma.sync m8n8k4 f64 (the denominators of the
+ * float64 kernels' rooflines; bench.py measures them in the same run).  tflops_out is a HOST pointer; synchronises. */
+int64_t lnasr_debug_fp64_peak_scratch_doubles(void);
+int lnasr_debug_fp64_peak(int kind, double* scratch, double* tflops_out /*host*/, void* stream);
 /* bring-up / test switch: 1 = lnasr_gmm_loglik_exact keeps the SIMT kernel even where the FP64 tensor-core (DMMA) kernel applies */
 int lnasr_debug_set_gmm_simt(int on);
 /* bring-up switch: exchange the LBO / SBO fields of the descriptors lnasr_gmm_loglik_tc builds (0 = as documented) */

@@ -142,6 +142,15 @@ trellis_small_kernel(TrellisArgs a) {
 #pragma unroll
     for (int i = 0; i < PF; ++i) bq[i] = (active && i < T) ? __ldg(bcol + emis_row(i) * a.ld_b) : BT(0);
     const double pi_j = (MODE != MODE_BACKWARD && active) ? __ldg(a.logpi + (int64_t)k * N + j) : neg_inf();
+    // running pointers (one add per step instead of 64-bit multiplies): emission row of step s+PF, output row of step s
+    const int64_t bstep = (MODE == MODE_BACKWARD) ? -a.ld_b : a.ld_b;
+    const BT* bnext = bcol + emis_row(PF) * a.ld_b;
+    const int64_t ostep = (MODE == MODE_BACKWARD) ? -ncol : ncol;
+    const int64_t o0 = ((MODE == MODE_BACKWARD) ? (f0 + T - 1) : f0) * ncol + col;
+    double* pfull = a.full_out ? a.full_out + o0 : nullptr;
+    uint32_t* pbt32 = (MODE == MODE_VITERBI && a.bt_out) ? a.bt_out + o0 : nullptr;
+    uint16_t* pbt16 = (MODE == MODE_VITERBI && a.bt_ws) ? a.bt_ws + o0 : nullptr;
+    const bool slow_out = (pfull != nullptr) || (pbt32 != nullptr);      // API-parity outputs (v / alpha / beta, uint32 bt)
 
     double cur = neg_inf();       // trellis value of my state
     for (int s0 = 0; s0 < Tmax; s0 += PF) {
@@ -149,7 +158,8 @@ trellis_small_kernel(TrellisArgs a) {
         for (int i = 0; i < PF; ++i) {
             const int s = s0 + i;
             const double e = (double)bq[i];
-            bq[i] = (active && s + PF < T) ? __ldg(bcol + emis_row(s + PF) * a.ld_b) : BT(0);
+            bq[i] = (active && s + PF < T) ? __ldg(bnext) : BT(0);
+            bnext += bstep;
             const bool live = active && s < T;
             double nv;
             int arg = 0;
@@ -182,24 +192,32 @@ trellis_small_kernel(TrellisArgs a) {
                 const double l = (mx == neg_inf()) ? mx : mx + log(sum);
                 nv = (s == 0) ? pi_j + e : l + e;
             } else {
-                // v[0] = pi + b[:,0] ; v[t,j] = max_i (v[t-1,i] + A[i,j]) + b[j,t] ; bt = first argmax (hmm.py:160-166)
-                double best = neg_inf();
+                // v[0] = pi + b[:,0] ; v[t,j] = max_i (v[t-1,i] + A[i,j]) + b[j,t] ; bt = FIRST argmax (hmm.py:160-166):
+                // maximum by a max tree, then the lowest q that attains it (all -inf -> 0, like np.argmax)
+                double cand[G];
 #pragma unroll
-                for (int q = 0; q < G; ++q) {
-                    const double c = grp(cur, q) + tr[q];
-                    if (c > best) { best = c; arg = q; }
-                }
+                for (int q = 0; q < G; ++q) cand[q] = grp(cur, q) + tr[q];
+                double best = cand[0];
+#pragma unroll
+                for (int q = 1; q < G; ++q) best = fmax(best, cand[q]);
+                arg = G - 1;
+#pragma unroll
+                for (int q = G - 2; q >= 0; --q) arg = (cand[q] == best) ? q : arg;
                 nv = (s == 0) ? pi_j + e : best + e;
                 if (s == 0) arg = 0;
             }
             if (live) {
                 cur = nv;
-                const int64_t row = (MODE == MODE_BACKWARD) ? (f0 + T - 1 - s) : (f0 + s);
-                if (a.full_out) a.full_out[row * ncol + col] = nv;
-                if (MODE == MODE_VITERBI) {
-                    if (a.bt_ws) a.bt_ws[row * ncol + col] = (uint16_t)arg;
-                    if (a.bt_out) a.bt_out[row * ncol + col] = (uint32_t)arg;
+                if (MODE == MODE_VITERBI && pbt16) *pbt16 = (uint16_t)arg;
+                if (slow_out) {
+                    if (pfull) *pfull = nv;
+                    if (MODE == MODE_VITERBI && pbt32) *pbt32 = (uint32_t)arg;
                 }
+            }
+            if (MODE == MODE_VITERBI && pbt16) pbt16 += ostep;
+            if (slow_out) {
+                if (pfull) pfull += ostep;
+                if (MODE == MODE_VITERBI && pbt32) pbt32 += ostep;
             }
         }
     }
@@ -227,10 +245,12 @@ trellis_small_kernel(TrellisArgs a) {
             // rows t+1 = T-1 .. 1 are consumed; round r covers rows hi .. hi-TS_BT+1 with hi = Tmax-1 - r*TS_BT
             for (int hi = Tmax - 1; hi >= 1; hi -= TS_BT) {
                 uint16_t q[TS_BT];
+                const uint16_t* bp = a.bt_ws + (f0 + hi) * ncol + col;
 #pragma unroll
                 for (int i = 0; i < TS_BT; ++i) {
                     const int row = hi - i;
-                    q[i] = (active && row >= 1 && row < T) ? a.bt_ws[(f0 + row) * ncol + col] : (uint16_t)0;
+                    q[i] = (active && row >= 1 && row < T) ? *bp : (uint16_t)0;
+                    bp -= ncol;
                 }
                 int mine = 0;                                      // state of frame hi-1-j, kept by lane j for a coalesced store
 #pragma unroll

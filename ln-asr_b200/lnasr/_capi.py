@@ -58,6 +58,8 @@ SIGNATURES = {
     "lnasr_gmm_loglik_tc": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, vp, i64, vp, sz, vp]),
     "lnasr_debug_set_umma_swap": (C.c_int, [C.c_int]),
     "lnasr_debug_set_gmm_simt": (C.c_int, [C.c_int]),
+    "lnasr_debug_fp64_peak_scratch_doubles": (i64, []),
+    "lnasr_debug_fp64_peak": (C.c_int, [C.c_int, vp, C.POINTER(C.c_double), vp]),
     "lnasr_emit_gather": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
     "lnasr_trans_degree": (C.c_int, [vp, i32, i32, vp, vp]),
     "lnasr_trans_pack": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),

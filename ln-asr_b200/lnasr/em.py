@@ -1,0 +1,95 @@
+"""Device-resident Baum-Welch for a GMM-HMM over a ragged batch of utterances (additive API; BASELINE config 3).
+
+`GMMHMM.train` / `train_batch` mirror the reference's loop (hmm.py:285-313): the model lives in numpy attributes and every
+iteration makes a host round trip.  `EmTrainer` keeps the model ON THE DEVICE for the whole run; one iteration is
+
+    lnasr_gmm_pack_exact -> lnasr_gmm_loglik_exact (b, bm) -> lnasr_forward_batch (alpha) -> lnasr_fb_accumulate
+    -> [all-reduce of the packed float64 accumulator over ranks] -> lnasr_mstep_finalize (in place)
+
+with no host synchronisation, so iterations can be queued back to back and the only multi-GPU traffic is the
+accumulator (lnasr_em_acc_doubles values, 15 KB for 3 states x 8 mixtures x 39 dims).  Every rank finalises the same
+numbers, so replicas stay bit-identical.  Semantics = GMMHMM._estimate (gmmhmm.py:69-156) in
+sufficient-statistic form with a diagonal covariance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi, _dev
+
+__all__ = ["EmTrainer"]
+
+
+class EmTrainer:
+    def __init__(self, model, min_std: Optional[float] = None):
+        """model: lnasr.gmmhmm.GMMHMM (or a dict with A, pi, w, mu and var [n,m,d] / si [n,m,d,d])."""
+        t = _dev.torch()
+        get = (lambda k: model[k]) if isinstance(model, dict) else (lambda k: getattr(model, k))
+        if isinstance(model, dict) and "var" in model:
+            var = np.asarray(model["var"], dtype=np.float64)
+        else:
+            var = np.diagonal(np.asarray(get("si"), dtype=np.float64), axis1=2, axis2=3).copy()
+        self.n, self.m, self.d = var.shape
+        if self.n > 32:
+            raise _capi.LnasrError("EmTrainer: the fused Baum-Welch kernel is built for n <= 32 states")
+        self.min_std = float(min_std if min_std is not None else (0.01 if isinstance(model, dict) else model.min_std))
+        self.logA = _dev.to_dev(np.asarray(get("A"), dtype=np.float64), t.float64)
+        self.logpi = _dev.to_dev(np.asarray(get("pi"), dtype=np.float64).reshape(-1), t.float64)
+        self.logw = _dev.to_dev(np.asarray(get("w"), dtype=np.float64), t.float64)
+        self.mu = _dev.to_dev(np.asarray(get("mu"), dtype=np.float64), t.float64)
+        self.var = _dev.to_dev(var, t.float64)
+        lib = _capi.lib()
+        self.packed = _dev.empty((int(lib.lnasr_gmm_exact_packed_doubles(self.n, self.m, self.d)),), t.float64)
+        self.acc = _dev.zeros((int(lib.lnasr_em_acc_doubles(self.n, self.m, self.d)),), t.float64)
+        self._bank = _capi.HmmBank(n_models=1, N=self.n, logA=self.logA.data_ptr(), logpi=self.logpi.data_ptr(),
+                                   max_in=0, max_out=0, pred_idx=0, pred_val=0, succ_idx=0, succ_val=0)
+        self._x = None
+
+    def load_batch(self, feats, frame_offsets):
+        """feats [T_total, d] CUDA tensor (float32/float64); frame_offsets [n_utt+1] host.  Buffers are allocated once."""
+        t = _dev.torch()
+        off = np.asarray(frame_offsets, dtype=np.int64)
+        self._x = _dev.to_dev(feats)
+        self._off_d = _dev.to_dev(off, t.int64)
+        self._n_utt, self._total = len(off) - 1, int(off[-1])
+        T = self._total
+        self._b = _dev.empty((T, self.n), t.float64)
+        self._bm = _dev.empty((T, self.n * self.m), t.float64)
+        self._alpha = _dev.empty((T, self.n), t.float64)
+        self._lp = _dev.empty((self._n_utt, 1), t.float64)
+        return self
+
+    def iterate(self, reduce_fn=None):
+        """One EM iteration, fully asynchronous.  Returns a 1-element device tensor: the total log-likelihood of the
+        batch (all ranks) under the model BEFORE the update (hmm.py:301)."""
+        if self._x is None:
+            raise _capi.LnasrError("EmTrainer.iterate: call load_batch first")
+        lib, ptr, st = _capi.lib(), _capi.ptr, _capi.stream_ptr()
+        x, n, m, d, T = self._x, self.n, self.m, self.d, self._total
+        _capi.check(lib.lnasr_gmm_pack_exact(ptr(self.logw), ptr(self.mu), ptr(self.var), n, m, d, ptr(self.packed), st), "gmm_pack_exact")
+        _capi.check(lib.lnasr_gmm_loglik_exact(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), T, ptr(self.packed), n, m, d,
+                                               ptr(self._b), _capi.DT_F64, n, ptr(self._bm), st), "gmm_loglik_exact")
+        _capi.check(lib.lnasr_forward_batch(ptr(self._b), _capi.DT_F64, n, ptr(self._off_d), self._n_utt, T,
+                                            C.byref(self._bank), ptr(self._alpha), ptr(self._lp), st), "forward_batch")
+        self.acc.zero_()
+        _capi.check(lib.lnasr_fb_accumulate(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), ptr(self._b), ptr(self._bm),
+                                            ptr(self._alpha), ptr(self._off_d), self._n_utt, T, ptr(self.logA), ptr(self.logw),
+                                            ptr(self.mu), n, m, d, ptr(self.acc), None, None, st), "fb_accumulate")
+        if reduce_fn is not None:
+            reduce_fn(self.acc)                       # SUM over ranks of S0 | S1 | S2c | xi_sum | pi_occ | loglik | n_utt
+        loglik = self.acc[-2:-1].clone()
+        _capi.check(lib.lnasr_mstep_finalize(ptr(self.acc), n, m, d, self.min_std, ptr(self.logA), ptr(self.logpi),
+                                             ptr(self.logw), ptr(self.mu), ptr(self.var), st), "mstep_finalize")
+        return loglik
+
+    def export(self) -> dict:
+        """Current model as numpy arrays: A, pi, w (log), mu, var [n,m,d] and si = diag(var) [n,m,d,d]."""
+        var = self.var.cpu().numpy()
+        si = np.zeros((self.n, self.m, self.d, self.d))
+        idx = np.arange(self.d)
+        si[:, :, idx, idx] = var
+        return {"A": self.logA.cpu().numpy(), "pi": self.logpi.cpu().numpy(), "w": self.logw.cpu().numpy(),
+                "mu": self.mu.cpu().numpy(), "var": var, "si": si}

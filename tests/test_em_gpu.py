@@ -119,3 +119,35 @@ def test_multi_utterance_em_against_oracle(n, mix, d, n_utt):
         assert_close(np.exp(m.w), np.exp(new_ref["w"]), 1e-8, "w")
         assert_close(np.exp(m.A), np.exp(new_ref["A"]), 1e-8, "A")
         assert_close(np.exp(m.pi), np.exp(new_ref["pi"]), 1e-8, "pi")
+
+
+def test_device_resident_em_trainer_matches_oracle():
+    """lnasr.em.EmTrainer (model stays on the device, BASELINE config 3 shape): three iterations against the oracle's
+    multi-utterance EM, and against GMMHMM.train_batch."""
+    import torch
+    from lnasr.em import EmTrainer
+    from lnasr.gmmhmm import GMMHMM
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(3)
+    n, mix, d = 3, 8, 39
+    mdl = O.random_gmmhmm(n, mix, d, rng)
+    utts = [0.6 * rng.standard_normal((int(T), d)) for T in rng.integers(20, 60, size=9)]
+    off = np.concatenate([[0], np.cumsum([len(u) for u in utts])])
+    tr = EmTrainer(mdl).load_batch(torch.from_numpy(np.concatenate(utts)).cuda(), off)
+    ref = dict(mdl)
+    m = GMMHMM(n, mix, d, A=mdl["A"], pi=mdl["pi"], w=mdl["w"], mu=mdl["mu"], si=mdl["var"][..., None] * np.eye(d))
+    for it in range(3):
+        ll = float(tr.iterate().item())
+        ref, tot = O.em_step_multi_diag(utts, ref)
+        assert abs(ll - tot["loglik"]) < 1e-8 * abs(tot["loglik"]), it
+    hist = m.train_batch(utts, iters=3, eps=0.0, verbose=False)
+    got = tr.export()
+    assert_close(got["mu"], ref["mu"], 1e-7, "mu")                          # bar: 1e-4 relative
+    assert_close(got["var"], ref["var"], 1e-7, "var")
+    assert_close(got["mu"], m.mu, 1e-9, "mu vs train_batch")
+    assert_close(got["var"], m.var, 1e-9, "var vs train_batch")
+    with np.errstate(all="ignore"):
+        assert_close(np.exp(got["w"]), np.exp(ref["w"]), 1e-7, "w")
+        assert_close(np.exp(got["A"]), np.exp(ref["A"]), 1e-7, "A")
+        assert_close(np.exp(got["pi"]), np.exp(ref["pi"]), 1e-7, "pi")
+    assert got["si"].shape == (n, mix, d, d) and len(hist) == 3
