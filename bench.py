@@ -429,11 +429,10 @@ def run_em(args):
         return float(ms.item())
 
     sampler = ClockSampler(local) if rank == 0 else None
-    t0 = time.perf_counter()
     ms_dev = timed(step, args.steps, args.warmup)
     ms_e2e = timed(step_e2e, args.steps, 3)
-    while time.perf_counter() - t0 < 1.5:
-        step()
+    for _ in range(400):                                  # ~1 s more load for the clock sampler; a FIXED count on every
+        step()                                            # rank (each step holds a collective -- never loop on wall time)
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
