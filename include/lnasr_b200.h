@@ -232,7 +232,8 @@ int lnasr_debug_umma_probe(const float* a_image /*[a_bytes/4]*/, int32_t a_bytes
  * float64 kernels' rooflines; bench.py measures them in the same run).  tflops_out is a HOST pointer; synchronises. */
 int64_t lnasr_debug_fp64_peak_scratch_doubles(void);
 int lnasr_debug_fp64_peak(int kind, double* scratch, double* tflops_out /*host*/, void* stream);
-/* bring-up / test switch: 1 = lnasr_gmm_loglik_exact keeps the SIMT kernel even where the FP64 tensor-core (DMMA) kernel applies */
+/* bring-up / test switch for lnasr_gmm_loglik_exact: 0 = default choice (persistent DMMA kernel when the model image fits in
+ * shared memory, else streaming DMMA kernel, else SIMT), 1 = always SIMT, 2 = streaming DMMA instead of persistent */
 int lnasr_debug_set_gmm_simt(int on);
 /* bring-up switch: exchange the LBO / SBO fields of the descriptors lnasr_gmm_loglik_tc builds (0 = as documented) */
 int lnasr_debug_set_umma_swap(int swap);

@@ -233,6 +233,69 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+
+// epilogue of both DMMA kernels: + log w, log-sum-exp over the MP (padded) mixtures of a state, stores.  `acc` are the
+// accumulator fragments of GM_MT m-blocks x GM_NT n-blocks; tbase = first frame of m-block 0; W = this group's rows.
+template <int MP, typename OutT>
+__device__ __forceinline__ void gm_epilogue(double (&acc)[GM_MT][GM_NT][2], const double* __restrict__ W, int g, int64_t tbase,
+                                            int r, int c, int64_t n_frames, int n_states, int n_mix, int64_t n_gauss,
+                                            OutT* __restrict__ b_out, int64_t ld_b, double* __restrict__ bm_out,
+                                            const double2* __restrict__ log_tab, const double* __restrict__ exp_tab) {
+    // ---- epilogue: + log w, log-sum-exp over the MP (padded) mixtures of a state, stores
+#pragma unroll
+    for (int nb = 0; nb < GM_NT; ++nb) {
+        const int gl = nb * 8 + 2 * c;                                   // my first Gaussian inside the group
+        const int64_t gp = (int64_t)g * GM_GROUP + gl;                   // padded global Gaussian index (row of the image)
+        const double lw0 = W[(size_t)gl * GM_LDB + 80], lw1 = W[(size_t)(gl + 1) * GM_LDB + 80];
+        const int64_t st0 = gp / MP, st1 = (gp + 1) / MP;
+        const int mx0 = (int)(gp % MP), mx1 = (int)((gp + 1) % MP);
+        double mxv[GM_MT], sum[GM_MT];
+#pragma unroll
+        for (int mb = 0; mb < GM_MT; ++mb) {
+            const int64_t t = tbase + mb * 8 + r;
+            const bool ok = t < n_frames;
+            const double g0 = acc[mb][nb][0], g1 = acc[mb][nb][1];       // pure Gaussian log-densities (gmm.py:59-68)
+            if (bm_out && ok) {                                          // gmmhmm.py:66
+                if (st0 < n_states && mx0 < n_mix) bm_out[t * n_gauss + st0 * n_mix + mx0] = g0;
+                if (st1 < n_states && mx1 < n_mix) bm_out[t * n_gauss + st1 * n_mix + mx1] = g1;
+            }
+            const double v0 = g0 + lw0, v1 = g1 + lw1;                   // + log w[j,m] (gmmhmm.py:67)
+            if (MP == 1) {
+                if (ok && st0 < n_states) b_out[t * ld_b + st0] = (OutT)v0;
+                if (ok && st1 < n_states) b_out[t * ld_b + st1] = (OutT)v1;
+            } else {
+                double mx = fmax(v0, v1);
+                if (MP >= 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                if (MP >= 8) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                double sm = 0.0;
+                if (mx != neg_inf()) sm = fast_exp_neg(v0 - mx, exp_tab) + fast_exp_neg(v1 - mx, exp_tab);
+                if (MP >= 4) sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+                if (MP >= 8) sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                mxv[mb] = mx;
+                sum[mb] = sm;
+            }
+        }
+        if (MP == 2) {
+#pragma unroll
+            for (int mb = 0; mb < GM_MT; ++mb) {
+                const int64_t t = tbase + mb * 8 + r;
+                if (t < n_frames && st0 < n_states)
+                    b_out[t * ld_b + st0] = (OutT)((mxv[mb] == neg_inf()) ? mxv[mb] : mxv[mb] + fast_log(sum[mb], log_tab));
+            }
+        } else if (MP >= 4) {
+            // the 2 (MP=4) or 4 (MP=8) lanes that share a state hold identical (max, sum) for every m-block: each of
+            // them finishes a different m-block, so the log is taken once per result instead of once per lane
+            static_assert(GM_MT == 2, "the m-block hand-out below assumes two m-blocks per warp");
+            const int mb = c & 1;
+            const double mx = mb ? mxv[1] : mxv[0], sm = mb ? sum[1] : sum[0];
+            const int64_t t = tbase + mb * 8 + r;
+            const bool writer = (MP == 4) || (c < 2);
+            if (writer && t < n_frames && st0 < n_states)
+                b_out[t * ld_b + st0] = (OutT)((mx == neg_inf()) ? mx : mx + fast_log(sm, log_tab));
+        }
+    }
+}
+
 template <int MP, typename FeatT, typename OutT>
 __global__ void __launch_bounds__(GM_WARPS * 32, 2)
 gmm_loglik_mma_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_frames, const double* __restrict__ img,
@@ -288,60 +351,99 @@ gmm_loglik_mma_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_f
 #pragma unroll
                 for (int nb = 0; nb < GM_NT; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bf[nb]);
         }
-        // ---- epilogue: + log w, log-sum-exp over the MP (padded) mixtures of a state, stores
-#pragma unroll
-        for (int nb = 0; nb < GM_NT; ++nb) {
-            const int gl = nb * 8 + 2 * c;                                   // my first Gaussian inside the group
-            const int64_t gp = (int64_t)g * GM_GROUP + gl;                   // padded global Gaussian index (row of the image)
-            const double lw0 = W[(size_t)gl * GM_LDB + 80], lw1 = W[(size_t)(gl + 1) * GM_LDB + 80];
-            const int64_t st0 = gp / MP, st1 = (gp + 1) / MP;
-            const int mx0 = (int)(gp % MP), mx1 = (int)((gp + 1) % MP);
-            double mxv[GM_MT], sum[GM_MT];
-#pragma unroll
-            for (int mb = 0; mb < GM_MT; ++mb) {
-                const int64_t t = t0 + (warp * GM_MT + mb) * 8 + r;
-                const bool ok = t < n_frames;
-                const double g0 = acc[mb][nb][0], g1 = acc[mb][nb][1];       // pure Gaussian log-densities (gmm.py:59-68)
-                if (bm_out && ok) {                                          // gmmhmm.py:66
-                    if (st0 < n_states && mx0 < n_mix) bm_out[t * n_gauss + st0 * n_mix + mx0] = g0;
-                    if (st1 < n_states && mx1 < n_mix) bm_out[t * n_gauss + st1 * n_mix + mx1] = g1;
-                }
-                const double v0 = g0 + lw0, v1 = g1 + lw1;                   // + log w[j,m] (gmmhmm.py:67)
-                if (MP == 1) {
-                    if (ok && st0 < n_states) b_out[t * ld_b + st0] = (OutT)v0;
-                    if (ok && st1 < n_states) b_out[t * ld_b + st1] = (OutT)v1;
-                } else {
-                    double mx = fmax(v0, v1);
-                    if (MP >= 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                    if (MP >= 8) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                    double sm = 0.0;
-                    if (mx != neg_inf()) sm = fast_exp_neg(v0 - mx, exp_tab) + fast_exp_neg(v1 - mx, exp_tab);
-                    if (MP >= 4) sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-                    if (MP >= 8) sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-                    mxv[mb] = mx;
-                    sum[mb] = sm;
-                }
-            }
-            if (MP == 2) {
-#pragma unroll
-                for (int mb = 0; mb < GM_MT; ++mb) {
-                    const int64_t t = t0 + (warp * GM_MT + mb) * 8 + r;
-                    if (t < n_frames && st0 < n_states)
-                        b_out[t * ld_b + st0] = (OutT)((mxv[mb] == neg_inf()) ? mxv[mb] : mxv[mb] + fast_log(sum[mb], log_tab));
-                }
-            } else if (MP >= 4) {
-                // the 2 (MP=4) or 4 (MP=8) lanes that share a state hold identical (max, sum) for every m-block: each of
-                // them finishes a different m-block, so the log is taken once per result instead of once per lane
-                static_assert(GM_MT == 2, "the m-block hand-out below assumes two m-blocks per warp");
-                const int mb = c & 1;
-                const double mx = mb ? mxv[1] : mxv[0], sm = mb ? sum[1] : sum[0];
-                const int64_t t = t0 + (warp * GM_MT + mb) * 8 + r;
-                const bool writer = (MP == 4) || (c < 2);
-                if (writer && t < n_frames && st0 < n_states)
-                    b_out[t * ld_b + st0] = (OutT)((mx == neg_inf()) ? mx : mx + fast_log(sm, log_tab));
+        gm_epilogue<MP, OutT>(acc, W, g, t0 + (int64_t)warp * GM_MT * 8, r, c, n_frames, n_states, n_mix, n_gauss, b_out, ld_b,
+                              bm_out, log_tab, exp_tab);
+        __syncthreads();                                       // buffer g&1 is refilled by issue(g+2)
+    }
+}
+
+// Persistent variant for models whose whole DMMA image fits in shared memory (config 2: 200 Gaussians = 134 KB; configs 1
+// and 3 a single group): one block per SM loads the image ONCE, then every WARP is an independent worker that walks
+// 16-frame slabs -- its own x slab arrives by cp.async one slab ahead, and there is no block barrier after the prologue.
+// Warps therefore drift out of phase and the DMMA phase of one warp overlaps the exp / log epilogue of another (the
+// streaming kernel above keeps all warps of a block in the same phase with its per-group barriers: tensor pipe 51 %).
+constexpr int GR_MAX_WARPS = 16;
+
+template <typename FeatT>
+__device__ __forceinline__ void cp_async_elem(FeatT* dst, const FeatT* src) {
+    if (sizeof(FeatT) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int MP, typename FeatT, typename OutT>
+__global__ void __launch_bounds__(GR_MAX_WARPS * 32, 1)
+gmm_loglik_mma_resident_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_frames, const double* __restrict__ img,
+                               int n_states, int n_mix, int dim, int n_groups, OutT* __restrict__ b_out, int64_t ld_b,
+                               double* __restrict__ bm_out) {
+    extern __shared__ __align__(16) unsigned char gx_smem[];
+    const int ldx = gm_ldx(dim), ks = gm_ksteps(dim);
+    const int n_warps = blockDim.x >> 5;
+    double* W = reinterpret_cast<double*>(gx_smem);                          // [n_groups*40][84]
+    double2* log_tab = reinterpret_cast<double2*>(W + (size_t)n_groups * GM_GROUP * GM_LDB);
+    double* exp_tab = reinterpret_cast<double*>(log_tab + 128);
+    FeatT* xall = reinterpret_cast<FeatT*>(exp_tab + 64);                    // [n_warps][2][16][ldx]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, c = lane & 3;
+    for (int64_t i = tid; i < (int64_t)n_groups * GM_GROUP * GM_LDB / 2; i += blockDim.x) cp_async16(W + 2 * i, img + 2 * i);
+    cp_async_commit();
+    fill_log_exp_tables(log_tab, exp_tab, tid, blockDim.x);
+    FeatT* xw = xall + (size_t)warp * 2 * 16 * ldx;
+    for (int i = lane; i < 2 * 16 * ldx; i += 32)          // constant column x[dim] = 1 and zero padding; columns < dim arrive by cp.async
+        if ((i % ldx) >= dim) xw[i] = ((i % ldx) == dim) ? FeatT(1) : FeatT(0);
+    const int64_t n_slabs = (n_frames + 15) >> 4;
+    const int64_t wstride = (int64_t)gridDim.x * n_warps;
+    int64_t slab = (int64_t)blockIdx.x * n_warps + warp;
+    auto fetch = [&](int64_t sl, int buf) {                // x rows of slab sl -> buffer buf (columns < dim only)
+        if (sl < n_slabs) {
+            FeatT* dst = xw + (size_t)buf * 16 * ldx;
+            const int64_t t0 = sl << 4;
+            const int rows = (int)min((int64_t)16, n_frames - t0);
+            for (int i = lane; i < rows * dim; i += 32) {
+                const int row = i / dim, col = i - row * dim;
+                cp_async_elem(dst + row * ldx + col, feats + (t0 + row) * ld_feats + col);
             }
         }
-        __syncthreads();                                       // buffer g&1 is refilled by issue(g+2)
+        cp_async_commit();
+    };
+    __syncwarp();
+    fetch(slab, 0);
+    cp_async_wait<0>();
+    __syncthreads();                                       // the image, the tables and (per warp) the first slab are in place
+    const bool sq = (c & 1) == 0;                          // even k: x^2, odd k: x
+    const int64_t n_gauss = (int64_t)n_states * n_mix;
+    for (int it = 0; slab < n_slabs; slab += wstride, ++it) {
+        const int buf = it & 1;
+        fetch(slab + wstride, buf ^ 1);                    // next slab flies during this one
+        const FeatT* xrow = xw + (size_t)buf * 16 * ldx + (size_t)r * ldx + (c >> 1);
+        const int64_t t0 = slab << 4;
+        for (int g = 0; g < n_groups; ++g) {
+            const double* Wg = W + (size_t)g * GM_GROUP * GM_LDB;
+            const double* wrow = Wg + (size_t)r * GM_LDB + c;
+            double acc[GM_MT][GM_NT][2];
+#pragma unroll
+            for (int mb = 0; mb < GM_MT; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < GM_NT; ++nb) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+#pragma unroll 2
+            for (int j = 0; j < ks; ++j) {
+                double a[GM_MT], bf[GM_NT];
+#pragma unroll
+                for (int mb = 0; mb < GM_MT; ++mb) {
+                    const double xv = (double)xrow[(size_t)mb * 8 * ldx + 2 * j];
+                    a[mb] = sq ? xv * xv : xv;
+                }
+#pragma unroll
+                for (int nb = 0; nb < GM_NT; ++nb) bf[nb] = wrow[(size_t)nb * 8 * GM_LDB + 4 * j];
+#pragma unroll
+                for (int mb = 0; mb < GM_MT; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < GM_NT; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bf[nb]);
+            }
+            gm_epilogue<MP, OutT>(acc, Wg, g, t0, r, c, n_frames, n_states, n_mix, n_gauss, b_out, ld_b, bm_out, log_tab, exp_tab);
+        }
+        cp_async_wait<0>();
+        __syncwarp();                                      // the next slab has landed and every lane is done with this buffer
     }
 }
 
@@ -446,11 +548,41 @@ static int launch_exact(const void* feats, int ld_feats, int64_t n_frames, const
 }
 
 
+static bool g_force_simt = false;     // bring-up / test switches: lnasr_debug_set_gmm_simt(1) keeps the SIMT kernel,
+static bool g_force_stream = false;   // (2) keeps the streaming DMMA kernel where the persistent one applies
+
 template <typename FeatT, typename OutT>
 static int launch_mma(const void* feats, int ld_feats, int64_t n_frames, const double* packed, int n_states,
                       int n_mix, int dim, void* b_out, int64_t ld_b, double* bm_out, cudaStream_t stream) {
     const double* img = packed + gx_simt_doubles(n_states, n_mix, dim);
     const int n_groups = (int)gm_groups(n_states, n_mix);
+    // persistent kernel with the whole image resident when it leaves room for >= 8 warps of double-buffered x slabs
+    {
+        const size_t fixed = ((size_t)n_groups * GM_GROUP * GM_LDB + 256 + 64) * sizeof(double);
+        const size_t per_warp = (size_t)2 * 16 * gm_ldx(dim) * sizeof(FeatT);
+        const size_t cap = 226 * 1024;
+        int nw = fixed < cap ? (int)std::min<size_t>(GR_MAX_WARPS, (cap - fixed) / per_warp) : 0;
+        const int64_t n_slabs = ceil_div(n_frames, 16);
+        if (nw >= 8 && !g_force_stream) {
+            const size_t smem_r = fixed + (size_t)nw * per_warp;
+            const unsigned grid_r = (unsigned)std::min<int64_t>(sm_count(), ceil_div(n_slabs, nw));
+#define LNASR_GR_LAUNCH(MPV)                                                                                              \
+    do {                                                                                                                  \
+        LNASR_CUDA(cudaFuncSetAttribute(gmm_loglik_mma_resident_kernel<MPV, FeatT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)); \
+        gmm_loglik_mma_resident_kernel<MPV, FeatT, OutT><<<grid_r, nw * 32, smem_r, stream>>>(                            \
+            (const FeatT*)feats, ld_feats, n_frames, img, n_states, n_mix, dim, n_groups, (OutT*)b_out, ld_b, bm_out);    \
+    } while (0)
+            switch (gm_mpad(n_mix)) {
+                case 1: LNASR_GR_LAUNCH(1); break;
+                case 2: LNASR_GR_LAUNCH(2); break;
+                case 4: LNASR_GR_LAUNCH(4); break;
+                default: LNASR_GR_LAUNCH(8); break;
+            }
+#undef LNASR_GR_LAUNCH
+            LNASR_LAUNCH_CHECK();
+            return LNASR_OK;
+        }
+    }
     const size_t smem = ((size_t)GM_TILE * gm_ldx(dim) + 2 * GM_GROUP * GM_LDB + 256 + 64) * sizeof(double);
     const unsigned grid = (unsigned)ceil_div(n_frames, GM_TILE);
 #define LNASR_GM_LAUNCH(MPV)                                                                                              \
@@ -470,9 +602,8 @@ static int launch_mma(const void* feats, int ld_feats, int64_t n_frames, const d
     return LNASR_OK;
 }
 
-static bool g_force_simt = false;     // bring-up / test switch: lnasr_debug_set_gmm_simt(1) keeps the SIMT kernel
 
-extern "C" int lnasr_debug_set_gmm_simt(int on) { g_force_simt = (on != 0); return LNASR_OK; }
+extern "C" int lnasr_debug_set_gmm_simt(int on) { g_force_simt = (on == 1); g_force_stream = (on == 2); return LNASR_OK; }
 
 extern "C" int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype, int32_t ld_feats, int64_t n_frames,
                                       const double* packed, int32_t n_states, int32_t n_mix, int32_t dim,

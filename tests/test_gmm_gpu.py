@@ -44,11 +44,23 @@ def test_map_b_diagonal_matches_reference(golden):
     assert_close(m.bm, g["dg_bm"], 1e-10, "bm")
 
 
-@pytest.mark.parametrize("n,m,d,T", [(1, 1, 1, 7), (3, 8, 39, 300), (50, 4, 39, 257), (7, 3, 2, 40), (200, 16, 39, 130)])
-def test_exact_kernel_against_oracle(n, m, d, T):
+@pytest.fixture
+def gmm_kernel_switch():
+    """lnasr_debug_set_gmm_simt: 0 = default (persistent DMMA when the image fits shared memory, else streaming DMMA, else
+    SIMT), 1 = SIMT, 2 = streaming DMMA.  Restored to 0 afterwards."""
+    from lnasr import _capi
+    yield _capi.lib().lnasr_debug_set_gmm_simt
+    _capi.lib().lnasr_debug_set_gmm_simt(0)
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("n,m,d,T", [(1, 1, 1, 7), (3, 8, 39, 300), (50, 4, 39, 257), (7, 3, 2, 40), (200, 16, 39, 130),
+                                     (9, 2, 13, 1000), (33, 5, 39, 77), (400, 4, 39, 33), (6, 1, 39, 129)])
+def test_exact_kernel_against_oracle(n, m, d, T, kernel, gmm_kernel_switch):
     import torch
     from lnasr.gmm import PackedGmm
     from oracle import lnasr_oracle as O
+    gmm_kernel_switch(kernel)
     rng = np.random.default_rng(n * 1000 + m)
     mdl = O.random_gmmhmm(n, m, d, rng)
     x = rng.standard_normal((T, d)) * 0.5
