@@ -96,12 +96,14 @@ __device__ __forceinline__ double fast_log(double x, const double2* __restrict__
 // exp(d) for d <= 0 (the terms of a log-sum-exp after subtracting the maximum): d = (n/64) ln2 + r, |r| <= ln2/128,
 // exp(d) = 2^(n>>6) * T[n & 63] * P5(r); relative error ~2e-16, 10 DFMA instead of the ~20 of exp().  T = 2^(i/64).
 __device__ __forceinline__ double fast_exp_neg(double d, const double* __restrict__ t64) {
-    if (!(d > -700.0)) return (d != d) ? d : 0.0;                   // -inf and anything below e^-700: 0 ; NaN stays NaN
+    // branch-free: anything below e^-700 (and -inf, and the NaN of -inf - -inf) gives 0 through the final select
+    const bool ok = d > -700.0;
+    const double dc = ok ? d : -700.0;
     const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52: the integer lands in the low word
-    double nf = fma(d, 92.33248261689366, MAGIC);                   // 64 / ln 2
+    double nf = fma(dc, 92.33248261689366, MAGIC);                  // 64 / ln 2
     const int n = __double2loint(nf);
     nf -= MAGIC;
-    double r = fma(nf, -0.01083042469326756, d);                    // ln2/64, high part (32 significant bits)
+    double r = fma(nf, -0.01083042469326756, dc);                   // ln2/64, high part (32 significant bits)
     r = fma(nf, -2.9815858269852933e-12, r);                        //         low part
     double p = 1.0 / 120.0;
     p = fma(p, r, 1.0 / 24.0);
@@ -110,7 +112,8 @@ __device__ __forceinline__ double fast_exp_neg(double d, const double* __restric
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const double res = t64[n & 63] * p;
-    return __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+    const double v = __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+    return ok ? v : 0.0;
 }
 
 // block-wide set-up of the two tables above: log_tab[128] = (1/c_i, -ln c_i), exp_tab[64] = 2^(i/64)

@@ -267,8 +267,7 @@ __device__ __forceinline__ void gm_epilogue(double (&acc)[GM_MT][GM_NT][2], cons
                 double mx = fmax(v0, v1);
                 if (MP >= 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                 if (MP >= 8) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                double sm = 0.0;
-                if (mx != neg_inf()) sm = fast_exp_neg(v0 - mx, exp_tab) + fast_exp_neg(v1 - mx, exp_tab);
+                double sm = fast_exp_neg(v0 - mx, exp_tab) + fast_exp_neg(v1 - mx, exp_tab);    // mx = -inf: NaN -> 0
                 if (MP >= 4) sm += __shfl_xor_sync(0xffffffffu, sm, 1);
                 if (MP >= 8) sm += __shfl_xor_sync(0xffffffffu, sm, 2);
                 mxv[mb] = mx;
@@ -425,20 +424,32 @@ gmm_loglik_mma_resident_kernel(const FeatT* __restrict__ feats, int ld_feats, in
             for (int mb = 0; mb < GM_MT; ++mb)
 #pragma unroll
                 for (int nb = 0; nb < GM_NT; ++nb) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+            // fragments of k-step j+1 are loaded before the 10 DMMAs of k-step j are issued
+            FeatT xa[GM_MT];
+            double bf[GM_NT];
+#pragma unroll
+            for (int mb = 0; mb < GM_MT; ++mb) xa[mb] = xrow[(size_t)mb * 8 * ldx];
+#pragma unroll
+            for (int nb = 0; nb < GM_NT; ++nb) bf[nb] = wrow[(size_t)nb * 8 * GM_LDB];
 #pragma unroll 2
             for (int j = 0; j < ks; ++j) {
-                double a[GM_MT], bf[GM_NT];
+                double a[GM_MT], bc[GM_NT];
 #pragma unroll
                 for (int mb = 0; mb < GM_MT; ++mb) {
-                    const double xv = (double)xrow[(size_t)mb * 8 * ldx + 2 * j];
+                    const double xv = (double)xa[mb];
                     a[mb] = sq ? xv * xv : xv;
                 }
 #pragma unroll
-                for (int nb = 0; nb < GM_NT; ++nb) bf[nb] = wrow[(size_t)nb * 8 * GM_LDB + 4 * j];
+                for (int nb = 0; nb < GM_NT; ++nb) bc[nb] = bf[nb];
+                const int jn = (j + 1 < ks) ? j + 1 : j;
+#pragma unroll
+                for (int mb = 0; mb < GM_MT; ++mb) xa[mb] = xrow[(size_t)mb * 8 * ldx + 2 * jn];
+#pragma unroll
+                for (int nb = 0; nb < GM_NT; ++nb) bf[nb] = wrow[(size_t)nb * 8 * GM_LDB + 4 * jn];
 #pragma unroll
                 for (int mb = 0; mb < GM_MT; ++mb)
 #pragma unroll
-                    for (int nb = 0; nb < GM_NT; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bf[nb]);
+                    for (int nb = 0; nb < GM_NT; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bc[nb]);
             }
             gm_epilogue<MP, OutT>(acc, Wg, g, t0, r, c, n_frames, n_states, n_mix, n_gauss, b_out, ld_b, bm_out, log_tab, exp_tab);
         }
