@@ -97,7 +97,8 @@ class AcousticPipeline:
         res = self.bank.score(mb.feats, mb.frame_offsets, n_utt, total, want_paths=want_paths, want_logprob=want_logprob)
         return res, mb
 
-    def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 8, want_paths: bool = False):
+    def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 6, want_paths: bool = False,
+                             n_compute_streams: int = 2):
         """End-to-end entry point for HOST audio: `pcm_host` is a pinned CPU tensor (int16 or float32) of concatenated
         utterances, `sample_offsets` [n+1] host.  The batch is cut into `n_chunks` groups of whole utterances.  All
         host->device copies are queued up front on a copy stream (one event per group), so the copy engine streams
@@ -126,10 +127,12 @@ class AcousticPipeline:
         dev = _dev.device()
         cur = t.cuda.current_stream()
         if not hasattr(self, "_streams"):
-            self._streams = (t.cuda.Stream(), t.cuda.Stream())
-        copy_s, comp_s = self._streams
+            self._streams = (t.cuda.Stream(), t.cuda.Stream(), t.cuda.Stream())
+        copy_s, comp_a, comp_b = self._streams
+        comps = (comp_a, comp_b) if n_compute_streams >= 2 else (comp_a,)
         copy_s.wait_stream(cur)
-        comp_s.wait_stream(cur)
+        for cs in comps:
+            cs.wait_stream(cur)
         total_samples = int(off[-1] - off[0])
         max_frames = max(int(p[2][-1]) for p in plan)
         with t.cuda.stream(copy_s):
@@ -143,31 +146,41 @@ class AcousticPipeline:
                 ev = t.cuda.Event()
                 ev.record(copy_s)
                 events.append(ev)
-        with t.cuda.stream(comp_s):
+        need = C.c_size_t(0)
+        _capi.check(_capi.lib().lnasr_mfcc_workspace_bytes(max_frames, max(h - l for l, h in bounds), C.byref(need)),
+                    "mfcc_workspace_bytes")
+        with t.cuda.stream(comps[0]):
             words = t.empty((n_utt,), dtype=t.int32, device=dev)
             best = t.empty((n_utt,), dtype=t.float64, device=dev)
-            need = C.c_size_t(0)
-            _capi.check(_capi.lib().lnasr_mfcc_workspace_bytes(max_frames, max(h - l for l, h in bounds), C.byref(need)),
-                        "mfcc_workspace_bytes")
-            ws = t.empty((need.value,), dtype=t.uint8, device=dev)
-            for (lo, hi), (p0, p1, f_rel), ev in zip(bounds, plan, events):
-                comp_s.wait_event(ev)
+        ws = []
+        for cs in comps:
+            with t.cuda.stream(cs):
+                cs.wait_stream(comps[0])
+                ws.append(t.empty((need.value,), dtype=t.uint8, device=dev))
+        # groups alternate between the compute streams: the latency-bound tail of one group (Viterbi chains, kernel tails)
+        # overlaps the head of the next
+        for i, ((lo, hi), (p0, p1, f_rel), ev) in enumerate(zip(bounds, plan, events)):
+            cs = comps[i % len(comps)]
+            with t.cuda.stream(cs):
+                cs.wait_event(ev)
                 s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
                 nu = hi - lo
                 mb = self.mfcc.calc_mfcc_batch(pcm_dev[s0:s1], sample_offsets=off[lo:hi + 1],
-                                               _plan=(meta_dev[p0:p1], meta_dev[p1:p1 + nu + 1], f_rel, ws))
-                res = self.bank.score(mb.feats, mb.frame_offsets, nu, int(f_rel[-1]), want_paths=want_paths,
-                                      words_out=words[lo:hi], best_out=best[lo:hi])
+                                               _plan=(meta_dev[p0:p1], meta_dev[p1:p1 + nu + 1], f_rel, ws[i % len(comps)]))
+                self.bank.score(mb.feats, mb.frame_offsets, nu, int(f_rel[-1]), want_paths=want_paths,
+                                words_out=words[lo:hi], best_out=best[lo:hi])
+        for cs in comps[1:]:
+            comps[0].wait_stream(cs)
+        with t.cuda.stream(comps[0]):
             out_w = t.empty((n_utt,), dtype=t.int32, pin_memory=True)
             out_b = t.empty((n_utt,), dtype=t.float64, pin_memory=True)
             out_w.copy_(words, non_blocking=True)
             out_b.copy_(best, non_blocking=True)
-        cur.wait_stream(comp_s)
-        for x in (pcm_dev, meta_dev):
-            x.record_stream(comp_s)
-        for x in (words, best, ws):
-            x.record_stream(cur)
-        comp_s.synchronize()
+        cur.wait_stream(comps[0])
+        for cs in comps:
+            for x in (pcm_dev, meta_dev, words, best):
+                x.record_stream(cs)
+        comps[0].synchronize()
         return out_w, out_b
 
     def recognize(self, signals: Sequence[np.ndarray]):
