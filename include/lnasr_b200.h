@@ -187,6 +187,24 @@ int lnasr_backward_batch(const void* b, int b_dtype, int64_t ld_b, const int64_t
 int lnasr_argmax_rows(const double* score /*[n_rows,n_cols]*/, int32_t n_rows, int32_t n_cols, int32_t* arg_out,
                       double* best_out, void* stream);
 
+/* ================================ (3b) the decode path in one call ==============================
+ * PCM -> MFCC (mfcc.py:108-175) -> emissions (gmmhmm.py:46-67) -> Viterbi (hmm.py:133-172) -> word = argmax over the bank's
+ * models of max_j v[T-1,j], on one workspace and one stream: no allocation, no synchronisation.
+ * gmm_kind 0: gmm_packed is the lnasr_gmm_pack_exact image (float64 emissions); 1: the lnasr_gmm_pack_tc image (float32).
+ * n_mix / dim describe the Gaussians; the bank's n_models*N states are the GMM's states, model k owning [k*N,(k+1)*N). */
+typedef struct lnasr_recognizer {
+    const lnasr_mfcc_tables* mfcc;   /* host struct of device pointers */
+    const lnasr_hmm_bank* bank;      /* host struct of device pointers */
+    const void* gmm_packed;          /* device */
+    int32_t gmm_kind, n_mix, dim;
+} lnasr_recognizer;
+int lnasr_recognize_workspace_bytes(int64_t total_frames, int32_t n_utt, const lnasr_recognizer* rec, int want_paths,
+                                    size_t* bytes /*host out*/);
+/* words_out [n_utt] int32, best_out [n_utt] float64 or NULL, paths_out [n_models, total_frames] uint32 or NULL (all device) */
+int lnasr_recognize_batch(const void* pcm, int pcm_dtype, const int64_t* sample_offsets, const int64_t* frame_offsets,
+                          int32_t n_utt, int64_t total_frames, const lnasr_recognizer* rec, int32_t* words_out,
+                          double* best_out, uint32_t* paths_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ================================ (4) Baum-Welch accumulation + M-step ==========================
  * Replaces HMM._baumwelch (lnasr/hmm.py:174-200) and GMMHMM._estimate (lnasr/gmmhmm.py:69-156) in
  * sufficient-statistic form, never materialising xi [T,N,N] or the

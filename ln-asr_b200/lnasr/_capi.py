@@ -39,6 +39,12 @@ class HmmBank(C.Structure):
     ]
 
 
+class Recognizer(C.Structure):
+    """lnasr_recognizer (include/lnasr_b200.h)."""
+    _fields_ = [("mfcc", C.POINTER(MfccTables)), ("bank", C.POINTER(HmmBank)), ("gmm_packed", vp),
+                ("gmm_kind", i32), ("n_mix", i32), ("dim", i32)]
+
+
 # name -> (restype, argtypes); every symbol include/lnasr_b200.h declares
 SIGNATURES = {
     "lnasr_last_error": (C.c_char_p, []),
@@ -68,6 +74,8 @@ SIGNATURES = {
     "lnasr_forward_batch": (C.c_int, [vp, C.c_int, i64, vp, i32, i64, C.POINTER(HmmBank), vp, vp, vp]),
     "lnasr_backward_batch": (C.c_int, [vp, C.c_int, i64, vp, i32, i64, C.POINTER(HmmBank), vp, vp]),
     "lnasr_argmax_rows": (C.c_int, [vp, i32, i32, vp, vp, vp]),
+    "lnasr_recognize_workspace_bytes": (C.c_int, [i64, i32, C.POINTER(Recognizer), C.c_int, C.POINTER(sz)]),
+    "lnasr_recognize_batch": (C.c_int, [vp, C.c_int, vp, vp, i32, i64, C.POINTER(Recognizer), vp, vp, vp, vp, sz, vp]),
     "lnasr_em_acc_doubles": (i64, [i32, i32, i32]),
     "lnasr_fb_accumulate": (C.c_int, [vp, C.c_int, i32, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "lnasr_mstep_finalize": (C.c_int, [vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]),

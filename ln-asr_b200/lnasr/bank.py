@@ -146,29 +146,36 @@ class AcousticPipeline:
                 ev = t.cuda.Event()
                 ev.record(copy_s)
                 events.append(ev)
-        need = C.c_size_t(0)
-        _capi.check(_capi.lib().lnasr_mfcc_workspace_bytes(max_frames, max(h - l for l, h in bounds), C.byref(need)),
-                    "mfcc_workspace_bytes")
         with t.cuda.stream(comps[0]):
             words = t.empty((n_utt,), dtype=t.int32, device=dev)
             best = t.empty((n_utt,), dtype=t.float64, device=dev)
-        ws = []
+        # groups alternate between the compute streams: the latency-bound tail of one group (Viterbi chains, kernel tails)
+        # overlaps the head of the next.  One C call per group (lnasr_recognize_batch: MFCC -> emissions -> Viterbi -> word).
+        lib = _capi.lib()
+        rec = self._recognizer_struct()
+        max_utt = max(h - l for l, h in bounds)
+        K = self.bank.K
+        need = C.c_size_t(0)
+        _capi.check(lib.lnasr_recognize_workspace_bytes(max_frames, max_utt, C.byref(rec), int(want_paths), C.byref(need)),
+                    "recognize_workspace_bytes")
+        ws, paths = [], []
         for cs in comps:
             with t.cuda.stream(cs):
                 cs.wait_stream(comps[0])
                 ws.append(t.empty((need.value,), dtype=t.uint8, device=dev))
-        # groups alternate between the compute streams: the latency-bound tail of one group (Viterbi chains, kernel tails)
-        # overlaps the head of the next
+                paths.append(t.empty((K * max_frames,), dtype=t.int32, device=dev) if want_paths else None)
+        isz = pcm_dev.element_size()
+        code = _dev.np_dtype_code(pcm_dev.dtype)
         for i, ((lo, hi), (p0, p1, f_rel), ev) in enumerate(zip(bounds, plan, events)):
             cs = comps[i % len(comps)]
-            with t.cuda.stream(cs):
-                cs.wait_event(ev)
-                s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
-                nu = hi - lo
-                mb = self.mfcc.calc_mfcc_batch(pcm_dev[s0:s1], sample_offsets=off[lo:hi + 1],
-                                               _plan=(meta_dev[p0:p1], meta_dev[p1:p1 + nu + 1], f_rel, ws[i % len(comps)]))
-                self.bank.score(mb.feats, mb.frame_offsets, nu, int(f_rel[-1]), want_paths=want_paths,
-                                words_out=words[lo:hi], best_out=best[lo:hi])
+            cs.wait_event(ev)
+            s0 = int(off[lo] - off[0])
+            nu = hi - lo
+            _capi.check(lib.lnasr_recognize_batch(
+                C.c_void_p(pcm_dev.data_ptr() + s0 * isz), code, C.c_void_p(meta_dev.data_ptr() + 8 * p0),
+                C.c_void_p(meta_dev.data_ptr() + 8 * p1), nu, int(f_rel[-1]), C.byref(rec),
+                C.c_void_p(words.data_ptr() + 4 * lo), C.c_void_p(best.data_ptr() + 8 * lo), _capi.ptr(paths[i % len(comps)]),
+                _capi.ptr(ws[i % len(comps)]), need.value, C.c_void_p(cs.cuda_stream)), "recognize_batch")
         for cs in comps[1:]:
             comps[0].wait_stream(cs)
         with t.cuda.stream(comps[0]):
@@ -182,6 +189,45 @@ class AcousticPipeline:
                 x.record_stream(cs)
         comps[0].synchronize()
         return out_w, out_b
+
+    def _recognizer_struct(self):
+        """lnasr_recognizer for the current device (cached; keeps the referenced structs alive)."""
+        t = _dev.torch()
+        dev = t.cuda.current_device()
+        cache = self.__dict__.setdefault("_rec_cache", {})
+        if dev not in cache:
+            tb = self.mfcc._device_tables()
+            bank = self.bank
+            tc = bank._tc is not None
+            packed = bank._tc.packed if tc else bank.gmm.packed
+            rec = _capi.Recognizer(mfcc=C.pointer(tb), bank=C.pointer(bank.trans.struct), gmm_packed=packed.data_ptr(),
+                                   gmm_kind=1 if tc else 0, n_mix=bank.m, dim=bank.d)
+            cache[dev] = (rec, tb, packed)
+        return cache[dev][0]
+
+    def recognize_batch_fused(self, pcm, sample_offsets, want_paths=False):
+        """Device-resident decode through the single C entry point lnasr_recognize_batch.  pcm: CUDA tensor (int16/float32);
+        returns (words int32 [n], best float64 [n], paths int32 [K, total_frames] or None) on the device."""
+        t = _dev.torch()
+        lib = _capi.lib()
+        off = np.asarray(sample_offsets, dtype=np.int64)
+        n_utt = len(off) - 1
+        f_off = _dev.offsets_from_lengths(self.mfcc.frame_counts(off))
+        total = int(f_off[-1])
+        meta = _dev.to_dev(np.concatenate([off - off[0], f_off]), t.int64)
+        rec = self._recognizer_struct()
+        need = C.c_size_t(0)
+        _capi.check(lib.lnasr_recognize_workspace_bytes(total, n_utt, C.byref(rec), int(want_paths), C.byref(need)),
+                    "recognize_workspace_bytes")
+        ws = _dev.empty((need.value,), t.uint8)
+        words, best = _dev.empty((n_utt,), t.int32), _dev.empty((n_utt,), t.float64)
+        paths = _dev.empty((self.bank.K, total), t.int32) if want_paths else None
+        pcm = _dev.to_dev(pcm)
+        _capi.check(lib.lnasr_recognize_batch(
+            _capi.ptr(pcm), _dev.np_dtype_code(pcm.dtype), _capi.ptr(meta), C.c_void_p(meta.data_ptr() + 8 * (n_utt + 1)), n_utt,
+            total, C.byref(rec), _capi.ptr(words), _capi.ptr(best), _capi.ptr(paths), _capi.ptr(ws), need.value,
+            _capi.stream_ptr()), "recognize_batch")
+        return words, best, paths
 
     def recognize(self, signals: Sequence[np.ndarray]):
         """Convenience: list of utterances -> numpy array of word indices."""

@@ -1,0 +1,69 @@
+"""PCM -> word pipeline (lnasr.bank.AcousticPipeline): the staged path, the single-C-call path (lnasr_recognize_batch) and
+the host-audio path (chunked, overlapped copies) must agree with each other and with the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(rng, lens):
+    sigs = []
+    for n in lens:
+        t = np.arange(n) / 16000.0
+        x = np.round(3000.0 * rng.standard_normal(n)) + 2000.0 * np.sin(2 * np.pi * rng.uniform(80, 400) * t)
+        sigs.append(np.clip(x, -32767, 32767).astype(np.int16))
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    return np.concatenate(sigs), off, sigs
+
+
+def _models(rng, K, n, m):
+    from oracle import lnasr_oracle as O
+    models = [O.random_gmmhmm(n, m, 39, rng) for _ in range(K)]
+    for mdl in models:
+        mdl["mu"] = mdl["mu"] * 100.0
+        mdl["var"] = mdl["var"] * 400.0
+    return models
+
+
+@pytest.mark.parametrize("K,n,m", [(10, 5, 4), (3, 3, 8), (4, 7, 2)])
+def test_three_entry_points_agree_and_match_oracle(K, n, m):
+    import torch
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(K * 100 + n)
+    lens = [int(x) for x in rng.integers(4000, 20000, size=37)]
+    pcm, off, sigs = _batch(rng, lens)
+    models = _models(rng, K, n, m)
+    pipe = AcousticPipeline(MFCC(), ModelBank(models, emission="exact"))
+    res, mb = pipe.recognize_batch(pcm, off, want_paths=True)
+    w_f, b_f, p_f = pipe.recognize_batch_fused(torch.from_numpy(pcm).cuda(), off, want_paths=True)
+    assert torch.equal(res.words, w_f) and torch.equal(res.best, b_f) and torch.equal(res.paths, p_f)
+    for chunks, streams in ((1, 1), (3, 2), (8, 2), (64, 2)):
+        w_h, b_h = pipe.recognize_batch_host(torch.from_numpy(pcm).pin_memory(), off, n_chunks=chunks, want_paths=True,
+                                             n_compute_streams=streams)
+        assert np.array_equal(w_h.numpy(), res.words.cpu().numpy()), (chunks, streams)
+        assert np.array_equal(b_h.numpy(), res.best.cpu().numpy()), (chunks, streams)
+    # oracle on a few utterances: same features -> same word and score
+    feats = mb.feats.double().cpu().numpy()
+    foff = mb.frame_offsets_host
+    for u in (0, 5, 36):
+        w_ref, s_ref, _, _, _ = O.score_words(feats[foff[u]:foff[u + 1]], models)
+        assert int(res.words[u]) == w_ref
+        np.testing.assert_allclose(res.scores[u].cpu().numpy(), s_ref, rtol=1e-9)
+
+
+def test_fused_entry_point_with_tensor_core_emissions():
+    import torch
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(9)
+    pcm, off, _ = _batch(rng, [8000, 12000, 5000, 16000])
+    mdl = O.random_gmmhmm(64, 16, 39, rng, left_to_right=True)
+    mdl["mu"] = mdl["mu"] * 100.0
+    mdl["var"] = mdl["var"] * 400.0
+    pipe = AcousticPipeline(MFCC(), ModelBank([mdl], emission="tc"))
+    res, _ = pipe.recognize_batch(pcm, off, want_paths=True)
+    w_f, b_f, p_f = pipe.recognize_batch_fused(torch.from_numpy(pcm).cuda(), off, want_paths=True)
+    assert torch.equal(res.words, w_f) and torch.equal(res.best, b_f) and torch.equal(res.paths, p_f)
