@@ -97,7 +97,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int 
     L.window = o;   o += FFT_N;                           // window (x 1/100 on the integer path), zero past frame_len
     L.logtab = o;   o += 2 * 128;                         // (1/c_i, log c_i) of the table-driven log
     L.dct = o;      o += n_mel * n_dct_cols;              // [n][k < n_dct_cols]
-    L.fb_w = o;     o += n_mel * fb_stride;               // double weights
+    L.fb_w = o;     o += (n_mel * fb_stride + 1) / 2;     // float weights
     L.fb_meta = o;  o += (4 * MAX_MEL) / 2 + 2;           // ints: fb_start[64] | fb_len[64] | assign[64] | order[64] | flags
     o = (o + 1) & ~1;
     L.per_hw = o;
@@ -152,7 +152,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     double* s_win = smem + L.window;
     double2* s_log = reinterpret_cast<double2*>(smem + L.logtab);
     double* s_dct = smem + L.dct;
-    double* s_fbw = smem + L.fb_w;
+    float* s_fbw = reinterpret_cast<float*>(smem + L.fb_w);
     int* s_fbs = reinterpret_cast<int*>(smem + L.fb_meta);
     int* s_fbl = s_fbs + MAX_MEL;
     int* s_asg = s_fbl + MAX_MEL;
@@ -171,7 +171,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         s_log[i] = make_double2(c, -log(c));
     }
     for (int i = tid; i < FFT_N; i += n_threads) s_win[i] = (i < P.frame_len) ? P.window[i] * (int_path ? 0.01 : 1.0) : 0.0;
-    for (int i = tid; i < P.n_mel * P.fb_stride; i += n_threads) s_fbw[i] = (double)P.fb_weight[i];
+    for (int i = tid; i < P.n_mel * P.fb_stride; i += n_threads) s_fbw[i] = P.fb_weight[i];
     for (int i = tid; i < P.n_mel * n_out; i += n_threads) {
         const int n = i / n_out, k = i - n * n_out;
         s_dct[i] = P.dct_t[n * P.n_mel + k];
@@ -226,7 +226,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
 
     double* hbase = smem + L.per_hw + (tid >> 4) * L.per_hw_doubles;
     double2* tr = reinterpret_cast<double2*>(hbase);     // [16][TR_LD] complex
-    double* s_pow = hbase;                               // aliases tr once the second DFT has read it
+    float* s_pow = reinterpret_cast<float*>(hbase);      // power spectrum (float), aliases tr once the second DFT has read it
     double* s_lm = hbase + 2 * 16 * TR_LD;
     PcmT* stage = reinterpret_cast<PcmT*>(hbase + L.stage_off);
 
@@ -364,36 +364,39 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             const double px = E.x + T.x, py = E.y + T.y;                   // 2 X[k]
             const double qx = E.x - T.x, qy = E.y - T.y;                   // conj(2 X[256-k])
             const double pk = px * px + py * py, pr = qx * qx + qy * qy;
-            s_pow[b + 16 * k2] = pk;
-            s_pow[HALF_N - b - 16 * k2] = pr;
+            s_pow[b + 16 * k2] = (float)pk;
+            s_pow[HALF_N - b - 16 * k2] = (float)pr;
             esum += pk + pr;
         }
         {
             const double2 z8 = v[NAT16(8)];                                // bin 128 (lane 0): X = conj(Z[128])
             const double p8 = 4.0 * (z8.x * z8.x + z8.y * z8.y);
-            if (b == 0) { s_pow[128] = p8; esum += p8; }
+            if (b == 0) { s_pow[128] = (float)p8; esum += p8; }
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
         __syncwarp();
         if (power_out && act_cur)
-            for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = (float)(s_pow[k] * PSCALE);
+            for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = s_pow[k] * (float)PSCALE;
         // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
         for (int s = 0; s < n_slots; ++s) {
             const int m = s_asg[s * 16 + b];
             double e = esum;                                               // m == -2: ln of the frame energy (mfcc.py:158-160)
             if (m >= 0) {
                 const int k0 = s_fbs[m], len = s_fbl[m];
-                const double* w = s_fbw + m * P.fb_stride;
-                const double* pw = s_pow + k0;
-                double e0 = 0.0, e1 = 0.0;
+                // The power spectrum is a set of positive numbers: once the float64 FFT has produced it, the banded sums are
+                // safe in float32 (<= 31 positive terms: relative error ~1e-6, i.e. ~1e-5 dB) -- half the shared-memory bytes
+                // of the hottest loop of this kernel, and FFMA instead of DFMA.  The energy sum above stays float64.
+                const float* w = s_fbw + m * P.fb_stride;
+                const float* pw = s_pow + k0;
+                float e0 = 0.f, e1 = 0.f;
                 int t = 0;
                 for (; t + 1 < len; t += 2) {
-                    e0 = fma(w[t], pw[t], e0);
-                    e1 = fma(w[t + 1], pw[t + 1], e1);
+                    e0 = fmaf(w[t], pw[t], e0);
+                    e1 = fmaf(w[t + 1], pw[t + 1], e1);
                 }
-                if (t < len) e0 = fma(w[t], pw[t], e0);
-                e = e0 + e1;
+                if (t < len) e0 = fmaf(w[t], pw[t], e0);
+                e = (double)(e0 + e1);
             }
             e *= PSCALE;
             if (m >= 0 && e == 0.0) e = 2.220446049250313e-16;             // np.finfo(float).eps
