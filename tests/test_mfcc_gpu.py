@@ -75,3 +75,30 @@ def test_large_batch_properties(mfcc):
     np.testing.assert_allclose(F[:, 0, 13:26], F[:, 1, :13], atol=1e-6)                       # delta row 0 = static row 1
     np.testing.assert_allclose(F[:, 1:, 26:], F[:, 1:, 13:26] - F[:, :-1, 13:26], atol=4e-4)  # delta-delta
     np.testing.assert_allclose(F[:, 0, 26:], F[:, 1, 13:26], atol=1e-6)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(frame_T=20e-3, frame_stride=10e-3, mfbank_num=26),                  # 320-sample frames, 26 filters
+    dict(fs=8000, frame_T=25e-3, frame_stride=10e-3, mfbank_num=20, hpf_alpha=0.95),
+    dict(hpf_alpha=0.9375, mfbank_num=64, cepstrum_num=12),                  # alpha*100 not an integer -> float64 pre-emphasis; 64 filters
+    dict(frame_T=32e-3, frame_stride=8e-3, mfbank_num=33, cepstrum_num=10),  # 512-sample frames (= fft_N), 11 static coefficients
+])
+def test_non_default_constructor_arguments_match_oracle(kw):
+    """MFCC(fs, frame_T, frame_stride, hpf_alpha, fft_N, mfbank_num, cepstrum_num) (mfcc.py:23-27): the kernel is generic in
+    frame length (<= fft_N), hop, filter count (<= 64), coefficient count and pre-emphasis; int16 and float input."""
+    from lnasr.mfcc import MFCC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(17)
+    m = MFCC(**kw)
+    p = O.MfccParams(**kw)
+    for n, as_float in ((9000, False), (2 * p.frame_L + 3, False), (7001, True)):
+        t = np.arange(n) / float(p.fs)
+        x = np.round(3000.0 * rng.standard_normal(n)) + 2000.0 * np.sin(2 * np.pi * 210.0 * t)
+        x = np.clip(x, -32767, 32767).astype(np.int16)
+        sig = x.astype(np.float32) * 0.37 if as_float else x
+        P, C, F = m.calc_mfcc(sig)
+        Pr, Cr, Fr = O.mfcc(sig.astype(np.float64), p)
+        assert F.shape == Fr.shape == (O.num_frames(n, p.frame_L, p.frame_step), 3 * (p.cepstrum_num + 1))
+        assert_close(P, Pr, 1e-4, "power")
+        assert_close(C, Cr, 1e-4, "cepstrum")
+        assert_close(F, Fr, 1e-4, "features")
