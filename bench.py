@@ -331,6 +331,10 @@ def run_ours(args):
         top = max(stages, key=lambda k: stages[k]["ms"])
         roof = roofline_for(top, stages[top], frames, cfg, models, hbm_peak, peaks, fp64)
         roof["kernel"] = top
+        if args.workload == "c2" and frames == NCU_TRAFFIC_C2["frames"]:
+            roof["traffic"] = NCU_TRAFFIC_C2[top]
+            roof["traffic_note"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/); algorithmic = %d" % (
+                roof.get("algorithmic_bytes_per_frame", 0) * frames)
         roof["peak_source"] = peak_src
         roof["stage_ms"] = {k: round(v["ms"], 4) for k, v in stages.items()}
         roof["all_stages"] = {}
@@ -549,6 +553,11 @@ def tf32_peak():
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
 
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of each stage, from the `ncu --set full`
+# captures of THIS workload size (c2, 403 867 frames): profiles/r1_mfcc_v4_ncu_full.txt, r1_gmm_dmma_resident_ncu_full.txt,
+# r1_trellis_small_ncu_full.txt.  Reported only when the run has exactly that shape.
+NCU_TRAFFIC_C2 = {"frames": 403867, "mfcc": 137.72e6 + 15.88e6, "gmm": 64.24e6 + 107.22e6, "viterbi": 161.88e6 + 29.87e6}
 
 MFCC_FP64_FLOPS_PER_FRAME = 18300     # 256-pt complex FFT 10.2k + split/power 4.1k + pre-emphasis/window 1.2k + mel 0.9k + log 0.8k + DCT 1.0k
 
