@@ -26,6 +26,7 @@ constexpr int MAX_THREADS = 512;      // 16 warps = 32 half-warps per SM (one bl
 constexpr int FRAMES_PER_RUN = 8;     // consecutive frames a warp walks (its two halves take alternate frames); small runs
                                       // keep the static schedule balanced for the few-ten-thousand-frame groups of the e2e path
 constexpr int STEPS_PER_RUN = FRAMES_PER_RUN / 2;
+constexpr double COLSUM_SCALE = 4294967296.0;      // per-utterance column sums are 32.32 fixed point (|c| < 2^18, < 2^13 frames)
 constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
 constexpr int P_LD = 264;             // power spectrum of one frame (257 doubles), aliases the transpose buffer
 constexpr int MAX_SLOTS = MAX_MEL / 16;
@@ -139,7 +140,7 @@ template <typename PcmT>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sample_off,
                    const int64_t* __restrict__ frame_off, int n_utt, int64_t total_frames, MfccDev P,
-                   float* __restrict__ raw, double* __restrict__ colsum, const int* __restrict__ run_utt,
+                   float* __restrict__ raw, unsigned long long* __restrict__ colsum, const int* __restrict__ run_utt,
                    float* __restrict__ power_out, float* __restrict__ ceps_raw_out) {
     extern __shared__ __align__(16) double smem[];
     constexpr bool kIntPcm = (sizeof(PcmT) == 2);
@@ -291,15 +292,19 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     bool more = locate(0);
     if (more) issue_copy();
     int acc_u = -1;
-    double acc[MAX_SLOTS] = {0.0, 0.0, 0.0, 0.0};        // running column sums of utterance acc_u: coefficient b + 16 i
+    // running column sums of utterance acc_u (coefficient b + 16 i) in 32.32 fixed point: integer addition is associative, so
+    // the per-utterance means -- and with them every feature -- do not depend on the order in which warps flush or on the
+    // batch the utterance is scored in (a float64 atomicAdd would make the last bits scheduling-dependent)
+    long long acc[MAX_SLOTS] = {0, 0, 0, 0};
     for (int64_t step = 0; more; ++step) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (act && ctx.u != acc_u) {                      // flush the column sums of the utterance just left
 #pragma unroll
             for (int i = 0; i < MAX_SLOTS; ++i) {
-                if (acc_u >= 0 && b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
-                acc[i] = 0.0;
+                if (acc_u >= 0 && b + 16 * i < n_out)
+                    atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, (unsigned long long)acc[i]);
+                acc[i] = 0;
             }
             acc_u = ctx.u;
         }
@@ -420,7 +425,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                 if (n < P.n_mel) c0 = fma(s_dct[n * n_out + k], s_lm[n], c0);
                 const double c = c0 + c1;
                 if (act_cur) {
-                    acc[i] += c;
+                    acc[i] += __double2ll_rn(c * COLSUM_SCALE);
                     // raw static row: cepstra 1..n_ceps then ln(sum power) (mfcc.py:158-160)
                     if (k >= 1 && k <= P.n_ceps) raw[f_cur * RAW_LD + (k - 1)] = (float)c;
                     if (full_ceps) ceps_raw_out[f_cur * P.n_mel + k] = (float)c;
@@ -432,7 +437,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     if (acc_u >= 0) {
 #pragma unroll
         for (int i = 0; i < MAX_SLOTS; ++i)
-            if (b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, acc[i]);
+            if (b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, (unsigned long long)acc[i]);
     }
 }
 
@@ -450,7 +455,7 @@ constexpr int FIN_WARPS = 8;
 constexpr int FIN_FRAMES = 30;
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-mfcc_finalize_kernel(const float* __restrict__ raw, const double* __restrict__ colsum,
+mfcc_finalize_kernel(const float* __restrict__ raw, const long long* __restrict__ colsum,
                      const int64_t* __restrict__ frame_off, int n_utt, int64_t total_frames, int n_ceps, int n_mel,
                      float* __restrict__ feats, int ld_feats, float* __restrict__ ceps_io, float dct_dc) {
     __shared__ float tile[FIN_WARPS][32][40];
@@ -477,7 +482,7 @@ mfcc_finalize_kernel(const float* __restrict__ raw, const double* __restrict__ c
             float s = 0.f, s_next = 0.f;
             if (valid) {
                 // feature = raw - (mean + 1e-8) for the cepstra (mfcc.py:151,156 folded, see file header); energy as is
-                const double mean = (c < n_ceps) ? (__ldg(colsum + (int64_t)u * MAX_MEL + c + 1) * inv_cnt + 1e-8) : 0.0;
+                const double mean = (c < n_ceps) ? ((double)__ldg(colsum + (int64_t)u * MAX_MEL + c + 1) * (1.0 / COLSUM_SCALE) * inv_cnt + 1e-8) : 0.0;
                 s = (float)((double)__ldg(raw + f * RAW_LD + c) - mean);
                 if (fl == 0) s_next = (float)((double)__ldg(raw + (f + 1) * RAW_LD + c) - mean);   // row 1 of the utterance
             }
@@ -514,7 +519,7 @@ mfcc_finalize_kernel(const float* __restrict__ raw, const double* __restrict__ c
                 const int uu = find_utt(frame_off, n_utt, ff);
                 const double ic = 1.0 / (double)(__ldg(frame_off + uu + 1) - __ldg(frame_off + uu));
                 for (int k = lane; k < n_mel; k += 32) {
-                    double mean = __ldg(colsum + (int64_t)uu * MAX_MEL + k) * ic;
+                    double mean = (double)__ldg(colsum + (int64_t)uu * MAX_MEL + k) * (1.0 / COLSUM_SCALE) * ic;
                     double v = (double)ceps_io[ff * n_mel + k] - mean;
                     if (k == 0) v -= 1e-8 * (double)dct_dc;       // DCT of the constant 1e-8 offset
                     if (k >= 1 && k <= n_ceps) v -= 1e-8;
@@ -567,7 +572,7 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     }
     float* raw = (float*)workspace;
     size_t raw_bytes = ((size_t)total_frames * RAW_LD * sizeof(float) + 255) & ~(size_t)255;
-    double* colsum = (double*)((char*)workspace + raw_bytes);
+    unsigned long long* colsum = (unsigned long long*)((char*)workspace + raw_bytes);
     LNASR_CUDA(cudaMemsetAsync(colsum, 0, (size_t)n_utt * MAX_MEL * sizeof(double), stream));
     const size_t col_bytes = ((size_t)n_utt * MAX_MEL * sizeof(double) + 255) & ~(size_t)255;
     int* run_utt = (int*)((char*)workspace + raw_bytes + col_bytes);
@@ -615,7 +620,7 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     if (grid2 < 1) grid2 = 1;
     // DCT-II ortho of a constant vector c is c*sqrt(n_mel) in coefficient 0 and 0 elsewhere
     const float dct_dc = sqrtf((float)tb->n_mel);
-    mfcc_finalize_kernel<<<grid2, FIN_WARPS * 32, 0, stream>>>(raw, colsum, frame_offsets, n_utt, total_frames,
+    mfcc_finalize_kernel<<<grid2, FIN_WARPS * 32, 0, stream>>>(raw, (const long long*)colsum, frame_offsets, n_utt, total_frames,
                                                               tb->n_ceps, tb->n_mel, feats, ld_feats, ceps_out, dct_dc);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
