@@ -215,12 +215,17 @@ int lnasr_recognize_batch(const void* pcm, int pcm_dtype, const int64_t* sample_
  *   S0[N*M] | S1[N*M*D] | S2c[N*M*D] (scatter about the OLD mean) | xi_sum[N*N] | pi_occ[N] | loglik | n_utt
  */
 int64_t lnasr_em_acc_doubles(int32_t N, int32_t n_mix, int32_t dim);
-/* alpha must come from lnasr_forward_batch, b/bm (float64) from lnasr_gmm_loglik_exact; single model (n_models=1) */
+/* alpha must come from lnasr_forward_batch, b/bm (float64) from lnasr_gmm_loglik_exact; single model (n_models=1).
+ * workspace = lnasr_fb_workspace_bytes() bytes selects the two-kernel form (backward recursion with G lanes per utterance
+ * writing log gamma to the workspace, then a frame-parallel statistics kernel) that fills the machine when there are
+ * fewer utterances than a few per SM x warps; workspace = NULL runs the single fused kernel (one CTA per utterance). */
+size_t lnasr_fb_workspace_bytes(int64_t total_frames, int32_t N);
 int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
                         const double* alpha, const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames,
                         const double* logA, const double* logw, const double* mu, int32_t N, int32_t n_mix,
                         int32_t dim, double* acc /*in/out, caller zeroes*/, double* gamma_out /*[T,N] log or NULL*/,
-                        double* beta_out /*[T,N] log or NULL*/, void* stream);
+                        double* beta_out /*[T,N] log or NULL*/, void* workspace /*or NULL*/, size_t workspace_bytes,
+                        void* stream);
 /* M-step from (all-reduced) statistics; writes the new model in place of the old device arrays */
 int lnasr_mstep_finalize(const double* acc, int32_t N, int32_t n_mix, int32_t dim, double min_std,
                          double* logA, double* logpi, double* logw, double* mu, double* var, void* stream);

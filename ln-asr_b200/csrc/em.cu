@@ -339,6 +339,239 @@ baumwelch_xi_kernel(const double* __restrict__ alpha, const double* __restrict__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-kernel form of the same statistics for batches whose utterance count cannot fill the machine with one CTA per
+// utterance (config 3: 1000 utterances of ~300 frames on 148 SMs).  The serial part of Baum-Welch is only the backward
+// recursion; everything weighted by the occupancies is a sum over frames with no order.
+//   em_gamma_kernel<G>  : G lanes per utterance (32/G utterances per warp, like the small trellis kernel): beta, Z_t,
+//                         log gamma[t,j] for ALL t -> workspace [T,N]; xi / pi statistics and log P(O) in registers.
+//                         alpha and b rows are prefetched PF frames ahead; exp / log are the table versions (common.cuh).
+//   em_stats_kernel     : persistent CTAs over 64-frame tiles: occ[t,j,m] = exp(log gamma + log w + bm - b)
+//                         (gmmhmm.py:89-106) into shared memory, then S0 += occ, S1 += occ x, S2c += occ (x-mu_old)^2
+//                         (gmmhmm.py:117-147) with every thread owning fixed (gaussian, dim) entries; one atomic flush per CTA.
+constexpr int EG_WARPS = 4;
+constexpr int EG_PF = 8;
+constexpr int ES_THREADS = 256;
+constexpr int ES_TILE = 64;
+
+template <int G>
+__global__ void __launch_bounds__(EG_WARPS * 32)
+em_gamma_kernel(FbArgs a, double* __restrict__ lgamma) {
+    __shared__ __align__(16) double2 log_tab[128];
+    __shared__ double exp_tab[64];
+    fill_log_exp_tables(log_tab, exp_tab, threadIdx.x, EG_WARPS * 32);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PPW = 32 / G;
+    const int N = a.N;
+    const int slot = lane / G, gbase = slot * G, j = lane - gbase;
+    const int64_t u = ((int64_t)blockIdx.x * EG_WARPS + warp) * PPW + slot;
+    const bool utt_ok = u < a.n_utt;
+    const bool act = utt_ok && j < N;
+    const int64_t f0 = utt_ok ? __ldg(a.frame_off + u) : 0;
+    const int T = utt_ok ? (int)(__ldg(a.frame_off + u + 1) - f0) : 0;
+    int Tmax = T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+    if (Tmax == 0) return;
+    auto grp = [&](double v, int q) { return __shfl_sync(0xffffffffu, v, gbase + q); };
+    auto glse = [&](double v) {                                   // log-sum-exp over the G lanes of my group
+        double mx = v;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double sm = fast_exp_neg(v - mx, exp_tab);               // v = mx = -inf: NaN -> 0
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        return (mx == neg_inf()) ? mx : mx + fast_log(sm, log_tab);
+    };
+    double tr[G], xi_acc[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+        tr[q] = (act && q < N) ? __ldg(a.logA + (int64_t)j * N + q) : neg_inf();     // row j of log A
+        xi_acc[q] = 0.0;
+    }
+    double pi_acc = 0.0;
+    // log P(O) = lse_j alpha[T-1, j]    (hmm.py:274)
+    const double L = glse((act && T > 0) ? __ldg(a.alpha + (f0 + T - 1) * N + j) : neg_inf());
+    // step s handles frame t = T-1-s ; rows prefetched PF steps ahead
+    const double* ap = a.alpha + (f0 + T - 1) * N + j;
+    const double* bp = a.b + (f0 + T - 1) * N + j;
+    double aq[EG_PF], bq[EG_PF];
+#pragma unroll
+    for (int i = 0; i < EG_PF; ++i) {
+        const bool ok = act && i < T;
+        aq[i] = ok ? __ldg(ap - (int64_t)i * N) : neg_inf();
+        bq[i] = ok ? __ldg(bp - (int64_t)i * N) : neg_inf();
+    }
+    ap -= (int64_t)EG_PF * N;
+    bp -= (int64_t)EG_PF * N;
+    double* gp = lgamma + (f0 + T - 1) * N + j;
+    double* bo = a.beta_out ? a.beta_out + (f0 + T - 1) * N + j : nullptr;
+    double* go = a.gamma_out ? a.gamma_out + (f0 + T - 1) * N + j : nullptr;
+    double cur = 0.0, e_next = 0.0;                               // beta[t+1,j], b[t+1,j]
+    for (int s0 = 0; s0 < Tmax; s0 += EG_PF) {
+#pragma unroll
+        for (int i = 0; i < EG_PF; ++i) {
+            const int s = s0 + i;
+            const double al = aq[i], e = bq[i];
+            const bool more = act && s + EG_PF < T;
+            aq[i] = more ? __ldg(ap) : neg_inf();
+            bq[i] = more ? __ldg(bp) : neg_inf();
+            ap -= N;
+            bp -= N;
+            const bool live = act && s < T;
+            const bool last = (s == 0);                           // frame T-1
+            // beta[T-1] = 0 ; beta[t,i] = lse_q (A[i,q] + b[t+1,q] + beta[t+1,q])     (hmm.py:126-130)
+            const double uj = cur + e_next;
+            double cand[G];
+            double mx = neg_inf();
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                cand[q] = grp(uj, q) + tr[q];
+                mx = fmax(mx, cand[q]);
+            }
+            double sm = 0.0;
+#pragma unroll
+            for (int q = 0; q < G; ++q) sm += fast_exp_neg(cand[q] - mx, exp_tab);
+            double beta = (mx == neg_inf()) ? mx : mx + fast_log(sm, log_tab);
+            if (last) beta = 0.0;                                 // hmm.py:125
+            const double ab = live ? al + beta : neg_inf();
+            const double Z = glse(ab);                            // == lse_{i,q} of the xi numerator
+            const double g2 = (ab == neg_inf() || Z == neg_inf()) ? neg_inf() : ab - Z;
+            if (live) {
+                *gp = g2;                                         // log gamma for ALL t (the mixture statistics use t = T-1 too)
+                if (bo) *bo = beta;
+                if (go) *go = last ? neg_inf() : g2;              // hmm.py:199
+                if (!last && Z != neg_inf()) {
+                    double rs = 0.0;
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        // xi[t,i,q] = alpha[t,i] + A[i,q] + b[t+1,q] + beta[t+1,q] - Z_t     (hmm.py:190-197)
+                        const double ex = (q < N) ? fast_exp_neg(al + cand[q] - Z, exp_tab) : 0.0;
+                        xi_acc[q] += ex;
+                        rs += ex;
+                    }
+                    if (s == T - 1) pi_acc += rs;                 // t = 0: pi' = gamma[0]   (gmmhmm.py:86)
+                }
+                cur = beta;
+                e_next = e;
+            }
+            gp -= N;
+            if (bo) bo -= N;
+            if (go) go -= N;
+        }
+    }
+    // xi_sum[N*N] | pi_occ[N] | loglik | n_utt
+    double* tail = a.acc + (int64_t)N * a.M * (2 * a.D + 1);
+    if (act) {
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+            if (q < N && xi_acc[q] != 0.0) atomicAdd(tail + (int64_t)j * N + q, xi_acc[q]);
+        if (pi_acc != 0.0) atomicAdd(tail + (int64_t)N * N + j, pi_acc);
+        if (j == 0 && T > 0) {
+            atomicAdd(tail + (int64_t)N * N + N, L);
+            atomicAdd(tail + (int64_t)N * N + N + 1, 1.0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ES_THREADS)
+em_stats_kernel(FbArgs a, const double* __restrict__ lgamma, int64_t total_frames) {
+    extern __shared__ __align__(16) unsigned char em_smem_raw[];
+    double* sm = reinterpret_cast<double*>(em_smem_raw);
+    const int N = a.N, M = a.M, D = a.D, NM = N * M;
+    const int tid = threadIdx.x;
+    double2* log_tab = reinterpret_cast<double2*>(sm);    // tables first: 16-byte aligned whatever the model shape
+    double* exp_tab = sm + 256;
+    double* acc_s = exp_tab + 64;                         // S0[NM] | S1[NM*D] | S2c[NM*D]
+    double* mu_s = acc_s + NM * (2 * D + 1);
+    double* logw_s = mu_s + NM * D;
+    double* occ_s = logw_s + NM;                          // [ES_TILE][NM]
+    double* x_s = occ_s + ES_TILE * NM;                   // [ES_TILE][D]
+    for (int i = tid; i < NM * (2 * D + 1); i += ES_THREADS) acc_s[i] = 0.0;
+    for (int i = tid; i < NM * D; i += ES_THREADS) mu_s[i] = a.mu[i];
+    for (int i = tid; i < NM; i += ES_THREADS) logw_s[i] = a.logw[i];
+    fill_log_exp_tables(log_tab, exp_tab, tid, ES_THREADS);
+    __syncthreads();
+    const int64_t n_tiles = (total_frames + ES_TILE - 1) / ES_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * ES_TILE;
+        const int nt = (int)min((int64_t)ES_TILE, total_frames - t0);
+        // mixture occupancies for ALL t (gmmhmm.py:98-100): exp(log gamma[t,j] + log w[j,m] + bm[t,j,m] - b[t,j])
+        for (int i = tid; i < nt * NM; i += ES_THREADS) {
+            const int tt = i / NM, p = i - tt * NM, j = p / M;
+            const double g = __ldg(lgamma + (t0 + tt) * N + j), bj = __ldg(a.b + (t0 + tt) * N + j);
+            double o = 0.0;
+            if (g != neg_inf() && bj != neg_inf()) o = fast_exp_neg(g + logw_s[p] + __ldg(a.bm + (t0 + tt) * NM + p) - bj, exp_tab);
+            occ_s[i] = o;
+        }
+        for (int i = tid; i < nt * D; i += ES_THREADS) {
+            const int r = i / D, d = i - r * D;
+            const int64_t row = t0 + r;
+            x_s[i] = a.feats_f64 ? __ldg((const double*)a.feats + row * a.ld_feats + d)
+                                 : (double)__ldg((const float*)a.feats + row * a.ld_feats + d);
+        }
+        __syncthreads();
+        for (int e = tid; e < NM * D; e += ES_THREADS) {
+            const int jm = e / D, d = e - jm * D;
+            double s1 = 0.0, s2 = 0.0;
+            const double m0 = mu_s[e];
+#pragma unroll 4
+            for (int tt = 0; tt < nt; ++tt) {
+                const double o = occ_s[tt * NM + jm];
+                const double x = x_s[tt * D + d];
+                const double df = x - m0;
+                s1 = fma(o, x, s1);
+                s2 = fma(o * df, df, s2);
+            }
+            acc_s[NM + e] += s1;
+            acc_s[NM + NM * D + e] += s2;
+        }
+        for (int jm = tid; jm < NM; jm += ES_THREADS) {
+            double s0 = 0.0;
+            for (int tt = 0; tt < nt; ++tt) s0 += occ_s[tt * NM + jm];
+            acc_s[jm] += s0;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < NM * (2 * D + 1); i += ES_THREADS) {
+        const double v = acc_s[i];
+        if (v != 0.0) atomicAdd(a.acc + i, v);
+    }
+}
+
+static int launch_fb_split(const FbArgs& a, int64_t total_frames, double* lgamma, cudaStream_t stream) {
+    int G = 1;
+    while (G < a.N) G <<= 1;
+    const int ppw = 32 / G;
+    const unsigned grid_g = (unsigned)ceil_div(a.n_utt, (int64_t)EG_WARPS * ppw);
+    switch (G) {
+        case 1:  em_gamma_kernel<1><<<grid_g, EG_WARPS * 32, 0, stream>>>(a, lgamma); break;
+        case 2:  em_gamma_kernel<2><<<grid_g, EG_WARPS * 32, 0, stream>>>(a, lgamma); break;
+        case 4:  em_gamma_kernel<4><<<grid_g, EG_WARPS * 32, 0, stream>>>(a, lgamma); break;
+        case 8:  em_gamma_kernel<8><<<grid_g, EG_WARPS * 32, 0, stream>>>(a, lgamma); break;
+        case 16: em_gamma_kernel<16><<<grid_g, EG_WARPS * 32, 0, stream>>>(a, lgamma); break;
+        default: em_gamma_kernel<32><<<grid_g, EG_WARPS * 32, 0, stream>>>(a, lgamma); break;
+    }
+    LNASR_LAUNCH_CHECK();
+    const int NM = a.N * a.M;
+    const size_t dbl = (size_t)NM * (2 * a.D + 1) + (size_t)NM * a.D + NM + (size_t)ES_TILE * NM + (size_t)ES_TILE * a.D + 256 + 64;
+    const size_t smem = dbl * sizeof(double);
+    if (smem > 220 * 1024) {
+        set_error("fb_accumulate: N*M=%d at dim=%d needs %zu bytes of shared memory (> 220 KB); model too large", NM, a.D, smem);
+        return LNASR_EINVAL;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
+    const int64_t n_tiles = ceil_div(total_frames, ES_TILE);
+    const int grid_s = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm));
+    if (smem > 48 * 1024)
+        LNASR_CUDA(cudaFuncSetAttribute(em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    em_stats_kernel<<<grid_s, ES_THREADS, smem, stream>>>(a, lgamma, total_frames);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 template <bool GMM>
 static int launch_fb(const FbArgs& a, cudaStream_t stream) {
     int G = 1;
@@ -386,10 +619,15 @@ extern "C" int64_t lnasr_hmm_acc_doubles(int32_t N, int32_t n_symbols) {
     return (int64_t)N * N + N + (int64_t)N * n_symbols + N + 2;
 }
 
+extern "C" size_t lnasr_fb_workspace_bytes(int64_t total_frames, int32_t N) {
+    return (size_t)total_frames * N * sizeof(double) + 256;      // log gamma [T, N]
+}
+
 extern "C" int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
                                    const double* alpha, const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames,
                                    const double* logA, const double* logw, const double* mu, int32_t N, int32_t n_mix,
-                                   int32_t dim, double* acc, double* gamma_out, double* beta_out, void* stream) {
+                                   int32_t dim, double* acc, double* gamma_out, double* beta_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
     LNASR_CHECK_ARG(feats && b && bm && alpha && frame_offsets && logA && logw && mu && acc, "fb_accumulate: null pointer");
     LNASR_CHECK_ARG(feats_dtype == LNASR_DT_F32 || feats_dtype == LNASR_DT_F64, "fb_accumulate: feats must be float32/float64");
     LNASR_CHECK_ARG(N >= 1 && N <= 32, "fb_accumulate: the fused kernel is built for 1 <= N <= 32 (got %d)", N);
@@ -400,6 +638,13 @@ extern "C" int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t l
     a.b = b; a.bm = bm; a.alpha = alpha; a.frame_off = frame_offsets; a.n_utt = n_utt;
     a.logA = logA; a.logw = logw; a.mu = mu; a.N = N; a.M = n_mix; a.D = dim; a.n_symbols = 0;
     a.acc = acc; a.gamma_out = gamma_out; a.beta_out = beta_out;
+    if (workspace) {
+        if (workspace_bytes < lnasr_fb_workspace_bytes(total_frames, N)) {
+            set_error("fb_accumulate: workspace %zu < %zu bytes", workspace_bytes, lnasr_fb_workspace_bytes(total_frames, N));
+            return LNASR_EWORKSPACE;
+        }
+        return launch_fb_split(a, total_frames, (double*)workspace, (cudaStream_t)stream);
+    }
     return launch_fb<true>(a, (cudaStream_t)stream);
 }
 

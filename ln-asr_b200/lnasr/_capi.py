@@ -77,7 +77,8 @@ SIGNATURES = {
     "lnasr_recognize_workspace_bytes": (C.c_int, [i64, i32, C.POINTER(Recognizer), C.c_int, C.POINTER(sz)]),
     "lnasr_recognize_batch": (C.c_int, [vp, C.c_int, vp, vp, i32, i64, C.POINTER(Recognizer), vp, vp, vp, vp, sz, vp]),
     "lnasr_em_acc_doubles": (i64, [i32, i32, i32]),
-    "lnasr_fb_accumulate": (C.c_int, [vp, C.c_int, i32, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "lnasr_fb_workspace_bytes": (sz, [i64, i32]),
+    "lnasr_fb_accumulate": (C.c_int, [vp, C.c_int, i32, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
     "lnasr_mstep_finalize": (C.c_int, [vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]),
     "lnasr_hmm_acc_doubles": (i64, [i32, i32]),
     "lnasr_hmm_fb_accumulate": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, vp]),

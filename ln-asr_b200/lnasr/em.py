@@ -60,6 +60,7 @@ class EmTrainer:
         self._bm = _dev.empty((T, self.n * self.m), t.float64)
         self._alpha = _dev.empty((T, self.n), t.float64)
         self._lp = _dev.empty((self._n_utt, 1), t.float64)
+        self._ws = _dev.empty((int(_capi.lib().lnasr_fb_workspace_bytes(T, self.n)),), t.uint8)
         return self
 
     def iterate(self, reduce_fn=None):
@@ -77,7 +78,8 @@ class EmTrainer:
         self.acc.zero_()
         _capi.check(lib.lnasr_fb_accumulate(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), ptr(self._b), ptr(self._bm),
                                             ptr(self._alpha), ptr(self._off_d), self._n_utt, T, ptr(self.logA), ptr(self.logw),
-                                            ptr(self.mu), n, m, d, ptr(self.acc), None, None, st), "fb_accumulate")
+                                            ptr(self.mu), n, m, d, ptr(self.acc), None, None, ptr(self._ws), self._ws.numel(), st),
+                    "fb_accumulate")
         if reduce_fn is not None:
             reduce_fn(self.acc)                       # SUM over ranks of S0 | S1 | S2c | xi_sum | pi_occ | loglik | n_utt
         loglik = self.acc[-2:-1].clone()

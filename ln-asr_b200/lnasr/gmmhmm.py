@@ -101,13 +101,24 @@ class GMMHMM(HMM):
     def _acc_size(self) -> int:
         return int(_capi.lib().lnasr_em_acc_doubles(self.n, self.m, self.d))
 
-    def _accumulate(self, x_d, b, bm, alpha, f_off_d, n_utt, total, acc):
+    _fb_split = None      # None: choose by batch size; True / False force the two-kernel / the fused Baum-Welch path
+
+    def _accumulate(self, x_d, b, bm, alpha, f_off_d, n_utt, total, acc, split=None):
+        """Baum-Welch statistics of a batch into `acc`.  split=True: two-kernel form (lane groups per utterance + frame-parallel
+        statistics), False: one fused kernel with a CTA per utterance; default: split when the batch has >= 8 utterances."""
         t = _dev.torch()
         g = self._packed()
-        _capi.check(_capi.lib().lnasr_fb_accumulate(
+        lib = _capi.lib()
+        if split is None:
+            split = self._fb_split if self._fb_split is not None else n_utt >= 8
+        ws, ws_bytes = None, 0
+        if split:
+            ws_bytes = int(lib.lnasr_fb_workspace_bytes(total, self.n))
+            ws = _dev.empty((ws_bytes,), t.uint8)
+        _capi.check(lib.lnasr_fb_accumulate(
             _capi.ptr(x_d), _dev.np_dtype_code(x_d.dtype), x_d.stride(0), _capi.ptr(b), _capi.ptr(bm), _capi.ptr(alpha),
             _capi.ptr(f_off_d), n_utt, total, _capi.ptr(self._trans().logA), _capi.ptr(g.logw_d), _capi.ptr(g.mu_d),
-            self.n, self.m, self.d, _capi.ptr(acc), None, None, _capi.stream_ptr()), "fb_accumulate")
+            self.n, self.m, self.d, _capi.ptr(acc), None, None, _capi.ptr(ws), ws_bytes, _capi.stream_ptr()), "fb_accumulate")
 
     def _finalize(self, acc) -> dict:
         t = _dev.torch()

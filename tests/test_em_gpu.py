@@ -99,8 +99,9 @@ def test_config1_first_iteration_matches_reference_exactly(golden):
     assert_close(np.exp(m.A), np.exp(g["A1"]), 1e-9, "A1")
 
 
-@pytest.mark.parametrize("n,mix,d,n_utt", [(3, 8, 39, 12), (5, 4, 39, 7), (1, 2, 3, 4), (8, 2, 5, 9)])
-def test_multi_utterance_em_against_oracle(n, mix, d, n_utt):
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("n,mix,d,n_utt", [(3, 8, 39, 12), (5, 4, 39, 7), (1, 2, 3, 4), (8, 2, 5, 9), (2, 1, 7, 33), (17, 3, 11, 5)])
+def test_multi_utterance_em_against_oracle(n, mix, d, n_utt, split):
     """BASELINE config 3 shapes (3 states x 8 mixtures x 39 dims): statistics summed over utterances."""
     from lnasr.gmmhmm import GMMHMM
     from oracle import lnasr_oracle as O
@@ -110,6 +111,7 @@ def test_multi_utterance_em_against_oracle(n, mix, d, n_utt):
     utts[0] = utts[0][:1]                                  # a one-frame utterance: no transition statistics
     new_ref, tot = O.em_step_multi_diag(utts, mdl)
     m = GMMHMM(n, mix, d, A=mdl["A"], pi=mdl["pi"], w=mdl["w"], mu=mdl["mu"], si=mdl["var"][..., None] * np.eye(d))
+    m._fb_split = split                                    # fused single kernel / lane-group recursion + frame-parallel statistics
     hist = m.train_batch(utts, iters=1, verbose=False)
     assert abs(hist[0][0] - tot["loglik"]) < 1e-3 * n_utt                   # 1e-3 absolute per utterance
     assert abs(hist[0][0] - tot["loglik"]) < 1e-8 * abs(tot["loglik"])
