@@ -248,6 +248,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = None
+    if world > 1 and not args.no_numa_bind:
+        from lnasr.dist import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)           # before the pinned host buffers are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = WORKLOADS[args.workload]
@@ -360,7 +364,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + cfg["desc"], "utts_per_gpu": n_utt, "frames_per_gpu_step": frames,
                        "pcm_bytes_per_gpu_step": int(pcm_np.nbytes), "l2": "inputs larger than L2 (PCM + intermediates > 126 MB per step)",
-                       "parallelism": f"utterance-sharded x{world}, no data-path collective", "viterbi_paths": want_paths},
+                       "parallelism": f"utterance-sharded x{world}, no data-path collective", "viterbi_paths": want_paths,
+                       "host_numa_binding": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pcm_np.nbytes) + int(off.nbytes) * 2, "d2h_bytes_per_step": n_utt * 12},
@@ -609,6 +614,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams the utterance groups alternate between")
     ap.add_argument("--e2e-chunks", type=int, default=6, help="utterance groups the host->device copy is pipelined over")
     args = ap.parse_args()
