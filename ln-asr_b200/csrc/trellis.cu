@@ -101,6 +101,14 @@ constexpr int TS_BT = 16;    // backpointer rows fetched per round of the in-ker
 template <int G, typename BT, int MODE, int PF>
 __global__ void __launch_bounds__(TS_WARPS * 32)
 trellis_small_kernel(TrellisArgs a) {
+    // log-sum-exp modes use the table-driven exp / log of common.cuh (the recursion is one serial chain per pair: the
+    // latency of exp() and log() IS the run time)
+    __shared__ __align__(16) double2 log_tab[MODE == MODE_VITERBI ? 1 : 128];
+    __shared__ double exp_tab[MODE == MODE_VITERBI ? 1 : 64];
+    if (MODE != MODE_VITERBI) {
+        fill_log_exp_tables(log_tab, exp_tab, threadIdx.x, TS_WARPS * 32);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PPW = 32 / G;                                   // pairs per warp
     const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
@@ -175,8 +183,8 @@ trellis_small_kernel(TrellisArgs a) {
                 }
                 double sum = 0.0;
 #pragma unroll
-                for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
-                nv = (s == 0) ? 0.0 : ((mx == neg_inf()) ? mx : mx + log(sum));
+                for (int q = 0; q < G; ++q) sum += fast_exp_neg(cand[q] - mx, exp_tab);          // -inf (and -inf - -inf) -> 0
+                nv = (s == 0) ? 0.0 : ((mx == neg_inf()) ? mx : mx + fast_log(sum, log_tab));
             } else if (MODE == MODE_FORWARD) {
                 // alpha[0] = pi + b[:,0] ; alpha[t,j] = lse_i (alpha[t-1,i] + A[i,j]) + b[j,t]   (hmm.py:95-99)
                 double cand[G];
@@ -188,8 +196,8 @@ trellis_small_kernel(TrellisArgs a) {
                 }
                 double sum = 0.0;
 #pragma unroll
-                for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
-                const double l = (mx == neg_inf()) ? mx : mx + log(sum);
+                for (int q = 0; q < G; ++q) sum += fast_exp_neg(cand[q] - mx, exp_tab);
+                const double l = (mx == neg_inf()) ? mx : mx + fast_log(sum, log_tab);
                 nv = (s == 0) ? pi_j + e : l + e;
             } else {
                 // v[0] = pi + b[:,0] ; v[t,j] = max_i (v[t-1,i] + A[i,j]) + b[j,t] ; bt = FIRST argmax (hmm.py:160-166):
@@ -276,8 +284,8 @@ trellis_small_kernel(TrellisArgs a) {
         }
         double sum = 0.0;
 #pragma unroll
-        for (int q = 0; q < G; ++q) sum += (cand[q] == neg_inf()) ? 0.0 : exp(cand[q] - mx);
-        if (pair_ok && j == 0 && a.score_out) a.score_out[p] = (mx == neg_inf()) ? mx : mx + log(sum);
+        for (int q = 0; q < G; ++q) sum += fast_exp_neg(cand[q] - mx, exp_tab);
+        if (pair_ok && j == 0 && a.score_out) a.score_out[p] = (mx == neg_inf()) ? mx : mx + fast_log(sum, log_tab);
     }
 }
 
