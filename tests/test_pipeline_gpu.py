@@ -67,3 +67,32 @@ def test_fused_entry_point_with_tensor_core_emissions():
     res, _ = pipe.recognize_batch(pcm, off, want_paths=True)
     w_f, b_f, p_f = pipe.recognize_batch_fused(torch.from_numpy(pcm).cuda(), off, want_paths=True)
     assert torch.equal(res.words, w_f) and torch.equal(res.best, b_f) and torch.equal(res.paths, p_f)
+
+
+def test_sixty_second_utterance_and_batch_of_one():
+    """BASELINE config 5 extremes through the whole path: one 60 s utterance (5 999 frames) alone in a batch, next to 0.1 s
+    ones in another; paths against the oracle's Viterbi on the same emissions."""
+    import torch
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+    from oracle import lnasr_oracle as O
+    from helpers import assert_paths_equal_ties_aside
+    rng = np.random.default_rng(60)
+    models = _models(rng, 3, 5, 4)
+    pipe = AcousticPipeline(MFCC(), ModelBank(models, emission="exact"))
+    pcm1, off1, _ = _batch(rng, [960000])
+    res1, mb1 = pipe.recognize_batch(pcm1, off1, want_paths=True)
+    assert int(mb1.frame_offsets_host[-1]) == 5999 and res1.paths.shape == (3, 5999)
+    pcm2, off2, _ = _batch(rng, [1600, 960000, 2000, 1700])
+    pcm2[off2[1]:off2[2]] = pcm1                                    # the same long utterance inside a ragged batch
+    res2, mb2 = pipe.recognize_batch(pcm2, off2, want_paths=True)
+    f = mb2.frame_offsets_host
+    assert torch.equal(res2.scores[1], res1.scores[0]) and torch.equal(res2.paths[:, f[1]:f[2]], res1.paths)
+    w_f, b_f, p_f = pipe.recognize_batch_fused(torch.from_numpy(pcm2).cuda(), off2, want_paths=True)
+    assert torch.equal(w_f, res2.words) and torch.equal(p_f, res2.paths)
+    # oracle Viterbi of model 1 on the long utterance, from the emissions the GPU produced
+    b = pipe.bank.emissions(mb1.feats).cpu().numpy()
+    k = 1
+    v, bt, path = O.viterbi(models[k]["pi"], models[k]["A"], b[:, 5 * k:5 * k + 5].T.copy())
+    assert abs(v[-1].max() - float(res1.scores[0, k])) < 1e-6
+    assert_paths_equal_ties_aside(res1.paths[k].cpu().numpy(), path, models[k]["pi"], models[k]["A"], b[:, 5 * k:5 * k + 5].T, what="60 s path")
