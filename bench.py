@@ -271,7 +271,7 @@ def run_ours(args):
     def step_e2e():
         # public host-facing API: pinned PCM in, decoded words + scores out; the H2D copy is chunked and overlapped
         return pipe.recognize_batch_host(pcm_host, off, n_chunks=args.e2e_chunks, want_paths=want_paths,
-                                         n_compute_streams=args.e2e_streams)
+                                         n_compute_streams=args.e2e_streams, taper=not args.e2e_uniform)
 
     def barrier():
         if world > 1:
@@ -615,6 +615,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA node")
+    ap.add_argument("--e2e-uniform", action="store_true", help="equal utterance groups instead of tapered ones")
     ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams the utterance groups alternate between")
     ap.add_argument("--e2e-chunks", type=int, default=6, help="utterance groups the host->device copy is pipelined over")
     args = ap.parse_args()

@@ -98,7 +98,7 @@ class AcousticPipeline:
         return res, mb
 
     def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 6, want_paths: bool = False,
-                             n_compute_streams: int = 2):
+                             n_compute_streams: int = 2, taper: bool = False, _timeline=None):
         """End-to-end entry point for HOST audio: `pcm_host` is a pinned CPU tensor (int16 or float32) of concatenated
         utterances, `sample_offsets` [n+1] host.  The batch is cut into `n_chunks` groups of whole utterances.  All
         host->device copies are queued up front on a copy stream (one event per group), so the copy engine streams
@@ -109,12 +109,40 @@ class AcousticPipeline:
         off = np.asarray(sample_offsets, dtype=np.int64)
         n_utt = len(off) - 1
         n_chunks = max(1, min(n_chunks, n_utt))
-        # chunk boundaries at utterance borders, ~equal sample counts
-        targets = off[0] + (off[-1] - off[0]) * np.arange(1, n_chunks) / n_chunks
+        # group boundaries at utterance borders.  Tapered sizes (1, 3, 4, .., 4, 3, 1): copy and compute are nearly balanced,
+        # so the time to the first result (first copy) and the tail after the last copy (last group's compute) are what is
+        # left to shave -- both want small groups at the ends, while few large groups in the middle keep the per-group
+        # launch and tail costs low.
+        if taper and n_chunks >= 3:
+            wts = np.minimum(np.minimum(1 + 2 * np.arange(n_chunks), 1 + 2 * np.arange(n_chunks)[::-1]), 4).astype(np.float64)
+        else:
+            wts = np.ones(n_chunks)
+        fr = np.cumsum(wts)[:-1] / wts.sum()
+        targets = off[0] + (off[-1] - off[0]) * fr
         cuts = np.unique(np.concatenate([[0], np.searchsorted(off, targets), [n_utt]]))
         bounds = [(int(cuts[i]), int(cuts[i + 1])) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+        # The path is bound by the one host->device copy engine, so (1) the first group's PCM goes out before any other host
+        # work, (2) the per-group offsets are computed while it flies and queued right behind it (they are tiny, but a copy
+        # queued after ALL the PCM would arrive last), (3) then the remaining groups.
+        dev = _dev.device()
+        cur = t.cuda.current_stream()
+        if not hasattr(self, "_streams"):
+            self._streams = (t.cuda.Stream(), t.cuda.Stream(), t.cuda.Stream())
+        copy_s, comp_a, comp_b = self._streams
+        comps = (comp_a, comp_b) if n_compute_streams >= 2 else (comp_a,)
+        copy_s.wait_stream(cur)
+        total_samples = int(off[-1] - off[0])
+        events = []
+
+        def queue_pcm(lo, hi):
+            s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
+            pcm_dev[s0:s1].copy_(pcm_host[int(off[lo]):int(off[hi])], non_blocking=True)
+
+        with t.cuda.stream(copy_s):
+            pcm_dev = t.empty((total_samples,), dtype=pcm_host.dtype, device=dev)
+            queue_pcm(*bounds[0])
+        # frame counts and offsets relative to each group's first sample / frame: [s_off | f_off] per group, one array
         n_fr = self.mfcc.frame_counts(off)
-        # per-group offsets relative to the group's first sample / frame, all groups in one array: [s_off | f_off] per group
         meta, plan = [], []
         pos = 0
         for lo, hi in bounds:
@@ -124,28 +152,18 @@ class AcousticPipeline:
             plan.append((pos, pos + len(s_rel), f_rel))
             pos += 2 * len(s_rel)
         meta_host = t.from_numpy(np.concatenate(meta)).pin_memory()
-        dev = _dev.device()
-        cur = t.cuda.current_stream()
-        if not hasattr(self, "_streams"):
-            self._streams = (t.cuda.Stream(), t.cuda.Stream(), t.cuda.Stream())
-        copy_s, comp_a, comp_b = self._streams
-        comps = (comp_a, comp_b) if n_compute_streams >= 2 else (comp_a,)
-        copy_s.wait_stream(cur)
-        for cs in comps:
-            cs.wait_stream(cur)
-        total_samples = int(off[-1] - off[0])
         max_frames = max(int(p[2][-1]) for p in plan)
         with t.cuda.stream(copy_s):
-            pcm_dev = t.empty((total_samples,), dtype=pcm_host.dtype, device=dev)
             meta_dev = t.empty((meta_host.numel(),), dtype=t.int64, device=dev)
             meta_dev.copy_(meta_host, non_blocking=True)
-            events = []
-            for lo, hi in bounds:
-                s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
-                pcm_dev[s0:s1].copy_(pcm_host[int(off[lo]):int(off[hi])], non_blocking=True)
-                ev = t.cuda.Event()
+            for i, (lo, hi) in enumerate(bounds):
+                if i > 0:
+                    queue_pcm(lo, hi)
+                ev = t.cuda.Event(enable_timing=_timeline is not None)
                 ev.record(copy_s)
                 events.append(ev)
+        for cs in comps:
+            cs.wait_stream(cur)
         with t.cuda.stream(comps[0]):
             words = t.empty((n_utt,), dtype=t.int32, device=dev)
             best = t.empty((n_utt,), dtype=t.float64, device=dev)
@@ -176,6 +194,10 @@ class AcousticPipeline:
                 C.c_void_p(meta_dev.data_ptr() + 8 * p1), nu, int(f_rel[-1]), C.byref(rec),
                 C.c_void_p(words.data_ptr() + 4 * lo), C.c_void_p(best.data_ptr() + 8 * lo), _capi.ptr(paths[i % len(comps)]),
                 _capi.ptr(ws[i % len(comps)]), need.value, C.c_void_p(cs.cuda_stream)), "recognize_batch")
+            if _timeline is not None:                      # diagnostic: (copy-done event, compute-done event) per group
+                done = t.cuda.Event(enable_timing=True)
+                done.record(cs)
+                _timeline.append((ev, done))
         for cs in comps[1:]:
             comps[0].wait_stream(cs)
         with t.cuda.stream(comps[0]):
