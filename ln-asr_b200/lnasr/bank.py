@@ -108,6 +108,8 @@ class AcousticPipeline:
         t = _dev.torch()
         off = np.asarray(sample_offsets, dtype=np.int64)
         n_utt = len(off) - 1
+        if n_utt <= 0:
+            return t.empty((0,), dtype=t.int32), t.empty((0,), dtype=t.float64)
         n_chunks = max(1, min(n_chunks, n_utt))
         # group boundaries at utterance borders.  Tapered sizes (1, 3, 4, .., 4, 3, 1): copy and compute are nearly balanced,
         # so the time to the first result (first copy) and the tail after the last copy (last group's compute) are what is
@@ -234,6 +236,8 @@ class AcousticPipeline:
         lib = _capi.lib()
         off = np.asarray(sample_offsets, dtype=np.int64)
         n_utt = len(off) - 1
+        if n_utt <= 0:
+            return _dev.empty((0,), t.int32), _dev.empty((0,), t.float64), (_dev.empty((self.bank.K, 0), t.int32) if want_paths else None)
         f_off = _dev.offsets_from_lengths(self.mfcc.frame_counts(off))
         total = int(f_off[-1])
         meta = _dev.to_dev(np.concatenate([off - off[0], f_off]), t.int64)

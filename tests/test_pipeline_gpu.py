@@ -96,3 +96,15 @@ def test_sixty_second_utterance_and_batch_of_one():
     v, bt, path = O.viterbi(models[k]["pi"], models[k]["A"], b[:, 5 * k:5 * k + 5].T.copy())
     assert abs(v[-1].max() - float(res1.scores[0, k])) < 1e-6
     assert_paths_equal_ties_aside(res1.paths[k].cpu().numpy(), path, models[k]["pi"], models[k]["A"], b[:, 5 * k:5 * k + 5].T, what="60 s path")
+
+
+def test_empty_batch():
+    import torch
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+    rng = np.random.default_rng(1)
+    pipe = AcousticPipeline(MFCC(), ModelBank(_models(rng, 2, 3, 2), emission="exact"))
+    w, b = pipe.recognize_batch_host(torch.empty((0,), dtype=torch.int16).pin_memory(), np.zeros(1, dtype=np.int64))
+    assert w.numel() == 0 and b.numel() == 0
+    w, b, p = pipe.recognize_batch_fused(torch.empty((0,), dtype=torch.int16, device="cuda"), np.zeros(1, dtype=np.int64), want_paths=True)
+    assert w.numel() == 0 and p.shape == (2, 0)
