@@ -24,31 +24,36 @@ constexpr int GX_MAX_DIM = 64;
 // log N(x) = sum_d (a_d x_d + b_d) x_d + c   -- two DFMA per (Gaussian, dim); float64 makes the expansion harmless.
 __host__ __device__ inline int gx_chunks(int n_mix) { return (n_mix + 3) / 4; }
 
+// one WARP per (state, chunk, mixture): the model is re-packed every EM iteration, so the pack must not be a serial loop
 __global__ void gmm_pack_exact_kernel(const double* __restrict__ logw, const double* __restrict__ mu,
                                       const double* __restrict__ var, int n_states, int n_mix, int dim,
                                       double* __restrict__ packed) {
     const int nch = gx_chunks(n_mix);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // (state, chunk, g)
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // (state, chunk, g)
+    const int lane = threadIdx.x & 31;
     if (idx >= n_states * nch * 4) return;
     const int g = idx & 3, ch = (idx >> 2) % nch, j = (idx >> 2) / nch;
     const int m = ch * 4 + g;
     double* o = packed + (int64_t)(j * nch + ch) * (dim + 1) * 8;
     if (m >= n_mix) {
-        for (int d = 0; d < dim; ++d) { o[d * 8 + g] = 0.0; o[d * 8 + 4 + g] = 0.0; }
-        o[dim * 8 + g] = 0.0;
-        o[dim * 8 + 4 + g] = neg_inf();
+        for (int d = lane; d < dim; d += 32) { o[d * 8 + g] = 0.0; o[d * 8 + 4 + g] = 0.0; }
+        if (lane == 0) { o[dim * 8 + g] = 0.0; o[dim * 8 + 4 + g] = neg_inf(); }
         return;
     }
     const int64_t gi = (int64_t)j * n_mix + m;
-    double c = (double)dim * 1.8378770664093453;  /* ln(2 pi) */
-    for (int d = 0; d < dim; ++d) {
+    double c = 0.0;
+    for (int d = lane; d < dim; d += 32) {
         const double v = var[gi * dim + d], mm = mu[gi * dim + d];
         o[d * 8 + g] = -0.5 / v;
         o[d * 8 + 4 + g] = mm / v;
         c += log(v) + mm * mm / v;
     }
-    o[dim * 8 + g] = -0.5 * c;
-    o[dim * 8 + 4 + g] = logw[gi];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0) {
+        o[dim * 8 + g] = -0.5 * (c + (double)dim * 1.8378770664093453);   /* ln(2 pi) */
+        o[dim * 8 + 4 + g] = logw[gi];
+    }
 }
 
 __device__ __forceinline__ void lse_push(double v, double& mx, double& sum) {
@@ -203,29 +208,37 @@ __host__ __device__ inline int64_t gm_groups(int n_states, int n_mix) {
 }
 __host__ __device__ inline bool gm_supported(int n_mix, int dim) { return n_mix <= 8 && dim <= GM_MAX_DIM; }
 
-// image: [n_groups*40][84] doubles, Gaussian (state j, mixture m) at row j*MP + m
+// image: [n_groups*40][84] doubles, Gaussian (state j, mixture m) at row j*MP + m.  One warp per row.
 __global__ void gmm_pack_mma_kernel(const double* __restrict__ logw, const double* __restrict__ mu,
                                     const double* __restrict__ var, int n_states, int n_mix, int dim,
                                     double* __restrict__ img) {
     const int MP = gm_mpad(n_mix);
     const int64_t rows = gm_groups(n_states, n_mix) * GM_GROUP;
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     double* o = img + row * GM_LDB;
-    for (int k = 0; k < GM_LDB; ++k) o[k] = 0.0;
     const int64_t j = row / MP;
     const int m = (int)(row % MP);
-    if (j >= n_states || m >= n_mix) { o[80] = neg_inf(); return; }
+    const bool real = j < n_states && m < n_mix;
     const int64_t gi = j * n_mix + m;
-    double c = (double)dim * 1.8378770664093453;  /* ln(2 pi) */
-    for (int d = 0; d < dim; ++d) {
-        const double v = var[gi * dim + d], mm = mu[gi * dim + d];
-        o[2 * d] = -0.5 / v;
-        o[2 * d + 1] = mm / v;
-        c += log(v) + mm * mm / v;
+    double c = 0.0;
+    for (int k = lane; k < GM_LDB; k += 32) {
+        double val = 0.0;
+        const int d = k >> 1;
+        if (real && k < 2 * dim) {
+            const double v = var[gi * dim + d], mm = mu[gi * dim + d];
+            if (k & 1) val = mm / v;
+            else { val = -0.5 / v; c += log(v) + mm * mm / v; }
+        }
+        if (k != 2 * dim && k != 80) o[k] = val;
     }
-    o[2 * dim] = -0.5 * c;
-    o[80] = logw[gi];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0) {
+        o[2 * dim] = real ? -0.5 * (c + (double)dim * 1.8378770664093453) : 0.0;   /* ln(2 pi) */
+        if (2 * dim != 80) o[80] = real ? logw[gi] : neg_inf();
+    }
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -527,11 +540,11 @@ extern "C" int lnasr_gmm_pack_exact(const double* logw, const double* mu, const 
     LNASR_CHECK_ARG(logw && mu && var && packed, "gmm_pack_exact: null pointer");
     LNASR_CHECK_ARG(n_states >= 1 && n_mix >= 1 && dim >= 1, "gmm_pack_exact: bad shape");
     const int n = n_states * gx_chunks(n_mix) * 4;
-    gmm_pack_exact_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, packed);
+    gmm_pack_exact_kernel<<<(n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, packed);
     LNASR_LAUNCH_CHECK();
     if (gm_supported(n_mix, dim)) {
         const int64_t rows = gm_groups(n_states, n_mix) * GM_GROUP;
-        gmm_pack_mma_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, (cudaStream_t)stream>>>(
+        gmm_pack_mma_kernel<<<(unsigned)ceil_div(rows * 32, 128), 128, 0, (cudaStream_t)stream>>>(
             logw, mu, var, n_states, n_mix, dim, packed + gx_simt_doubles(n_states, n_mix, dim));
         LNASR_LAUNCH_CHECK();
     }
