@@ -226,6 +226,13 @@ int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t ld_feats, co
                         int32_t dim, double* acc /*in/out, caller zeroes*/, double* gamma_out /*[T,N] log or NULL*/,
                         double* beta_out /*[T,N] log or NULL*/, void* workspace /*or NULL*/, size_t workspace_bytes,
                         void* stream);
+/* The same statistics from alpha AND beta (lnasr_forward_batch, lnasr_backward_batch: two independent trellis passes that
+ * can run concurrently on two streams): everything that is not a recursion -- Z_t, gamma, xi / pi sums, mixture occupancies,
+ * S0 / S1 / S2c -- in one frame-parallel kernel.  Same accumulator layout; gamma_out [T,N] optional (row T-1 = -inf). */
+int lnasr_em_statistics(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
+                        const double* alpha, const double* beta, const int64_t* frame_offsets, int32_t n_utt,
+                        int64_t total_frames, const double* logA, const double* logw, const double* mu, int32_t N,
+                        int32_t n_mix, int32_t dim, double* acc /*in/out*/, double* gamma_out /*or NULL*/, void* stream);
 /* M-step from (all-reduced) statistics; writes the new model in place of the old device arrays */
 int lnasr_mstep_finalize(const double* acc, int32_t N, int32_t n_mix, int32_t dim, double min_std,
                          double* logA, double* logpi, double* logw, double* mu, double* var, void* stream);

@@ -541,6 +541,155 @@ em_stats_kernel(FbArgs a, const double* __restrict__ lgamma, int64_t total_frame
     }
 }
 
+// Third form: BOTH recursions are plain trellis passes (lnasr_forward_batch, lnasr_backward_batch -- independent of each
+// other, so they can run concurrently on two streams) and EVERYTHING else is frame-parallel here: Z_t, log gamma, the xi /
+// pi statistics (hmm.py:190-199, gmmhmm.py:83-86), the mixture occupancies and S0 / S1 / S2c (gmmhmm.py:89-147).
+// The serial chain per utterance shrinks to 4 exp + 1 log per step; with ~1000 utterances (config 3) the recursions are
+// pure latency, so this is what sets the iteration time.
+__global__ void __launch_bounds__(ES_THREADS)
+em_stats_ab_kernel(FbArgs a, const double* __restrict__ beta, int64_t total_frames) {
+    extern __shared__ __align__(16) unsigned char em_smem_raw[];
+    double* sm = reinterpret_cast<double*>(em_smem_raw);
+    const int N = a.N, M = a.M, D = a.D, NM = N * M;
+    const int tid = threadIdx.x;
+    double2* log_tab = reinterpret_cast<double2*>(sm);
+    double* exp_tab = sm + 256;
+    double* acc_s = exp_tab + 64;                         // S0[NM] | S1[NM*D] | S2c[NM*D] | xi[N*N] | pi[N] | loglik | n_utt
+    const int n_acc = NM * (2 * D + 1) + N * N + N + 2;
+    double* mu_s = acc_s + n_acc;
+    double* logw_s = mu_s + NM * D;
+    double* A_s = logw_s + NM;                            // [N][N]
+    double* occ_s = A_s + N * N;                          // [ES_TILE][NM]
+    double* x_s = occ_s + ES_TILE * NM;                   // [ES_TILE][D]
+    double* al_s = x_s + ES_TILE * D;                     // [ES_TILE][N]      alpha[t]
+    double* ub_s = al_s + ES_TILE * N;                    // [ES_TILE+1][N]    beta[t] (then b[t]+beta[t] for the xi pass)
+    double* z_s = ub_s + (ES_TILE + 1) * N;               // [ES_TILE]
+    int* flag_s = reinterpret_cast<int*>(z_s + ES_TILE);  // [ES_TILE] bit0 = first frame of its utterance, bit1 = last
+    for (int i = tid; i < n_acc; i += ES_THREADS) acc_s[i] = 0.0;
+    for (int i = tid; i < NM * D; i += ES_THREADS) mu_s[i] = a.mu[i];
+    for (int i = tid; i < NM; i += ES_THREADS) logw_s[i] = a.logw[i];
+    for (int i = tid; i < N * N; i += ES_THREADS) A_s[i] = a.logA[i];
+    fill_log_exp_tables(log_tab, exp_tab, tid, ES_THREADS);
+    __syncthreads();
+    double* xi_s = acc_s + NM * (2 * D + 1);
+    double* pi_s = xi_s + N * N;
+    const int64_t n_tiles = (total_frames + ES_TILE - 1) / ES_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * ES_TILE;
+        const int nt = (int)min((int64_t)ES_TILE, total_frames - t0);
+        const int nt1 = (int)min((int64_t)ES_TILE + 1, total_frames - t0);       // one more row for the xi terms
+        for (int i = tid; i < nt * N; i += ES_THREADS) al_s[i] = __ldg(a.alpha + t0 * N + i);
+        for (int i = tid; i < nt1 * N; i += ES_THREADS) ub_s[i] = __ldg(beta + t0 * N + i);
+        for (int i = tid; i < nt; i += ES_THREADS) {
+            const int u = find_utt(a.frame_off, a.n_utt, t0 + i);
+            flag_s[i] = (t0 + i == __ldg(a.frame_off + u) ? 1 : 0) | (t0 + i == __ldg(a.frame_off + u + 1) - 1 ? 2 : 0);
+        }
+        for (int i = tid; i < nt * D; i += ES_THREADS) {
+            const int r = i / D, d = i - r * D;
+            const int64_t row = t0 + r;
+            x_s[i] = a.feats_f64 ? __ldg((const double*)a.feats + row * a.ld_feats + d)
+                                 : (double)__ldg((const float*)a.feats + row * a.ld_feats + d);
+        }
+        __syncthreads();
+        // Z_t = lse_j (alpha + beta)  -- one thread per frame
+        for (int tt = tid; tt < nt; tt += ES_THREADS) {
+            double mx = neg_inf();
+            for (int j = 0; j < N; ++j) mx = fmax(mx, al_s[tt * N + j] + ub_s[tt * N + j]);
+            double sum = 0.0;
+            for (int j = 0; j < N; ++j) sum += fast_exp_neg(al_s[tt * N + j] + ub_s[tt * N + j] - mx, exp_tab);
+            const double Z = (mx == neg_inf()) ? mx : mx + fast_log(sum, log_tab);
+            z_s[tt] = Z;
+            if ((flag_s[tt] & 2) && Z == Z) {                      // last frame: beta = 0, so Z = log P(O)   (hmm.py:274)
+                atomicAdd(acc_s + n_acc - 2, Z);
+                atomicAdd(acc_s + n_acc - 1, 1.0);
+            }
+        }
+        __syncthreads();
+        // mixture occupancies for ALL t (gmmhmm.py:98-100); gamma output; pi statistics
+        for (int i = tid; i < nt * NM; i += ES_THREADS) {
+            const int tt = i / NM, p = i - tt * NM, j = p / M;
+            const double ab = al_s[tt * N + j] + ub_s[tt * N + j], Z = z_s[tt];
+            const double bj = __ldg(a.b + (t0 + tt) * N + j);
+            double o = 0.0;
+            if (ab != neg_inf() && Z != neg_inf() && bj != neg_inf())
+                o = fast_exp_neg(ab - Z + logw_s[p] + __ldg(a.bm + (t0 + tt) * NM + p) - bj, exp_tab);
+            occ_s[i] = o;
+        }
+        for (int i = tid; i < nt * N; i += ES_THREADS) {
+            const int tt = i / N;
+            const double ab = al_s[i] + ub_s[i], Z = z_s[tt];
+            const double g2 = (ab == neg_inf() || Z == neg_inf()) ? neg_inf() : ab - Z;
+            if (a.gamma_out) a.gamma_out[t0 * N + i] = (flag_s[tt] & 2) ? neg_inf() : g2;      // hmm.py:199
+            if ((flag_s[tt] & 3) == 1 && g2 != neg_inf()) atomicAdd(pi_s + (i - tt * N), fast_exp_neg(g2, exp_tab));   // pi' = gamma[0]
+        }
+        __syncthreads();
+        // u[t,j] = b[t,j] + beta[t,j] replaces beta in place (rows 0..nt1-1); row tt+1 feeds xi[tt]
+        for (int i = tid; i < nt1 * N; i += ES_THREADS) ub_s[i] += __ldg(a.b + t0 * N + i);
+        // sufficient statistics
+        for (int e = tid; e < NM * D; e += ES_THREADS) {
+            const int jm = e / D, d = e - jm * D;
+            double s1 = 0.0, s2 = 0.0;
+            const double m0 = mu_s[e];
+#pragma unroll 4
+            for (int tt = 0; tt < nt; ++tt) {
+                const double o = occ_s[tt * NM + jm];
+                const double x = x_s[tt * D + d];
+                const double df = x - m0;
+                s1 = fma(o, x, s1);
+                s2 = fma(o * df, df, s2);
+            }
+            acc_s[NM + e] += s1;
+            acc_s[NM + NM * D + e] += s2;
+        }
+        for (int jm = tid; jm < NM; jm += ES_THREADS) {
+            double s0 = 0.0;
+            for (int tt = 0; tt < nt; ++tt) s0 += occ_s[tt * NM + jm];
+            acc_s[jm] += s0;
+        }
+        __syncthreads();
+        // xi[t,i,j] = alpha[t,i] + A[i,j] + b[t+1,j] + beta[t+1,j] - Z_t, t not the last frame of its utterance (hmm.py:190-197)
+        // (lane = transition, warp = every 8th frame: N*N is 9 for a 3-state model, far fewer than the block has threads)
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int e = lane; e < N * N; e += 32) {
+                const int i = e / N, j = e - i * N;
+                const double aij = A_s[e];
+                if (aij == neg_inf()) continue;
+                double sx = 0.0;
+                for (int tt = warp; tt < nt; tt += ES_THREADS / 32) {
+                    if (flag_s[tt] & 2) continue;
+                    sx += fast_exp_neg(al_s[tt * N + i] + aij + ub_s[(tt + 1) * N + j] - z_s[tt], exp_tab);   // -inf / NaN -> 0
+                }
+                if (sx != 0.0) atomicAdd(xi_s + e, sx);
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n_acc; i += ES_THREADS) {
+        const double v = acc_s[i];
+        if (v != 0.0) atomicAdd(a.acc + i, v);
+    }
+}
+
+static int launch_stats_ab(const FbArgs& a, const double* beta, int64_t total_frames, cudaStream_t stream) {
+    const int NM = a.N * a.M, N = a.N;
+    const size_t dbl = 256 + 64 + (size_t)NM * (2 * a.D + 1) + (size_t)N * N + N + 2 + (size_t)NM * a.D + NM + (size_t)N * N +
+                       (size_t)ES_TILE * NM + (size_t)ES_TILE * a.D + (size_t)ES_TILE * N + (size_t)(ES_TILE + 1) * N + ES_TILE + ES_TILE / 2 + 2;
+    const size_t smem = dbl * sizeof(double);
+    if (smem > 220 * 1024) {
+        set_error("em_statistics: N=%d, N*M=%d at dim=%d needs %zu bytes of shared memory (> 220 KB); model too large", N, NM, a.D, smem);
+        return LNASR_EINVAL;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
+    const int64_t n_tiles = ceil_div(total_frames, ES_TILE);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm));
+    if (smem > 48 * 1024)
+        LNASR_CUDA(cudaFuncSetAttribute(em_stats_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    em_stats_ab_kernel<<<grid, ES_THREADS, smem, stream>>>(a, beta, total_frames);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 static int launch_fb_split(const FbArgs& a, int64_t total_frames, double* lgamma, cudaStream_t stream) {
     int G = 1;
     while (G < a.N) G <<= 1;
@@ -646,6 +795,22 @@ extern "C" int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t l
         return launch_fb_split(a, total_frames, (double*)workspace, (cudaStream_t)stream);
     }
     return launch_fb<true>(a, (cudaStream_t)stream);
+}
+
+extern "C" int lnasr_em_statistics(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
+                                   const double* alpha, const double* beta, const int64_t* frame_offsets, int32_t n_utt,
+                                   int64_t total_frames, const double* logA, const double* logw, const double* mu, int32_t N,
+                                   int32_t n_mix, int32_t dim, double* acc, double* gamma_out, void* stream) {
+    LNASR_CHECK_ARG(feats && b && bm && alpha && beta && frame_offsets && logA && logw && mu && acc, "em_statistics: null pointer");
+    LNASR_CHECK_ARG(feats_dtype == LNASR_DT_F32 || feats_dtype == LNASR_DT_F64, "em_statistics: feats must be float32/float64");
+    LNASR_CHECK_ARG(N >= 1 && N <= 32 && n_mix >= 1 && dim >= 1 && ld_feats >= dim && n_utt >= 0, "em_statistics: bad shape (1 <= N <= 32)");
+    if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    FbArgs a{};
+    a.feats = feats; a.feats_f64 = (feats_dtype == LNASR_DT_F64); a.ld_feats = ld_feats;
+    a.b = b; a.bm = bm; a.alpha = alpha; a.frame_off = frame_offsets; a.n_utt = n_utt;
+    a.logA = logA; a.logw = logw; a.mu = mu; a.N = N; a.M = n_mix; a.D = dim; a.n_symbols = 0;
+    a.acc = acc; a.gamma_out = gamma_out; a.beta_out = nullptr;
+    return launch_stats_ab(a, beta, total_frames, (cudaStream_t)stream);
 }
 
 extern "C" int lnasr_mstep_finalize(const double* acc, int32_t N, int32_t n_mix, int32_t dim, double min_std,

@@ -3,7 +3,8 @@
 `GMMHMM.train` / `train_batch` mirror the reference's loop (hmm.py:285-313): the model lives in numpy attributes and every
 iteration makes a host round trip.  `EmTrainer` keeps the model ON THE DEVICE for the whole run; one iteration is
 
-    lnasr_gmm_pack_exact -> lnasr_gmm_loglik_exact (b, bm) -> lnasr_forward_batch (alpha) -> lnasr_fb_accumulate
+    lnasr_gmm_pack_exact -> lnasr_gmm_loglik_exact (b, bm) -> lnasr_forward_batch (alpha) || lnasr_backward_batch (beta, on a
+    side stream) -> lnasr_em_statistics (frame-parallel: gamma, xi, occupancies, S0/S1/S2c)
     -> [all-reduce of the packed float64 accumulator over ranks] -> lnasr_mstep_finalize (in place)
 
 with no host synchronisation, so iterations can be queued back to back and the only multi-GPU traffic is the
@@ -60,7 +61,8 @@ class EmTrainer:
         self._bm = _dev.empty((T, self.n * self.m), t.float64)
         self._alpha = _dev.empty((T, self.n), t.float64)
         self._lp = _dev.empty((self._n_utt, 1), t.float64)
-        self._ws = _dev.empty((int(_capi.lib().lnasr_fb_workspace_bytes(T, self.n)),), t.uint8)
+        self._beta = _dev.empty((T, self.n), t.float64)
+        self._side = t.cuda.Stream()
         return self
 
     def iterate(self, reduce_fn=None):
@@ -73,13 +75,19 @@ class EmTrainer:
         _capi.check(lib.lnasr_gmm_pack_exact(ptr(self.logw), ptr(self.mu), ptr(self.var), n, m, d, ptr(self.packed), st), "gmm_pack_exact")
         _capi.check(lib.lnasr_gmm_loglik_exact(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), T, ptr(self.packed), n, m, d,
                                                ptr(self._b), _capi.DT_F64, n, ptr(self._bm), st), "gmm_loglik_exact")
+        # the two recursions are independent: backward on a side stream, forward here; everything else is frame-parallel
+        t = _dev.torch()
+        main = t.cuda.current_stream()
+        self._side.wait_stream(main)
+        _capi.check(lib.lnasr_backward_batch(ptr(self._b), _capi.DT_F64, n, ptr(self._off_d), self._n_utt, T, C.byref(self._bank),
+                                             ptr(self._beta), C.c_void_p(self._side.cuda_stream)), "backward_batch")
         _capi.check(lib.lnasr_forward_batch(ptr(self._b), _capi.DT_F64, n, ptr(self._off_d), self._n_utt, T,
                                             C.byref(self._bank), ptr(self._alpha), ptr(self._lp), st), "forward_batch")
         self.acc.zero_()
-        _capi.check(lib.lnasr_fb_accumulate(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), ptr(self._b), ptr(self._bm),
-                                            ptr(self._alpha), ptr(self._off_d), self._n_utt, T, ptr(self.logA), ptr(self.logw),
-                                            ptr(self.mu), n, m, d, ptr(self.acc), None, None, ptr(self._ws), self._ws.numel(), st),
-                    "fb_accumulate")
+        main.wait_stream(self._side)
+        _capi.check(lib.lnasr_em_statistics(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), ptr(self._b), ptr(self._bm),
+                                            ptr(self._alpha), ptr(self._beta), ptr(self._off_d), self._n_utt, T, ptr(self.logA),
+                                            ptr(self.logw), ptr(self.mu), n, m, d, ptr(self.acc), None, st), "em_statistics")
         if reduce_fn is not None:
             reduce_fn(self.acc)                       # SUM over ranks of S0 | S1 | S2c | xi_sum | pi_occ | loglik | n_utt
         loglik = self.acc[-2:-1].clone()

@@ -123,17 +123,19 @@ def test_multi_utterance_em_against_oracle(n, mix, d, n_utt, split):
         assert_close(np.exp(m.pi), np.exp(new_ref["pi"]), 1e-8, "pi")
 
 
-def test_device_resident_em_trainer_matches_oracle():
-    """lnasr.em.EmTrainer (model stays on the device, BASELINE config 3 shape): three iterations against the oracle's
-    multi-utterance EM, and against GMMHMM.train_batch."""
+@pytest.mark.parametrize("n,mix,d,n_utt", [(3, 8, 39, 9), (1, 2, 3, 5), (17, 3, 11, 4), (32, 2, 5, 3), (5, 4, 39, 40)])
+def test_device_resident_em_trainer_matches_oracle(n, mix, d, n_utt):
+    """lnasr.em.EmTrainer (model stays on the device; forward || backward on two streams, then the frame-parallel
+    lnasr_em_statistics): three iterations against the oracle's multi-utterance EM, and against GMMHMM.train_batch."""
     import torch
     from lnasr.em import EmTrainer
     from lnasr.gmmhmm import GMMHMM
     from oracle import lnasr_oracle as O
-    rng = np.random.default_rng(3)
-    n, mix, d = 3, 8, 39
+    rng = np.random.default_rng(3 + n)
     mdl = O.random_gmmhmm(n, mix, d, rng)
-    utts = [0.6 * rng.standard_normal((int(T), d)) for T in rng.integers(20, 60, size=9)]
+    utts = [0.6 * rng.standard_normal((int(T), d)) for T in rng.integers(20, 60, size=n_utt)]
+    utts[-1] = utts[-1][:1]                                   # a one-frame utterance: no transition / pi statistics
+    utts[0] = utts[0][:2]
     off = np.concatenate([[0], np.cumsum([len(u) for u in utts])])
     tr = EmTrainer(mdl).load_batch(torch.from_numpy(np.concatenate(utts)).cuda(), off)
     ref = dict(mdl)
