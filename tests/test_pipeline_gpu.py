@@ -108,3 +108,24 @@ def test_empty_batch():
     assert w.numel() == 0 and b.numel() == 0
     w, b, p = pipe.recognize_batch_fused(torch.empty((0,), dtype=torch.int16, device="cuda"), np.zeros(1, dtype=np.int64), want_paths=True)
     assert w.numel() == 0 and p.shape == (2, 0)
+
+
+def test_recognizer_isolated_words(tmp_path):
+    """lnasr.recognizer.Recognizer with several acoustic models: the word is the model with the best Viterbi score."""
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.gmmhmm import GMMHMM
+    from lnasr.mfcc import MFCC
+    from lnasr.recognizer import Recognizer
+    rng = np.random.default_rng(12)
+    models = _models(rng, 4, 5, 4)
+    files = {}
+    for name, mdl in zip(["yes", "no", "stop", "go"], models):
+        g = GMMHMM(5, 4, 39, A=mdl["A"], pi=mdl["pi"], w=mdl["w"], mu=mdl["mu"], si=mdl["var"][..., None] * np.eye(39))
+        files[name] = str(tmp_path / f"{name}.npz")
+        g.save(files[name])
+    r = Recognizer({"am": files, "lm": None})
+    _, _, sigs = _batch(rng, [9000, 12000, 7000, 15000, 8000])
+    words = r.recognize_batch(sigs)
+    ref = AcousticPipeline(MFCC(), ModelBank(models, emission="exact")).recognize(sigs)
+    assert words == [list(files)[i] for i in ref]
+    assert r.recognize(sigs[2]) == words[2]

@@ -88,3 +88,23 @@ def test_reference_recognizer_runs_unchanged(tmp_path):
     assert np.array_equal(r.am.gmmhmm.mu, am.mu)
     assert r.lm.ngram.order == 3 and np.isfinite(r.lm.ngram.calc_prob(ngram.Tokenizer.get_tokens(CORPUS[0])))
     assert r.recognize(np.zeros(16000, dtype=np.int16)) is None             # unimplemented in the reference (recognizer.py:46-48)
+
+
+def test_package_recognizer_module(tmp_path):
+    """`from lnasr.recognizer import Recognizer` (test/recognizer-test.py:13) resolves in this package too; with one acoustic
+    model `recognize` returns None like the reference's stub (recognizer.py:46-48)."""
+    from lnasr import ngram
+    from lnasr.gmmhmm import GMMHMM
+    from lnasr.recognizer import AcousticModel, LanguageModel, Recognizer
+    np.random.seed(5)
+    am = GMMHMM(n=3, m=2, d=39)
+    am.reset("random")
+    am_path, lm_path = str(tmp_path / "am.npz"), str(tmp_path / "tri.lm")
+    am.save(am_path)
+    ngram.NGramModelARPA().save(ngram.NGramModel(ngram.NGramCounter(2, _tokens(ngram))), lm_path)
+    r = Recognizer({"am": am_path, "lm": lm_path})
+    assert isinstance(r.am, AcousticModel) and isinstance(r.lm, LanguageModel)
+    assert (r.am.gmmhmm.n, r.am.gmmhmm.m, r.am.gmmhmm.d) == (3, 2, 39) and r.lm.ngram.order == 2
+    assert r.recognize(np.zeros(16000, dtype=np.int16)) is None
+    with pytest.raises(ValueError):
+        r.recognize_batch([np.zeros(16000, dtype=np.int16)])
