@@ -158,7 +158,6 @@ constexpr int TC_MAX_DIM = 39;                // the K axis is laid out for 39 d
 constexpr int TC_KP = 80;                     // 2*39 + 1 -> 80
 constexpr int TC_KH = TC_KP / 2;              // K values per ring slot
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-constexpr float TC_LOG2E = 1.4426950408889634f;
 constexpr float TC_LN2 = 0.6931471805599453f;
 
 struct TcHeader {       // 512 bytes at the start of the packed image

@@ -2,14 +2,14 @@
 //
 // Replaces MFCC.calc_mfcc, /root/reference/lnasr/mfcc.py:108-175 (see include/lnasr_b200.h).
 //
-// Pass A  (mfcc_frames_kernel): one warp owns one frame at a time and walks a contiguous run of
-//   frames.  pre-emphasis + framing + Hamming while loading (mfcc.py:63, utils.py:119-130, mfcc.py:138),
-//   512-point real FFT as a 256-point complex radix-4 Stockham FFT in shared memory (mfcc.py:141),
-//   power spectrum (mfcc.py:142), triangular mel filters as a banded product (mfcc.py:148; 453 non-zeros
-//   instead of a dense 257x40 GEMM), eps substitution + 20 log10 (mfcc.py:149-150), DCT-II ortho
-//   (mfcc.py:152), ln energy (mfcc.py:158-160).  Because the DCT is linear, the two per-utterance mean
-//   removals (mfcc.py:151,156) commute with it: pass A writes raw cepstra and accumulates per-utterance
-//   column sums in float64.
+// Pass A  (mfcc_frames_kernel): a half-warp (16 threads) owns one frame at a time; the two halves of a warp walk
+//   alternate frames of an 8-frame run.  Samples arrive by cp.async one frame ahead; pre-emphasis + framing + Hamming
+//   on the way into registers (mfcc.py:63, utils.py:119-130, mfcc.py:138); 512-point real FFT as a 256-point complex
+//   FFT done 16 x 16 in registers with one shared-memory transpose (mfcc.py:141); real-FFT split + power spectrum
+//   (mfcc.py:142); triangular mel filters as a banded float32 product (mfcc.py:148; 453 non-zeros instead of a dense
+//   257x40 GEMM); eps substitution + 20 log10 (mfcc.py:149-150); DCT-II ortho (mfcc.py:152); ln energy
+//   (mfcc.py:158-160).  Because the DCT is linear, the two per-utterance mean removals (mfcc.py:151,156) commute
+//   with it: pass A writes raw cepstra and accumulates per-utterance column sums in 32.32 fixed point.
 // Pass B  (mfcc_finalize_kernel): subtract the means (+1e-8 constants), delta / delta-delta with the
 //   reference's row-0 rule (mfcc.py:162-172) exchanged through warp shuffles, coalesced 39-float rows.
 //
@@ -28,7 +28,6 @@ constexpr int FRAMES_PER_RUN = 8;     // consecutive frames a warp walks (its tw
 constexpr int STEPS_PER_RUN = FRAMES_PER_RUN / 2;
 constexpr double COLSUM_SCALE = 4294967296.0;      // per-utterance column sums are 32.32 fixed point (|c| < 2^18, < 2^13 frames)
 constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
-constexpr int P_LD = 264;             // power spectrum of one frame (257 doubles), aliases the transpose buffer
 constexpr int MAX_SLOTS = MAX_MEL / 16;
 
 struct MfccDev {
