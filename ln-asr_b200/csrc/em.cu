@@ -559,7 +559,8 @@ em_stats_ab_kernel(FbArgs a, const double* __restrict__ beta, int64_t total_fram
     double* mu_s = acc_s + n_acc;
     double* logw_s = mu_s + NM * D;
     double* A_s = logw_s + NM;                            // [N][N]
-    double* occ_s = A_s + N * N;                          // [ES_TILE][NM]
+    double* occ_s = A_s + N * N;                          // [ES_TILE][NM], 16-byte aligned for the double2 loads below
+    occ_s += (occ_s - sm) & 1;
     double* x_s = occ_s + ES_TILE * NM;                   // [ES_TILE][D]
     double* al_s = x_s + ES_TILE * D;                     // [ES_TILE][N]      alpha[t]
     double* ub_s = al_s + ES_TILE * N;                    // [ES_TILE+1][N]    beta[t] (then b[t]+beta[t] for the xi pass)
@@ -625,21 +626,49 @@ em_stats_ab_kernel(FbArgs a, const double* __restrict__ beta, int64_t total_fram
         __syncthreads();
         // u[t,j] = b[t,j] + beta[t,j] replaces beta in place (rows 0..nt1-1); row tt+1 feeds xi[tt]
         for (int i = tid; i < nt1 * N; i += ES_THREADS) ub_s[i] += __ldg(a.b + t0 * N + i);
-        // sufficient statistics
-        for (int e = tid; e < NM * D; e += ES_THREADS) {
-            const int jm = e / D, d = e - jm * D;
-            double s1 = 0.0, s2 = 0.0;
-            const double m0 = mu_s[e];
-#pragma unroll 4
-            for (int tt = 0; tt < nt; ++tt) {
-                const double o = occ_s[tt * NM + jm];
-                const double x = x_s[tt * D + d];
-                const double df = x - m0;
-                s1 = fma(o, x, s1);
-                s2 = fma(o * df, df, s2);
+        // sufficient statistics: a work item = (4 consecutive Gaussians, one dim): the feature value is read once for four
+        // occupancies (two 16-byte loads when N*M is a multiple of 4), 1.25 shared-memory loads per 4 x 4 float64 operations
+        {
+            const int ngrp = (NM + 3) >> 2;
+            for (int w = tid; w < ngrp * D; w += ES_THREADS) {
+                const int g4 = w / D, d = w - g4 * D;
+                const int jm0 = g4 * 4;
+                const int cnt = min(4, NM - jm0);
+                double m0[4], s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) m0[q] = (q < cnt) ? mu_s[(jm0 + q) * D + d] : 0.0;
+                if ((NM & 3) == 0) {
+                    for (int tt = 0; tt < nt; ++tt) {
+                        const double x = x_s[tt * D + d];
+                        const double2 o01 = *reinterpret_cast<const double2*>(occ_s + tt * NM + jm0);
+                        const double2 o23 = *reinterpret_cast<const double2*>(occ_s + tt * NM + jm0 + 2);
+                        const double o[4] = {o01.x, o01.y, o23.x, o23.y};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double df = x - m0[q];
+                            s1[q] = fma(o[q], x, s1[q]);
+                            s2[q] = fma(o[q] * df, df, s2[q]);
+                        }
+                    }
+                } else {
+                    for (int tt = 0; tt < nt; ++tt) {
+                        const double x = x_s[tt * D + d];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double o = (q < cnt) ? occ_s[tt * NM + jm0 + q] : 0.0;
+                            const double df = x - m0[q];
+                            s1[q] = fma(o, x, s1[q]);
+                            s2[q] = fma(o * df, df, s2[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < cnt) {
+                        acc_s[NM + (jm0 + q) * D + d] += s1[q];
+                        acc_s[NM + NM * D + (jm0 + q) * D + d] += s2[q];
+                    }
             }
-            acc_s[NM + e] += s1;
-            acc_s[NM + NM * D + e] += s2;
         }
         for (int jm = tid; jm < NM; jm += ES_THREADS) {
             double s0 = 0.0;
@@ -674,7 +703,7 @@ em_stats_ab_kernel(FbArgs a, const double* __restrict__ beta, int64_t total_fram
 static int launch_stats_ab(const FbArgs& a, const double* beta, int64_t total_frames, cudaStream_t stream) {
     const int NM = a.N * a.M, N = a.N;
     const size_t dbl = 256 + 64 + (size_t)NM * (2 * a.D + 1) + (size_t)N * N + N + 2 + (size_t)NM * a.D + NM + (size_t)N * N +
-                       (size_t)ES_TILE * NM + (size_t)ES_TILE * a.D + (size_t)ES_TILE * N + (size_t)(ES_TILE + 1) * N + ES_TILE + ES_TILE / 2 + 2;
+                       (size_t)ES_TILE * NM + (size_t)ES_TILE * a.D + (size_t)ES_TILE * N + (size_t)(ES_TILE + 1) * N + ES_TILE + ES_TILE / 2 + 4;
     const size_t smem = dbl * sizeof(double);
     if (smem > 220 * 1024) {
         set_error("em_statistics: N=%d, N*M=%d at dim=%d needs %zu bytes of shared memory (> 220 KB); model too large", N, NM, a.D, smem);
