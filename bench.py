@@ -254,7 +254,10 @@ def run_ours(args):
         numa = bind_to_gpu_numa_node(local)           # before the pinned host buffers are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
+    if cfg["emission"] == "tc" and args.tc_format == "f16":
+        cfg["emission"] = "tc16"
+        cfg["desc"] = cfg["desc"].replace("TC emissions", "tensor-core emissions (2 FP16 slices)")
     models = make_models(args.workload)
     pipe = AcousticPipeline(MFCC(), ModelBank(models, emission=cfg["emission"]))
     # every rank owns its own shard of utterances (weak scaling: per-GPU batch fixed)
@@ -360,7 +363,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if cfg["emission"] == "exact" else "f64 MFCC + trellis / 3xTF32 emissions",
+            "dtype": "f64" if cfg["emission"] == "exact" else ("f64 MFCC + trellis / 3xTF32 emissions" if cfg["emission"] == "tc"
+                                                                else "f64 MFCC + trellis / 2xFP16-slice emissions (fp32 accumulate)"),
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + cfg["desc"], "utts_per_gpu": n_utt, "frames_per_gpu_step": frames,
                        "pcm_bytes_per_gpu_step": int(pcm_np.nbytes), "l2": "inputs larger than L2 (PCM + intermediates > 126 MB per step)",
@@ -486,7 +490,7 @@ def run_em(args):
 def launches_per_step(pipe, want_paths):
     """Kernels of liblnasr_b200.so launched by one device-resident step."""
     n = 3                                   # mfcc_run_index, mfcc_frames, mfcc_finalize
-    n += 2 if pipe.bank.emission == "tc" else 1          # gmm_tc_stage + gmm_tc | gmm_loglik_exact
+    n += 2 if pipe.bank.emission in ("tc", "tc16") else 1          # stage + contraction | gmm_loglik_exact
     n += 1                                  # trellis (N <= 32: backtrace fused into the kernel)
     if want_paths and pipe.bank.n > 32:
         n += 1                              # backtrace
@@ -598,6 +602,14 @@ def roofline_for(name, st, frames, cfg, models, hbm_peak, peaks, fp64):
                 "executed_frac": 3.04 * ach / peak,
                 "note": "peak = cuBLAS TF32 GEMM (8192^3, sustained) measured in this run; MEASURED_PEAKS.json has no TF32 figure. "
                         "achieved counts ALGORITHMIC flops; the kernel executes 3.04x that (3xTF32 error compensation)"}
+    if cfg["emission"] == "tc16":
+        ach = flops * frames / sec / 1e12         # executed = 3 products of FP16 slices, K padded to 80
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "algorithmic_flops_per_frame": flops, "executed_over_algorithmic": 3.04,
+                "executed_frac": 3.04 * ach / peak,
+                "note": "tcgen05 kind::f16 on two FP16 slices per operand; peak = sustained 16-bit dense GEMM of MEASURED_PEAKS.json "
+                        "(bf16; fp16 runs at the same rate). achieved counts ALGORITHMIC flops; the kernel executes 3.04x that"}
     ach = flops * frames / sec / 1e12
     peak = fp64["fp64_mma_tflops"]
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
@@ -614,6 +626,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tc-format", default="f16", choices=["f16", "tf32"],
+                    help="c4: operand slices of the tensor-core emission kernel (two FP16 slices, or 3xTF32)")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--e2e-uniform", action="store_true", help="equal utterance groups instead of tapered ones")
     ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams the utterance groups alternate between")

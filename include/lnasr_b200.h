@@ -135,6 +135,19 @@ int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t n_frames, 
                         int32_t n_states, int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* FP16-slice variant of the tensor-core path (csrc/gmm_tc16.cu): the same contraction with every operand split into two FP16
+ * slices (22 significant bits, like TF32 hi + lo) and tcgen05 kind::f16 -- K = 16 per instruction, half the MMA count.
+ * FP16 has no exponent range to spare, so `scale` [dim] (device, powers of two; NULL = 1) brings the centred features to
+ * |x'| <~ 32 and every Gaussian's weights carry their own power-of-two scale (undone in the epilogue).  Same workspace as
+ * lnasr_gmm_loglik_tc. */
+int lnasr_gmm_tc16_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes /*host out*/);
+int lnasr_gmm_pack_tc16(const double* logw, const double* mu, const double* var, int32_t n_states, int32_t n_mix,
+                        int32_t dim, const double* shift /*[dim] or NULL*/, const double* scale /*[dim] or NULL*/,
+                        void* packed, void* stream);
+int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed,
+                          int32_t n_states, int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* discrete emissions: HMM._map_b (lnasr/hmm.py:47-61): b[t, j] = B[j, obs[t]] */
 int lnasr_emit_gather(const double* logB /*[n_states, n_symbols]*/, const int32_t* obs /*[n_frames]*/,
                       int64_t n_frames, int32_t n_states, int32_t n_symbols, double* b_out /*[n_frames,n_states]*/,
@@ -190,7 +203,8 @@ int lnasr_argmax_rows(const double* score /*[n_rows,n_cols]*/, int32_t n_rows, i
 /* ================================ (3b) the decode path in one call ==============================
  * PCM -> MFCC (mfcc.py:108-175) -> emissions (gmmhmm.py:46-67) -> Viterbi (hmm.py:133-172) -> word = argmax over the bank's
  * models of max_j v[T-1,j], on one workspace and one stream: no allocation, no synchronisation.
- * gmm_kind 0: gmm_packed is the lnasr_gmm_pack_exact image (float64 emissions); 1: the lnasr_gmm_pack_tc image (float32).
+ * gmm_kind 0: gmm_packed is the lnasr_gmm_pack_exact image (float64 emissions); 1: the lnasr_gmm_pack_tc image (float32);
+ * 2: the lnasr_gmm_pack_tc16 image (float32).
  * n_mix / dim describe the Gaussians; the bank's n_models*N states are the GMM's states, model k owning [k*N,(k+1)*N). */
 typedef struct lnasr_recognizer {
     const lnasr_mfcc_tables* mfcc;   /* host struct of device pointers */

@@ -1,0 +1,494 @@
+// gmm_tc16.cu -- the tensor-core GMM contraction of gmm_tc.cu with FP16 operand slices instead of TF32.
+//
+// Same maths as gmm_tc.cu (GMMHMM._map_b, /root/reference/lnasr/gmmhmm.py:46-67; gaussian_multi_distribution_log,
+// /root/reference/lnasr/gmm.py:59-68):  [x^2 | x | 1] . [-1/(2 var) | mu/var | c]^T  with every operand
+// split v = hi + lo and  D = Al.Bh + Ah.Bl + Ah.Bh  accumulated in fp32 in TMEM.  TF32 and FP16 carry the SAME 11
+// significant bits, so hi + lo resolves 22 bits either way -- but tcgen05 kind::f16 consumes K = 16 per instruction
+// where kind::tf32 consumes K = 8: 15 MMAs per 128-frame tile instead of 30.  What FP16 lacks is exponent range, so the
+// operands are scaled by exact powers of two:
+//   * features: x' = (x - shift_d) * p_d, p_d chosen by the caller from the model so that |x'| stays within ~32
+//     (the weights absorb 1/p_d^2 and 1/p_d);
+//   * every accumulator column (= Gaussian) n: its 80 weights are multiplied by t_n = 2^k so that the largest is in
+//     [4096, 8192); the epilogue multiplies the accumulator by 1/t_n.
+// Small entries then lose nothing that matters: an FP16 slice pair resolves 2^-22 relative for normal numbers and 2^-25
+// absolute below, against column maxima of 2^12.  The per-state constant trick, the correction-first MMA order and the
+// TMEM epilogue are those of gmm_tc.cu.
+//
+// CTA = 17 warps, one CTA per SM: warps 8-11 produce the lo slice of A, 12-15 the hi slice (thread = frame row, straight
+// into the UMMA canonical K-major layout: core matrix = 8 rows x 16 bytes = 8 halves), warp 16 issues the MMAs, warps 0-7
+// run the epilogue.  Four ring slots of [128 x 80] halves: lo and hi each double-buffered over tiles.
+#include <algorithm>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace lnasr {
+
+constexpr uint32_t H_MAGIC = 0x4c4e4836u;    // "LNH6"
+constexpr int H_BM = 128;                     // frames per tile (UMMA M)
+constexpr int H_THREADS = 544;
+constexpr int H_MAX_DIM = 39;
+constexpr int H_KP = 80;                      // [x^2 (39) | x (39) | 1 | 0]
+constexpr int H_XT_D = 40;
+constexpr int H_SMEM_LIMIT = 227 * 1024;
+constexpr float H_LN2 = 0.6931471805599453f;
+
+struct H16Header {      // 1024 bytes at the start of the packed image
+    uint32_t magic;
+    int32_t n_states, n_mix, Mp, dim, Kp, SPT, NT, n_wtiles;
+    int32_t pad[7];
+    float shift[64];
+    float scale[64];
+    uint8_t reserved[1024 - 16 * 4 - 2 * 64 * 4];
+};
+static_assert(sizeof(H16Header) == 1024, "H16Header must be 1024 bytes");
+
+struct H16Geom { int Mp, SPT, NT, n_wtiles; size_t w_part, cst_bytes, tile_bytes, total_bytes, smem_bytes; };
+
+static bool h16_geometry(int n_states, int n_mix, int dim, H16Geom* g) {
+    if (n_states < 1 || n_mix < 1 || n_mix > 16 || dim < 1 || dim > H_MAX_DIM) return false;
+    int Mp = 1;
+    while (Mp < n_mix) Mp <<= 1;
+    const int gran = 16 / Mp;
+    const int ring = 4 * H_BM * H_KP * 2;
+    int nt_max = (H_SMEM_LIMIT - ring - 4096) / (2 * H_KP * 2 + 8);
+    nt_max = std::min(nt_max, 256) / 16 * 16;
+    const int spt_max = nt_max / Mp;
+    // states per W tile: one CTA per SM keeps one tile resident, frames are split over the CTAs left over; choose the tile
+    // width (down to half of the maximum) that leaves the fewest SMs idle -- 2000 states x 16 mixtures: 14 states = 143 tiles
+    // on 148 SMs rather than 16 states = 125 tiles
+    const int sms = sm_count();
+    int spt = spt_max;
+    double best = -1.0;
+    for (int cand = spt_max / gran * gran; cand >= std::max(gran, spt_max / 2); cand -= gran) {
+        if (cand > n_states && cand - gran >= n_states) continue;
+        const int nw = (n_states + cand - 1) / cand;
+        const int fsplit = std::max(1, sms / nw);
+        const int items = nw * fsplit;
+        const int waves = (items + sms - 1) / sms;
+        const double eff = (double)items / ((double)waves * sms) * (0.75 + 0.25 * cand / spt_max);   // mild preference for wide tiles
+        if (eff > best + 1e-9) { best = eff; spt = cand; }
+    }
+    spt = std::min(spt, (n_states + gran - 1) / gran * gran);
+    g->Mp = Mp; g->SPT = spt; g->NT = spt * Mp;
+    g->n_wtiles = (n_states + spt - 1) / spt;
+    g->w_part = (size_t)g->NT * H_KP * 2;
+    g->cst_bytes = (size_t)((g->SPT * 4 + 15) / 16 * 16);
+    g->tile_bytes = 2 * g->w_part + 2 * g->cst_bytes;                       // W hi | W lo | per-state constant | per-state 1 / t
+    g->total_bytes = sizeof(H16Header) + g->tile_bytes * g->n_wtiles;
+    g->smem_bytes = g->tile_bytes + ring + 1024;
+    return true;
+}
+
+// byte offset of element (row n, k) inside one K-major no-swizzle image of `rows` x K halves:
+// core matrix = 8 rows x 16 bytes (8 halves); [n/8][k/8][n%8][k%8] -> LBO (next K chunk) = 128 B, SBO (next 8 rows) = (K/8)*128 B
+__host__ __device__ inline uint32_t kmajor16_off(int n, int k, int K) {
+    return (uint32_t)(((n >> 3) * (K >> 3) + (k >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+// instruction descriptor for kind::f16: fp32 accumulate, A and B FP16, both K-major
+__host__ __device__ inline uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// one thread per accumulator column (Gaussian): 80 weights in base 2 with the feature scales folded in, the column scale,
+// the hi / lo FP16 slices
+__global__ void gmm_pack_tc16_kernel(const double* __restrict__ logw, const double* __restrict__ mu, const double* __restrict__ var,
+                                     int n_states, int n_mix, int dim, const double* __restrict__ shift,
+                                     const double* __restrict__ scale, H16Geom g, uint8_t* __restrict__ packed) {
+    const int64_t cols_total = (int64_t)g.n_wtiles * g.NT;
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col == 0) {
+        H16Header* h = reinterpret_cast<H16Header*>(packed);
+        h->magic = H_MAGIC; h->n_states = n_states; h->n_mix = n_mix; h->Mp = g.Mp; h->dim = dim; h->Kp = H_KP;
+        h->SPT = g.SPT; h->NT = g.NT; h->n_wtiles = g.n_wtiles;
+        for (int d = 0; d < 64; ++d) {
+            h->shift[d] = (shift && d < dim) ? (float)shift[d] : 0.f;
+            h->scale[d] = (scale && d < dim) ? (float)scale[d] : 1.f;
+        }
+    }
+    if (col >= cols_total) return;
+    const int tile = (int)(col / g.NT), n = (int)(col - (int64_t)tile * g.NT);
+    const int j = tile * g.SPT + n / g.Mp, m = n % g.Mp;
+    constexpr double LOG2E = 1.4426950408889634;
+    // constant of Gaussian (j, mm) incl. log w, base 2 (about the shifted origin)
+    auto gconst = [&](int mm_) -> double {
+        const int64_t gi = (int64_t)j * n_mix + mm_;
+        double c = (double)dim * 1.8378770664093453;
+        for (int d = 0; d < dim; ++d) {
+            const double sh = shift ? shift[d] : 0.0;
+            const double dm = mu[gi * dim + d] - sh;
+            c += log(var[gi * dim + d]) + dm * dm / var[gi * dim + d];
+        }
+        c = (logw[gi] - 0.5 * c) * LOG2E;
+        return (c > -1e30) ? c : -1e30;               // log w = -inf
+    };
+    double cmax = -1e30;
+    if (j < n_states)
+        for (int mm_ = 0; mm_ < n_mix; ++mm_) cmax = fmax(cmax, gconst(mm_));
+    uint8_t* base = packed + sizeof(H16Header) + (size_t)tile * g.tile_bytes;
+    __half* w_hi = reinterpret_cast<__half*>(base);
+    __half* w_lo = reinterpret_cast<__half*>(base + g.w_part);
+    float* ctab = reinterpret_cast<float*>(base + 2 * g.w_part);
+    float* cs = reinterpret_cast<float*>(base + 2 * g.w_part + g.cst_bytes);
+    if (m == 0) ctab[n / g.Mp] = (float)cmax;
+    double crel = -1e30;
+    if (j < n_states && m < n_mix) {
+        const double c = gconst(m);
+        if (c > -1e30) crel = c - cmax;
+    }
+    auto put = [&](int k, double v) {
+        const __half hi = __float2half_rn((float)v);
+        const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+        const uint32_t off = kmajor16_off(n, k, H_KP) / 2;
+        w_hi[off] = hi;
+        w_lo[off] = lo;
+    };
+    auto state_exp = [](double mx_) -> int {
+        int e_ = 0;
+        if (mx_ > 0.0) {
+            frexp(mx_, &e_);                             // mx = f * 2^e, f in [0.5, 1)
+            e_ = 13 - e_;                                // mx * 2^e in [4096, 8192)
+        }
+        return max(-40, min(7, e_));
+    };
+    if (crel < -30000.0) {
+        // padding, log w = -inf, or a mixture 2^-30000 below the best of its state: -32768 / t <= -256, exp2 -> 0
+        for (int k = 0; k < H_KP; ++k) put(k, k == 2 * H_MAX_DIM ? -32768.0 : 0.0);
+        if (m == 0 && !(j < n_states)) cs[n / g.Mp] = 1.f;
+        if (m == 0 && j < n_states && !(cmax > -1e30)) cs[n / g.Mp] = 1.f;      // a state with no mass at all
+        if (!(m == 0 && j < n_states && cmax > -1e30)) return;
+        // mixture 0 of a live state is itself negligible: its thread still owes the state's scale (below)
+    }
+    const int64_t gi = (int64_t)j * n_mix + m;
+    auto weight = [&](int k) -> double {
+        if (k < H_MAX_DIM) {
+            if (k >= dim) return 0.0;
+            const double p = scale ? scale[k] : 1.0;
+            return -0.5 / var[gi * dim + k] * LOG2E / (p * p);
+        }
+        if (k < 2 * H_MAX_DIM) {
+            const int d = k - H_MAX_DIM;
+            if (d >= dim) return 0.0;
+            const double p = scale ? scale[d] : 1.0, sh = shift ? shift[d] : 0.0;
+            return (mu[gi * dim + d] - sh) / var[gi * dim + d] * LOG2E / p;
+        }
+        return (k == 2 * H_MAX_DIM) ? crel : 0.0;
+    };
+    // one power-of-two scale per STATE (the largest weight of any of its mixtures lands in [4096, 8192), capped at 2^7 so
+    // that the -32768 of a padded column still means "nothing" after the epilogue has undone the scale): the epilogue then
+    // folds 1/t into the exponent argument for free
+    double mx = 0.0;
+    for (int mm_ = 0; mm_ < n_mix; ++mm_) {
+        const double c = gconst(mm_);
+        if (!(c > -1e30) || c - cmax < -30000.0) continue;
+        const int64_t gq = (int64_t)j * n_mix + mm_;
+        mx = fmax(mx, fabs(c - cmax));
+        for (int d = 0; d < dim; ++d) {
+            const double p = scale ? scale[d] : 1.0, sh = shift ? shift[d] : 0.0;
+            mx = fmax(mx, fabs(0.5 / var[gq * dim + d] * LOG2E / (p * p)));
+            mx = fmax(mx, fabs((mu[gq * dim + d] - sh) / var[gq * dim + d] * LOG2E / p));
+        }
+    }
+    const int e = state_exp(mx);
+    const double t = ldexp(1.0, e);
+    if (!(crel < -30000.0))
+        for (int k = 0; k < H_KP; ++k) put(k, weight(k) * t);
+    if (m == 0) cs[n / g.Mp] = (float)ldexp(1.0, -e);
+}
+
+// xt[tile][d < 40][row < 128] = (feats[tile*128 + row][d] - shift[d]) * scale[d]   (0 beyond n_frames / dim)
+__global__ void __launch_bounds__(256) gmm_tc16_stage_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
+                                                             const uint8_t* __restrict__ packed, float* __restrict__ xt) {
+    __shared__ float tile[H_BM][H_XT_D + 1];
+    const H16Header* hdr = reinterpret_cast<const H16Header*>(packed);
+    const int64_t f0 = (int64_t)blockIdx.x * H_BM;
+    const int rows = (int)min((int64_t)H_BM, n_frames - f0);
+    for (int i = threadIdx.x; i < H_BM * H_XT_D; i += 256) {
+        const int r = i / H_XT_D, d = i - r * H_XT_D;
+        tile[r][d] = 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * dim; i += 256) {
+        const int r = i / dim, d = i - r * dim;
+        tile[r][d] = (__ldg(feats + (f0 + r) * ld_feats + d) - hdr->shift[d]) * hdr->scale[d];
+    }
+    __syncthreads();
+    float* dst = xt + (int64_t)blockIdx.x * H_XT_D * H_BM;
+    for (int i = threadIdx.x; i < H_XT_D * H_BM; i += 256) {
+        const int d = i / H_BM, r = i - d * H_BM;
+        dst[i] = tile[r][d];
+    }
+}
+
+struct H16Args {
+    const float* xt; int64_t n_frames;
+    const uint8_t* packed; float* b_out; int64_t ld_b;
+    int n_states, dim, Mp, SPT, NT, n_wtiles, n_fsplit;
+    int64_t frames_per_split;
+    uint32_t w_part, cst_bytes, tile_bytes;
+};
+
+__device__ __forceinline__ float h_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float h_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MP>
+__device__ __forceinline__ void h_lse_store(const float* v, const float* c_state, const float* q_state, float* out_row, int st_local0,
+                                            int st_global0, int st_end) {
+    // 16 accumulator columns = 16/MP states, MP mixtures each, base-2 domain, still multiplied by the state's scale t = 1/q
+#pragma unroll
+    for (int g = 0; g < 16 / MP; ++g) {
+        const float q = q_state[st_local0 + g];
+        float mx = v[g * MP];
+#pragma unroll
+        for (int i = 1; i < MP; ++i) mx = fmaxf(mx, v[g * MP + i]);
+        const float nm = -mx * q;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MP; ++i) s += h_ex2(fmaf(v[g * MP + i], q, nm));
+        const float r = ((h_lg2(s) - nm) + c_state[st_local0 + g]) * H_LN2;
+        if (st_global0 + g < st_end) out_row[st_global0 + g] = r;
+    }
+}
+
+constexpr int H_EPI_WARPS = 8, H_WARP_LO = 8, H_WARP_HI = 12, H_WARP_MMA = 16;
+
+__global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
+    extern __shared__ __align__(1024) uint8_t h_smem[];
+    const int NT = a.NT;
+    const uint32_t slot_bytes = H_BM * H_KP * 2;
+    uint8_t* s_w = h_smem;                        // [W hi | W lo | c_state | 1/t per state], the packed tile image verbatim
+    const float* s_c = reinterpret_cast<const float*>(h_smem + 2 * a.w_part);
+    const float* s_cs = reinterpret_cast<const float*>(h_smem + 2 * a.w_part + a.cst_bytes);
+    uint8_t* s_a = h_smem + ((a.tile_bytes + 127) & ~127u);     // 4 ring slots: lo (tile even / odd), hi (tile even / odd)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + 4 * slot_bytes);
+    uint64_t* a_full = bars;                      // [4] producers -> MMA
+    uint64_t* a_empty = bars + 4;                 // [4] MMA (commit) -> producers
+    uint64_t* t_full = bars + 8;                  // [2] MMA (commit) -> epilogue
+    uint64_t* t_empty = bars + 10;                // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, H_EPI_WARPS * 32); }
+        fence_barrier_init();
+    }
+    if (warp == H_WARP_MMA) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t idesc = make_idesc_f16(H_BM, NT);
+    constexpr uint32_t LBO = 128, SBO = (H_KP / 8) * 128;       // both operands: [rows/8][K/8][8][8 halves]
+
+    uint32_t tile_cnt = 0;      // tiles processed so far by this role (every role advances it identically)
+    int cur_wtile = -1;
+    const int n_items = a.n_wtiles * a.n_fsplit;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int wt = item % a.n_wtiles, fsp = item / a.n_wtiles;
+        const int64_t fs = (int64_t)fsp * a.frames_per_split;
+        const int64_t fe = min(a.n_frames, fs + a.frames_per_split);
+        if (fs >= fe) continue;
+        if (wt != cur_wtile) {
+            __syncthreads();
+            const uint4* src = reinterpret_cast<const uint4*>(a.packed + sizeof(H16Header) + (size_t)wt * a.tile_bytes);
+            uint4* dst = reinterpret_cast<uint4*>(s_w);
+            for (uint32_t i = tid; i < a.tile_bytes / 16; i += H_THREADS) dst[i] = __ldg(src + i);
+            fence_proxy_async();
+            __syncthreads();
+            cur_wtile = wt;
+        }
+        const int n_tiles = (int)((fe - fs + H_BM - 1) / H_BM);
+
+        if (warp >= H_WARP_LO && warp < H_WARP_MMA) {
+            // ===================== producers: thread = frame row; group 0 writes the lo slice, group 1 the hi slice
+            const bool hi_group = warp >= H_WARP_HI;
+            const int r = tid - (hi_group ? H_WARP_HI : H_WARP_LO) * 32;
+            const uint32_t row_off = (uint32_t)((r >> 3) * (H_KP >> 3) * 128 + (r & 7) * 16);
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t tc = tile_cnt + t;
+                const int64_t f = fs + (int64_t)t * H_BM + r;
+                float x[H_MAX_DIM];
+                const float* xr = a.xt + (f / H_BM) * (int64_t)(H_XT_D * H_BM) + r;
+#pragma unroll
+                for (int d = 0; d < H_MAX_DIM; ++d) x[d] = __ldg(xr + d * H_BM);
+                const int s = (hi_group ? 2 : 0) + (int)(tc & 1);
+                mbar_wait(a_empty + s, ((tc >> 1) & 1) ^ 1);
+                uint8_t* slot = s_a + s * slot_bytes + row_off;
+#pragma unroll
+                for (int cc = 0; cc < H_KP / 8; ++cc) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        float v[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int k = cc * 8 + 2 * e2 + h;                 // compile-time after unrolling
+                            // K axis: [x^2 (39) | x (39) | 1 | 0]; clamps keep wild outliers finite in FP16
+                            if (k < H_MAX_DIM) v[h] = fminf(x[k] * x[k], 60000.f);
+                            else if (k < 2 * H_MAX_DIM) v[h] = fminf(fmaxf(x[k - H_MAX_DIM], -60000.f), 60000.f);
+                            else v[h] = (k == 2 * H_MAX_DIM) ? 1.f : 0.f;
+                        }
+                        __half2 hi2 = __floats2half2_rn(v[0], v[1]);           // one F2FP for the pair
+                        if (!hi_group) {
+                            const float2 back = __half22float2(hi2);
+                            hi2 = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
+                        }
+                        pk[e2] = *reinterpret_cast<uint32_t*>(&hi2);
+                    }
+                    *reinterpret_cast<uint4*>(slot + cc * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                fence_proxy_async();
+                mbar_arrive(a_full + s);
+            }
+        } else if (warp == H_WARP_MMA) {
+            // ===================== MMA issuer: one thread
+            if (lane == 0) {
+                const uint32_t wh = smem_u32(s_w), wl = wh + a.w_part;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const uint32_t tc = tile_cnt + t;
+                    const uint32_t stage = tc & 1;
+                    mbar_wait(t_empty + stage, ((tc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + stage * (uint32_t)NT;
+                    const int s_lo = (int)(tc & 1), s_hi = 2 + (int)(tc & 1);
+                    uint32_t acc = 0;
+                    // corrections first (Al.Bh, Ah.Bl), the main product Ah.Bh last: fewer accumulations at full magnitude
+                    auto issue = [&](int s, uint32_t wbase) {
+                        const uint32_t sa = smem_u32(s_a + s * slot_bytes);
+                        for (int j = 0; j < H_KP / 16; ++j) {               // K = 16 per instruction = 2 core matrices
+                            umma_f16(d_tmem, make_smem_desc(sa + j * 2 * LBO, LBO, SBO, 0),
+                                     make_smem_desc(wbase + j * 2 * LBO, LBO, SBO, 0), idesc, acc);
+                            acc = 1;
+                        }
+                    };
+                    mbar_wait(a_full + s_lo, (tc >> 1) & 1);
+                    tc_fence_after();
+                    issue(s_lo, wh);                                    // Al . Bh
+                    umma_commit(a_empty + s_lo);
+                    mbar_wait(a_full + s_hi, (tc >> 1) & 1);
+                    tc_fence_after();
+                    issue(s_hi, wl);                                    // Ah . Bl
+                    issue(s_hi, wh);                                    // Ah . Bh
+                    umma_commit(a_empty + s_hi);
+                    umma_commit(t_full + stage);
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===================== epilogue: warps w and w+4 read TMEM lanes 32(w&3).. (= frame rows), half of the columns each
+            const int quad = warp & 3, chalf = warp >> 2;
+            const int row = quad * 32 + lane;
+            const int st_tile0 = wt * a.SPT;
+            const int st_end = min(a.n_states, st_tile0 + a.SPT);
+            const int n16 = NT / 16;
+            const int c16_begin = chalf ? (n16 + 1) / 2 : 0, c16_end = chalf ? n16 : (n16 + 1) / 2;
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t tc = tile_cnt + t;
+                const uint32_t stage = tc & 1;
+                mbar_wait(t_full + stage, (tc >> 1) & 1);
+                tc_fence_after();
+                const int64_t f = fs + (int64_t)t * H_BM + row;
+                float* out_row = a.b_out + f * a.ld_b;
+                const int se = (f < fe) ? st_end : 0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + stage * (uint32_t)NT;
+                for (int c16 = c16_begin; c16 < c16_end; ++c16) {
+                    float v[16];
+                    tmem_ld16(taddr + c16 * 16, v);
+                    const int sl0 = (c16 * 16) / a.Mp;
+                    switch (a.Mp) {
+                        case 16: h_lse_store<16>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
+                        case 8: h_lse_store<8>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
+                        case 4: h_lse_store<4>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
+                        case 2: h_lse_store<2>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
+                        default: h_lse_store<1>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(t_empty + stage);
+            }
+        }
+        tile_cnt += n_tiles;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == H_WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace lnasr
+
+using namespace lnasr;
+
+extern "C" int lnasr_gmm_tc16_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes) {
+    H16Geom g;
+    LNASR_CHECK_ARG(bytes, "gmm_tc16_packed_bytes: null pointer");
+    LNASR_CHECK_ARG(h16_geometry(n_states, n_mix, dim, &g), "gmm_tc16: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", H_MAX_DIM, n_mix, dim);
+    *bytes = g.total_bytes;
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_gmm_pack_tc16(const double* logw, const double* mu, const double* var, int32_t n_states, int32_t n_mix,
+                                   int32_t dim, const double* shift, const double* scale, void* packed, void* stream) {
+    H16Geom g;
+    LNASR_CHECK_ARG(logw && mu && var && packed, "gmm_pack_tc16: null pointer");
+    LNASR_CHECK_ARG(h16_geometry(n_states, n_mix, dim, &g), "gmm_tc16: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", H_MAX_DIM, n_mix, dim);
+    const int64_t n = (int64_t)g.n_wtiles * g.NT;
+    gmm_pack_tc16_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, shift, scale, g,
+                                                                                       (uint8_t*)packed);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed, int32_t n_states,
+                                     int32_t n_mix, int32_t dim, float* b_out, int64_t ld_b, void* workspace, size_t workspace_bytes,
+                                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    H16Geom g;
+    LNASR_CHECK_ARG(feats && packed && b_out, "gmm_loglik_tc16: null pointer");
+    LNASR_CHECK_ARG(h16_geometry(n_states, n_mix, dim, &g), "gmm_tc16: need n_mix <= 16 and dim <= %d (got n_mix=%d dim=%d)", H_MAX_DIM, n_mix, dim);
+    LNASR_CHECK_ARG(ld_feats >= dim && ld_b >= n_states, "gmm_loglik_tc16: bad leading dimensions");
+    if (n_frames == 0) return LNASR_OK;
+    size_t need = 0;
+    lnasr_gmm_tc_workspace_bytes(n_frames, &need);                      // same staging copy as the TF32 kernel
+    if (!workspace || workspace_bytes < need) {
+        set_error("gmm_loglik_tc16: workspace %zu < %zu bytes", workspace_bytes, need);
+        return LNASR_EWORKSPACE;
+    }
+    float* xt = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const int64_t frame_tiles = ceil_div(n_frames, H_BM);
+    gmm_tc16_stage_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, xt);
+    LNASR_LAUNCH_CHECK();
+    H16Args a{};
+    a.xt = xt; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
+    a.n_states = n_states; a.dim = dim; a.Mp = g.Mp; a.SPT = g.SPT; a.NT = g.NT; a.n_wtiles = g.n_wtiles;
+    a.w_part = (uint32_t)g.w_part; a.cst_bytes = (uint32_t)g.cst_bytes; a.tile_bytes = (uint32_t)g.tile_bytes;
+    const int sms = sm_count();
+    int n_fsplit = (int)std::max<int64_t>(1, std::min<int64_t>(frame_tiles, sms / std::max(1, g.n_wtiles)));
+    const int64_t tiles_per_split = ceil_div(frame_tiles, n_fsplit);
+    n_fsplit = (int)ceil_div(frame_tiles, tiles_per_split);
+    a.n_fsplit = n_fsplit;
+    a.frames_per_split = tiles_per_split * H_BM;
+    const int grid = std::min(sms, g.n_wtiles * n_fsplit);
+    const size_t smem = ((g.tile_bytes + 127) & ~(size_t)127) + 4 * (size_t)H_BM * H_KP * 2 + 1024;
+    LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_tc16_kernel<<<grid, H_THREADS, smem, stream>>>(a);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}

@@ -25,9 +25,9 @@ static int pipe_layout(int64_t total_frames, int32_t n_utt, const lnasr_recogniz
     int rc = lnasr_mfcc_workspace_bytes(total_frames, n_utt, &mw);
     if (rc) return rc;
     L->mfcc_ws = o; L->mfcc_ws_bytes = mw; o += up256(mw);
-    L->b = o; o += up256((size_t)total_frames * ncol * (r->gmm_kind == 1 ? sizeof(float) : sizeof(double)));
+    L->b = o; o += up256((size_t)total_frames * ncol * (r->gmm_kind >= 1 ? sizeof(float) : sizeof(double)));
     size_t gw = 0;
-    if (r->gmm_kind == 1) {
+    if (r->gmm_kind >= 1) {
         rc = lnasr_gmm_tc_workspace_bytes(total_frames, &gw);
         if (rc) return rc;
     }
@@ -41,7 +41,7 @@ static int pipe_layout(int64_t total_frames, int32_t n_utt, const lnasr_recogniz
 
 static int check_rec(const lnasr_recognizer* r, const char* who) {
     if (!r || !r->mfcc || !r->bank || !r->gmm_packed) { set_error("%s: null pointer in lnasr_recognizer", who); return LNASR_EINVAL; }
-    if (r->gmm_kind != 0 && r->gmm_kind != 1) { set_error("%s: gmm_kind must be 0 (exact) or 1 (tc)", who); return LNASR_EINVAL; }
+    if (r->gmm_kind < 0 || r->gmm_kind > 2) { set_error("%s: gmm_kind must be 0 (exact), 1 (tc) or 2 (tc16)", who); return LNASR_EINVAL; }
     if (r->dim != 3 * (r->mfcc->n_ceps + 1)) { set_error("%s: model dim %d != %d MFCC features", who, r->dim, 3 * (r->mfcc->n_ceps + 1)); return LNASR_EINVAL; }
     return LNASR_OK;
 }
@@ -84,12 +84,15 @@ extern "C" int lnasr_recognize_batch(const void* pcm, int pcm_dtype, const int64
     if (rec->gmm_kind == 1)
         rc = lnasr_gmm_loglik_tc(feats, ncf, total_frames, rec->gmm_packed, (int32_t)ncol, rec->n_mix, rec->dim, (float*)b, ncol,
                                  ws + L.gmm_ws, L.gmm_ws_bytes, stream);
+    else if (rec->gmm_kind == 2)
+        rc = lnasr_gmm_loglik_tc16(feats, ncf, total_frames, rec->gmm_packed, (int32_t)ncol, rec->n_mix, rec->dim, (float*)b, ncol,
+                                   ws + L.gmm_ws, L.gmm_ws_bytes, stream);
     else
         rc = lnasr_gmm_loglik_exact(feats, LNASR_DT_F32, ncf, total_frames, (const double*)rec->gmm_packed, (int32_t)ncol, rec->n_mix,
                                     rec->dim, b, LNASR_DT_F64, ncol, nullptr, stream);
     if (rc) return rc;
     double* scores = (double*)(ws + L.scores);
-    rc = lnasr_viterbi_batch(b, rec->gmm_kind == 1 ? LNASR_DT_F32 : LNASR_DT_F64, ncol, frame_offsets, n_utt, total_frames, rec->bank,
+    rc = lnasr_viterbi_batch(b, rec->gmm_kind >= 1 ? LNASR_DT_F32 : LNASR_DT_F64, ncol, frame_offsets, n_utt, total_frames, rec->bank,
                              paths_out, scores, nullptr, nullptr, paths_out ? ws + L.vit_ws : nullptr, L.vit_ws_bytes, stream);
     if (rc) return rc;
     return lnasr_argmax_rows(scores, n_utt, rec->bank->n_models, words_out, best_out, stream);

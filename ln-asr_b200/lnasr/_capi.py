@@ -62,6 +62,9 @@ SIGNATURES = {
     "lnasr_gmm_pack_tc": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "lnasr_gmm_tc_workspace_bytes": (C.c_int, [i64, C.POINTER(sz)]),
     "lnasr_gmm_loglik_tc": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, vp, i64, vp, sz, vp]),
+    "lnasr_gmm_tc16_packed_bytes": (C.c_int, [i32, i32, i32, C.POINTER(sz)]),
+    "lnasr_gmm_pack_tc16": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "lnasr_gmm_loglik_tc16": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, vp, i64, vp, sz, vp]),
     "lnasr_debug_set_umma_swap": (C.c_int, [C.c_int]),
     "lnasr_debug_set_gmm_simt": (C.c_int, [C.c_int]),
     "lnasr_debug_fp64_peak_scratch_doubles": (i64, []),

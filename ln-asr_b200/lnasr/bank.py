@@ -34,7 +34,8 @@ class ModelBank:
 
     def __init__(self, models: Sequence, emission: str = "auto"):
         """models: GMMHMM objects or dicts with keys A, pi, w, mu and si ([n,m,d,d]) or var ([n,m,d]).
-        emission: 'exact' (float64 SIMT), 'tc' (3xTF32 tensor cores) or 'auto' (tc when K*n*m >= 2048)."""
+        emission: 'exact' (float64, FP64 tensor cores), 'tc' (3xTF32 tcgen05), 'tc16' (two FP16 slices per operand, tcgen05
+        kind::f16: half the MMAs of 'tc') or 'auto' (tc when K*n*m >= 2048)."""
         def get(mdl, k):
             return mdl[k] if isinstance(mdl, dict) else getattr(mdl, k)
 
@@ -54,13 +55,14 @@ class ModelBank:
         self.gmm = PackedGmm(w, mu, cv)
         if emission == "auto":
             emission = "tc" if (self.K * self.n * self.m >= 2048 and not self.gmm.full) else "exact"
-        if emission not in ("exact", "tc"):
-            raise ValueError("emission must be 'exact', 'tc' or 'auto'")
+        if emission not in ("exact", "tc", "tc16"):
+            raise ValueError("emission must be 'exact', 'tc', 'tc16' or 'auto'")
         self.emission = emission
         self._tc = None
-        if emission == "tc":
+        if emission in ("tc", "tc16"):
             from .gmm_tc import PackedGmmTC
-            self._tc = PackedGmmTC(w, mu, cv if cv.ndim == 3 else np.diagonal(cv, axis1=2, axis2=3))
+            self._tc = PackedGmmTC(w, mu, cv if cv.ndim == 3 else np.diagonal(cv, axis1=2, axis2=3),
+                                   fmt="f16" if emission == "tc16" else "tf32")
 
     def emissions(self, feats, b_out=None):
         """feats [T, d] float32/float64 device -> b [T, K*n] (float64 exact / float32 tc)."""
@@ -225,7 +227,7 @@ class AcousticPipeline:
             tc = bank._tc is not None
             packed = bank._tc.packed if tc else bank.gmm.packed
             rec = _capi.Recognizer(mfcc=C.pointer(tb), bank=C.pointer(bank.trans.struct), gmm_packed=packed.data_ptr(),
-                                   gmm_kind=1 if tc else 0, n_mix=bank.m, dim=bank.d)
+                                   gmm_kind=(2 if bank._tc.fmt == "f16" else 1) if tc else 0, n_mix=bank.m, dim=bank.d)
             cache[dev] = (rec, tb, packed)
         return cache[dev][0]
 

@@ -79,13 +79,14 @@ def test_config2_full_size_properties():
     assert np.array_equal(w_h.numpy(), res.words.cpu().numpy()) and np.array_equal(b_h.numpy(), res.best.cpu().numpy())
 
 
-def test_config4_shape_properties():
+@pytest.mark.parametrize("emission", ["tc", "tc16"])
+def test_config4_shape_properties(emission):
     import torch
     import bench
     from lnasr.bank import AcousticPipeline, ModelBank
     from lnasr.mfcc import MFCC
     models = bench.make_models("c4")
-    pipe = AcousticPipeline(MFCC(), ModelBank(models, emission="tc"))
+    pipe = AcousticPipeline(MFCC(), ModelBank(models, emission=emission))
     pcm, off = bench.synth_batch(78, 48, 40000, 48000)
     res, mb = pipe.recognize_batch(pcm, off, want_paths=True, want_logprob=True)
     N = pipe.bank.n

@@ -51,9 +51,10 @@ def test_umma_descriptor_convention():
     assert err_doc < 1e-4, f"documented LBO/SBO convention is wrong on this hardware (swapped err {err_sw:.3e})"
 
 
+@pytest.mark.parametrize("fmt", ["tf32", "f16"])
 @pytest.mark.parametrize("n,mix,d,T", [(14, 16, 39, 128), (30, 16, 39, 1000), (200, 16, 39, 777), (64, 4, 13, 300),
                                        (100, 8, 39, 129), (33, 3, 20, 260)])
-def test_gmm_tc_matches_oracle(n, mix, d, T):
+def test_gmm_tc_matches_oracle(n, mix, d, T, fmt):
     import torch
     from lnasr.gmm_tc import PackedGmmTC
     from oracle import lnasr_oracle as O
@@ -61,12 +62,12 @@ def test_gmm_tc_matches_oracle(n, mix, d, T):
     mdl = O.random_gmmhmm(n, mix, d, rng)
     x = (0.5 * rng.standard_normal((T, d))).astype(np.float32)
     b_ref, _ = O.map_b(x.astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
-    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"])
+    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], fmt=fmt)
     b = g.loglik(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
     got = b.cpu().numpy().T
     err = np.abs(got - b_ref)
-    print(f"tc n={n} m={mix} d={d} T={T}: max abs err {err.max():.3e}, max rel {np.max(err / np.abs(b_ref)):.3e}, "
+    print(f"tc {fmt} n={n} m={mix} d={d} T={T}: max abs err {err.max():.3e}, max rel {np.max(err / np.abs(b_ref)):.3e}, "
           f"mean signed err {np.mean(got - b_ref):+.3e}")
     assert np.max(err / np.abs(b_ref)) < 1e-4
     assert err.max() < 2e-4         # fp32-level: what the per-utterance 1e-3 log-probability budget needs
@@ -77,7 +78,8 @@ def test_gmm_tc_matches_oracle(n, mix, d, T):
     assert torch.equal(b, b2)
 
 
-def test_gmm_tc_large_feature_magnitudes_with_shift():
+@pytest.mark.parametrize("fmt", ["tf32", "f16"])
+def test_gmm_tc_large_feature_magnitudes_with_shift(fmt):
     """Real MFCC magnitudes (|x| ~ 100) need the centring shift to stay inside 1e-4 relative comfortably."""
     import torch
     from lnasr.gmm_tc import PackedGmmTC
@@ -89,12 +91,14 @@ def test_gmm_tc_large_feature_magnitudes_with_shift():
     mdl["mu"] = mdl["mu"] * 10 + centre
     x = (centre + 3.0 * rng.standard_normal((T, d))).astype(np.float32)
     b_ref, _ = O.map_b(x.astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
-    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], shift=centre)
+    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], shift=centre, fmt=fmt)
     b = g.loglik(torch.from_numpy(x).cuda()).cpu().numpy().T
+    print(f"tc {fmt} large magnitudes: max abs err {np.abs(b - b_ref).max():.3e}, max rel {np.max(np.abs(b - b_ref) / np.abs(b_ref)):.3e}")
     assert np.max(np.abs(b - b_ref) / np.abs(b_ref)) < 1e-4
 
 
-def test_bank_with_tc_emissions_decodes_like_oracle():
+@pytest.mark.parametrize("emission", ["tc", "tc16"])
+def test_bank_with_tc_emissions_decodes_like_oracle(emission):
     """Viterbi on tensor-core emissions: paths bit-exact, ties / fp32 near-ties aside."""
     import torch
     from lnasr.bank import ModelBank
@@ -107,7 +111,7 @@ def test_bank_with_tc_emissions_decodes_like_oracle():
     lens = [300, 150, 299]
     utts = [(0.5 * rng.standard_normal((T, 39))).astype(np.float32) for T in lens]
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    bank = ModelBank([mdl], emission="tc")
+    bank = ModelBank([mdl], emission=emission)
     res = bank.score(torch.from_numpy(np.concatenate(utts)).cuda(), torch.from_numpy(off).cuda(), 3, int(off[-1]),
                      want_paths=True, want_logprob=True)
     paths = res.paths.cpu().numpy()[0]
@@ -121,5 +125,5 @@ def test_bank_with_tc_emissions_decodes_like_oracle():
             lp_ref = O.lse(O.forward(mdl["pi"], mdl["A"], b)[-1])
             d_v = res.scores.cpu().numpy()[u, 0] - np.max(v[-1])
             d_lp = res.logprob.cpu().numpy()[u, 0] - lp_ref
-            print(f"tc utt T={lens[u]}: viterbi score err {d_v:+.3e}, log-prob err {d_lp:+.3e}")
+            print(f"{emission} utt T={lens[u]}: viterbi score err {d_v:+.3e}, log-prob err {d_lp:+.3e}")
             assert abs(d_v) < 1e-3 and abs(d_lp) < 1e-3              # BASELINE.json: 1e-3 absolute per utterance
