@@ -14,9 +14,10 @@
 // absolute below, against column maxima of 2^12.  The per-state constant trick, the correction-first MMA order and the
 // TMEM epilogue are those of gmm_tc.cu.
 //
-// CTA = 17 warps, one CTA per SM: warps 8-11 produce the lo slice of A, 12-15 the hi slice (thread = frame row, straight
-// into the UMMA canonical K-major layout: core matrix = 8 rows x 16 bytes = 8 halves), warp 16 issues the MMAs, warps 0-7
-// run the epilogue.  Four ring slots of [128 x 80] halves: lo and hi each double-buffered over tiles.
+// CTA = 21 warps, one CTA per SM: warps 12-15 produce the lo slice of A, 16-19 the hi slice (thread = frame row, straight
+// into the UMMA canonical K-major layout: core matrix = 8 rows x 16 bytes = 8 halves), warp 20 issues the MMAs, warps 0-11
+// run the epilogue (three per TMEM lane quadrant, a third of the columns each: with half the MMA time of the TF32 kernel the
+// exp2 / log2 epilogue is what has to be hidden).  Four ring slots of [128 x 80] halves: lo and hi each double-buffered over tiles.
 #include <algorithm>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -26,7 +27,7 @@ namespace lnasr {
 
 constexpr uint32_t H_MAGIC = 0x4c4e4836u;    // "LNH6"
 constexpr int H_BM = 128;                     // frames per tile (UMMA M)
-constexpr int H_THREADS = 544;
+constexpr int H_THREADS = 672;                // 12 epilogue + 4 lo-producer + 4 hi-producer + 1 MMA warp
 constexpr int H_MAX_DIM = 39;
 constexpr int H_KP = 80;                      // [x^2 (39) | x (39) | 1 | 0]
 constexpr int H_XT_D = 40;
@@ -266,7 +267,39 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
     }
 }
 
-constexpr int H_EPI_WARPS = 8, H_WARP_LO = 8, H_WARP_HI = 12, H_WARP_MMA = 16;
+template <int MP>
+__device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base, const float* s_c, const float* s_cs, int warp, int lane,
+                                           int wt, int64_t fs, int64_t fe, int n_tiles, uint32_t tile_cnt, uint64_t* t_full,
+                                           uint64_t* t_empty) {
+    const int NT = a.NT;
+    constexpr int PARTS = 3;                                 // H_EPI_WARPS / 4: epilogue warps per TMEM lane quadrant
+    const int quad = warp & 3, part = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int st_tile0 = wt * a.SPT;
+    const int st_end = min(a.n_states, st_tile0 + a.SPT);
+    const int n16 = NT / 16;
+    const int c16_begin = n16 * part / PARTS, c16_end = n16 * (part + 1) / PARTS;
+    for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t tc = tile_cnt + t;
+        const uint32_t stage = tc & 1;
+        mbar_wait(t_full + stage, (tc >> 1) & 1);
+        tc_fence_after();
+        const int64_t f = fs + (int64_t)t * H_BM + row;
+        float* out_row = a.b_out + f * a.ld_b;
+        const int se = (f < fe) ? st_end : 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + stage * (uint32_t)NT;
+        for (int c16 = c16_begin; c16 < c16_end; ++c16) {
+            float v[16];
+            tmem_ld16(taddr + c16 * 16, v);
+            const int sl0 = c16 * (16 / MP);
+            h_lse_store<MP>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se);
+        }
+        tc_fence_before();
+        mbar_arrive(t_empty + stage);
+    }
+}
+
+constexpr int H_EPI_WARPS = 12, H_WARP_LO = 12, H_WARP_HI = 16, H_WARP_MMA = 20;
 
 __global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
     extern __shared__ __align__(1024) uint8_t h_smem[];
@@ -328,7 +361,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
                 float x[H_MAX_DIM];
                 const float* xr = a.xt + (f / H_BM) * (int64_t)(H_XT_D * H_BM) + r;
 #pragma unroll
-                for (int d = 0; d < H_MAX_DIM; ++d) x[d] = __ldg(xr + d * H_BM);
+                for (int d = 0; d < H_MAX_DIM; ++d) x[d] = fminf(fmaxf(__ldg(xr + d * H_BM), -240.f), 240.f);   // x^2 stays finite in FP16
                 const int s = (hi_group ? 2 : 0) + (int)(tc & 1);
                 mbar_wait(a_empty + s, ((tc >> 1) & 1) ^ 1);
                 uint8_t* slot = s_a + s * slot_bytes + row_off;
@@ -341,9 +374,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int k = cc * 8 + 2 * e2 + h;                 // compile-time after unrolling
-                            // K axis: [x^2 (39) | x (39) | 1 | 0]; clamps keep wild outliers finite in FP16
-                            if (k < H_MAX_DIM) v[h] = fminf(x[k] * x[k], 60000.f);
-                            else if (k < 2 * H_MAX_DIM) v[h] = fminf(fmaxf(x[k - H_MAX_DIM], -60000.f), 60000.f);
+                            // K axis: [x^2 (39) | x (39) | 1 | 0]
+                            if (k < H_MAX_DIM) v[h] = x[k] * x[k];
+                            else if (k < 2 * H_MAX_DIM) v[h] = x[k - H_MAX_DIM];
                             else v[h] = (k == 2 * H_MAX_DIM) ? 1.f : 0.f;
                         }
                         __half2 hi2 = __floats2half2_rn(v[0], v[1]);           // one F2FP for the pair
@@ -394,35 +427,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
             __syncwarp();
         } else {
             // ===================== epilogue: warps w and w+4 read TMEM lanes 32(w&3).. (= frame rows), half of the columns each
-            const int quad = warp & 3, chalf = warp >> 2;
-            const int row = quad * 32 + lane;
-            const int st_tile0 = wt * a.SPT;
-            const int st_end = min(a.n_states, st_tile0 + a.SPT);
-            const int n16 = NT / 16;
-            const int c16_begin = chalf ? (n16 + 1) / 2 : 0, c16_end = chalf ? n16 : (n16 + 1) / 2;
-            for (int t = 0; t < n_tiles; ++t) {
-                const uint32_t tc = tile_cnt + t;
-                const uint32_t stage = tc & 1;
-                mbar_wait(t_full + stage, (tc >> 1) & 1);
-                tc_fence_after();
-                const int64_t f = fs + (int64_t)t * H_BM + row;
-                float* out_row = a.b_out + f * a.ld_b;
-                const int se = (f < fe) ? st_end : 0;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + stage * (uint32_t)NT;
-                for (int c16 = c16_begin; c16 < c16_end; ++c16) {
-                    float v[16];
-                    tmem_ld16(taddr + c16 * 16, v);
-                    const int sl0 = (c16 * 16) / a.Mp;
-                    switch (a.Mp) {
-                        case 16: h_lse_store<16>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
-                        case 8: h_lse_store<8>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
-                        case 4: h_lse_store<4>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
-                        case 2: h_lse_store<2>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
-                        default: h_lse_store<1>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se); break;
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(t_empty + stage);
+            switch (a.Mp) {
+                case 16: h_epilogue<16>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 8:  h_epilogue<8>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 4:  h_epilogue<4>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 2:  h_epilogue<2>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                default: h_epilogue<1>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
             }
         }
         tile_cnt += n_tiles;
