@@ -35,7 +35,7 @@ class ModelBank:
     def __init__(self, models: Sequence, emission: str = "auto"):
         """models: GMMHMM objects or dicts with keys A, pi, w, mu and si ([n,m,d,d]) or var ([n,m,d]).
         emission: 'exact' (float64, FP64 tensor cores), 'tc' (3xTF32 tcgen05), 'tc16' (two FP16 slices per operand, tcgen05
-        kind::f16: half the MMAs of 'tc') or 'auto' (tc when K*n*m >= 2048)."""
+        kind::f16: half the MMAs of 'tc') or 'auto' (tc16 when K*n*m >= 2048)."""
         def get(mdl, k):
             return mdl[k] if isinstance(mdl, dict) else getattr(mdl, k)
 
@@ -54,7 +54,7 @@ class ModelBank:
         self.trans = TransitionBank(A, pi)
         self.gmm = PackedGmm(w, mu, cv)
         if emission == "auto":
-            emission = "tc" if (self.K * self.n * self.m >= 2048 and not self.gmm.full) else "exact"
+            emission = "tc16" if (self.K * self.n * self.m >= 2048 and not self.gmm.full) else "exact"
         if emission not in ("exact", "tc", "tc16"):
             raise ValueError("emission must be 'exact', 'tc', 'tc16' or 'auto'")
         self.emission = emission
