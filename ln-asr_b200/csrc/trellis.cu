@@ -413,12 +413,38 @@ trellis_reg_kernel(TrellisArgs a) {
             val[i][d] = ok ? __ldg(eval + (int64_t)d * N + j) : neg_inf();
         }
     }
+    // Viterbi decode without the API-parity outputs (v, uint32 bt) is the hot case (config 4): running pointers instead of
+    // per-state 64-bit index arithmetic, no output tests inside the state loop
+    const bool lean = (MODE == MODE_VITERBI) && !a.full_out && !a.bt_out && a.bt_ws;
+    uint16_t* btp = lean ? a.bt_ws + f0 * ncol + cbase + threadIdx.x : nullptr;
     for (int s = 0; s < T; ++s) {
         asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");     // row s has landed (my copies) ...
         __syncthreads();                                                       // ... and everyone's; step s-1's column is complete
         issue_row(s + PF - 1);                                                 // its buffer was last read in step s-1
         const BT* er = erow + (size_t)(s % PF) * n_pad;
         const int64_t row = erow_of(s);
+        if (lean && s > 0) {
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                const int j = threadIdx.x + TG_THREADS * i;
+                if (j < N) {
+                    double best = prev[idx[i][0]] + val[i][0];
+                    int arg = idx[i][0];
+#pragma unroll
+                    for (int d = 1; d < TR_DEG; ++d) {
+                        const double c = prev[idx[i][d]] + val[i][d];
+                        if (c > best) { best = c; arg = idx[i][d]; }            // ascending predecessor index: first max
+                    }
+                    if (best == neg_inf()) arg = 0;                             // no finite predecessor: np.argmax gives 0
+                    next[j] = best + (double)er[j];
+                    btp[TG_THREADS * i] = (uint16_t)arg;
+                }
+            }
+            btp += ncol;
+            double* t = prev; prev = next; next = t;
+            continue;
+        }
+        if (lean) btp += ncol;                                                 // s == 0 goes through the general code below
 #pragma unroll
         for (int i = 0; i < SPT; ++i) {
             const int j = threadIdx.x + TG_THREADS * i;
