@@ -263,7 +263,8 @@ __device__ __forceinline__ void lse_store(const float* v, const float* c_state, 
     for (int g = 0; g < 16 / MP; ++g) {
         float mx = v[g * MP];
 #pragma unroll
-        for (int i = 1; i < MP; ++i) mx = fmaxf(mx, v[g * MP + i]);
+        for (int i = 1; i + 1 < MP; i += 2) mx = fmax3(mx, v[g * MP + i], v[g * MP + i + 1]);
+        if ((MP & 1) == 0 && MP > 1) mx = fmaxf(mx, v[g * MP + MP - 1]);
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MP; ++i) s += ex2_approx(v[g * MP + i] - mx);

@@ -257,7 +257,8 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
         const float q = q_state[st_local0 + g];
         float mx = v[g * MP];
 #pragma unroll
-        for (int i = 1; i < MP; ++i) mx = fmaxf(mx, v[g * MP + i]);
+        for (int i = 1; i + 1 < MP; i += 2) mx = fmax3(mx, v[g * MP + i], v[g * MP + i + 1]);
+        if ((MP & 1) == 0 && MP > 1) mx = fmaxf(mx, v[g * MP + MP - 1]);
         const float nm = -mx * q;
         float s = 0.f;
 #pragma unroll
