@@ -260,9 +260,24 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
         for (int i = 1; i + 1 < MP; i += 2) mx = fmax3(mx, v[g * MP + i], v[g * MP + i + 1]);
         if ((MP & 1) == 0 && MP > 1) mx = fmaxf(mx, v[g * MP + MP - 1]);
         const float nm = -mx * q;
-        float s = 0.f;
+        float s;
+        if (MP >= 2) {
+            // (v - mx) * q for two mixtures per FFMA2, the exponentials (MUFU, scalar) summed two per FADD2
+            const unsigned long long q2 = pack_f2(q, q), nm2 = pack_f2(nm, nm);
+            unsigned long long s2 = 0ull;
 #pragma unroll
-        for (int i = 0; i < MP; ++i) s += h_ex2(fmaf(v[g * MP + i], q, nm));
+            for (int i = 0; i < MP; i += 2) {
+                float a0, a1;
+                unpack_f2(ffma2(pack_f2(v[g * MP + i], v[g * MP + i + 1]), q2, nm2), a0, a1);
+                const unsigned long long e2 = pack_f2(h_ex2(a0), h_ex2(a1));
+                s2 = (i == 0) ? e2 : fadd2(s2, e2);
+            }
+            float s_lo, s_hi;
+            unpack_f2(s2, s_lo, s_hi);
+            s = s_lo + s_hi;
+        } else {
+            s = h_ex2(fmaf(v[g * MP], q, nm));
+        }
         const float r = ((h_lg2(s) - nm) + c_state[st_local0 + g]) * H_LN2;
         if (st_global0 + g < st_end) out_row[st_global0 + g] = r;
     }

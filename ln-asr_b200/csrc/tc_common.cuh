@@ -83,4 +83,25 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return r;
 }
 
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100): the log-sum-exp epilogues are bound by instruction issue, and everything
+// in them except the MUFU.EX2 itself comes in pairs
+__device__ __forceinline__ unsigned long long pack_f2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long p, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 }  // namespace lnasr
