@@ -251,6 +251,8 @@ __device__ __forceinline__ float h_lg2(float x) {
 template <int MP>
 __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state, const float* q_state, float* out_row, int st_local0,
                                             int st_global0, int st_end) {
+    // c_state / q_state: per-state constant and 1/t, indexed [st_local0 + g] (shared memory, or registers when the caller
+    // passes arrays already offset so that st_local0 == 0)
     // 16 accumulator columns = 16/MP states, MP mixtures each, base-2 domain, still multiplied by the state's scale t = 1/q
 #pragma unroll
     for (int g = 0; g < 16 / MP; ++g) {
@@ -295,6 +297,18 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
     const int st_end = min(a.n_states, st_tile0 + a.SPT);
     const int n16 = NT / 16;
     const int c16_begin = n16 * part / PARTS, c16_end = n16 * (part + 1) / PARTS;
+    constexpr int MAXC = 6;                                  // ceil(16 / PARTS): 16-column groups per epilogue warp (NT <= 256)
+    constexpr int SPC = (MP >= 8) ? 16 / MP : 1;             // states per 16-column group
+    float creg[MAXC * SPC], qreg[MAXC * SPC];
+    if (MP >= 8) {
+#pragma unroll
+        for (int i = 0; i < MAXC * SPC; ++i) {
+            const int sl = c16_begin * SPC + i;
+            const bool ok = sl < c16_end * SPC;
+            creg[i] = ok ? s_c[sl] : 0.f;
+            qreg[i] = ok ? s_cs[sl] : 1.f;
+        }
+    }
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t tc = tile_cnt + t;
         const uint32_t stage = tc & 1;
@@ -304,11 +318,25 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
         float* out_row = a.b_out + f * a.ld_b;
         const int se = (f < fe) ? st_end : 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + stage * (uint32_t)NT;
-        for (int c16 = c16_begin; c16 < c16_end; ++c16) {
-            float v[16];
-            tmem_ld16(taddr + c16 * 16, v);
-            const int sl0 = c16 * (16 / MP);
-            h_lse_store<MP>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se);
+        if (MP >= 8) {
+            // one or two states per 16 columns: their constants were lifted into registers before the tile loop
+#pragma unroll
+            for (int ci = 0; ci < MAXC; ++ci) {
+                const int c16 = c16_begin + ci;
+                if (c16 < c16_end) {
+                    float v[16];
+                    tmem_ld16(taddr + c16 * 16, v);
+                    const int sl0 = c16 * (16 / MP);
+                    h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), out_row, 0, st_tile0 + sl0, se);
+                }
+            }
+        } else {
+            for (int c16 = c16_begin; c16 < c16_end; ++c16) {
+                float v[16];
+                tmem_ld16(taddr + c16 * 16, v);
+                const int sl0 = c16 * (16 / MP);
+                h_lse_store<MP>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se);
+            }
         }
         tc_fence_before();
         mbar_arrive(t_empty + stage);
