@@ -102,3 +102,21 @@ def test_non_default_constructor_arguments_match_oracle(kw):
         assert_close(P, Pr, 1e-4, "power")
         assert_close(C, Cr, 1e-4, "cepstrum")
         assert_close(F, Fr, 1e-4, "features")
+
+
+def test_fuzz_lengths_and_alignments(mfcc):
+    """Many short utterances of arbitrary (odd and even) lengths packed back to back: every frame start alignment, the
+    zero-padded last frames and the row-0 delta rule, int16 and float32, against the oracle."""
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(2024)
+    lens = [401, 402, 559, 560, 561, 562, 720, 721] + [int(x) for x in rng.integers(401, 4000, size=56)]
+    sigs = [np.clip(np.round(4000.0 * rng.standard_normal(n)), -32767, 32767).astype(np.int16) for n in lens]
+    for as_float in (False, True):
+        batch = [s.astype(np.float32) * 0.5 for s in sigs] if as_float else sigs
+        res = mfcc.calc_mfcc_batch(batch)
+        feats = res.feats.double().cpu().numpy()
+        off = res.frame_offsets_host
+        assert list(np.diff(off)) == [O.num_frames(n) for n in lens]
+        for u, s in enumerate(batch):
+            _, _, F = O.mfcc(s.astype(np.float64))
+            assert_close(feats[off[u]:off[u + 1]], F, 1e-4, f"utt{u} len {lens[u]} float={as_float}")
