@@ -18,7 +18,7 @@ from . import _capi, _dev
 from ._trellis import TransitionBank
 from .gmm import PackedGmm
 
-__all__ = ["ModelBank", "AcousticPipeline", "BankResult"]
+__all__ = ["ModelBank", "AcousticPipeline", "BankResult", "PendingRecognition"]
 
 
 class BankResult(NamedTuple):
@@ -27,6 +27,22 @@ class BankResult(NamedTuple):
     scores: "object"                # [n_utt, K] float64 Viterbi scores max_j v[T-1,j]
     paths: Optional["object"]       # [K, total_frames] int32 state paths per model, or None
     logprob: Optional["object"]     # [n_utt, K] float64 forward log-probabilities, or None
+
+
+class PendingRecognition:
+    """Handle of an asynchronous `AcousticPipeline.submit_host`: `.result()` -> (words int32 [n], best float64 [n]) on the host."""
+
+    def __init__(self, words, best, event, keep):
+        self._words, self._best, self._event, self._keep = words, best, event, keep
+
+    def done(self) -> bool:
+        return self._event is None or self._event.query()
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event, self._keep = None, ()
+        return self._words, self._best
 
 
 class ModelBank:
@@ -101,7 +117,17 @@ class AcousticPipeline:
 
     def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 6, want_paths: bool = False,
                              n_compute_streams: int = 2, taper: bool = False, _timeline=None):
-        """End-to-end entry point for HOST audio: `pcm_host` is a pinned CPU tensor (int16 or float32) of concatenated
+        """Synchronous form of `submit_host`: (words int32 [n], best float64 [n]) as CPU tensors."""
+        return self.submit_host(pcm_host, sample_offsets, n_chunks=n_chunks, want_paths=want_paths,
+                                n_compute_streams=n_compute_streams, taper=taper, _timeline=_timeline).result()
+
+    def submit_host(self, pcm_host, sample_offsets, n_chunks: int = 6, want_paths: bool = False,
+                    n_compute_streams: int = 2, taper: bool = False, _timeline=None) -> "PendingRecognition":
+        """Asynchronous end-to-end entry point for HOST audio; returns a handle whose `.result()` waits for the words.
+        Consecutive submissions pipeline: the copies of batch i+1 start while the last groups of batch i are still being
+        decoded (a streaming server keeps two batches in flight).
+
+        End-to-end entry point for HOST audio: `pcm_host` is a pinned CPU tensor (int16 or float32) of concatenated
         utterances, `sample_offsets` [n+1] host.  The batch is cut into `n_chunks` groups of whole utterances.  All
         host->device copies are queued up front on a copy stream (one event per group), so the copy engine streams
         the PCM without waiting for the host; MFCC / GMM / Viterbi of group i (compute stream) start when its copy
@@ -111,7 +137,7 @@ class AcousticPipeline:
         off = np.asarray(sample_offsets, dtype=np.int64)
         n_utt = len(off) - 1
         if n_utt <= 0:
-            return t.empty((0,), dtype=t.int32), t.empty((0,), dtype=t.float64)
+            return PendingRecognition(t.empty((0,), dtype=t.int32), t.empty((0,), dtype=t.float64), None, ())
         n_chunks = max(1, min(n_chunks, n_utt))
         # group boundaries at utterance borders.  Tapered sizes (1, 3, 4, .., 4, 3, 1): copy and compute are nearly balanced,
         # so the time to the first result (first copy) and the tail after the last copy (last group's compute) are what is
@@ -209,12 +235,13 @@ class AcousticPipeline:
             out_b = t.empty((n_utt,), dtype=t.float64, pin_memory=True)
             out_w.copy_(words, non_blocking=True)
             out_b.copy_(best, non_blocking=True)
-        cur.wait_stream(comps[0])
+            done = t.cuda.Event()
+            done.record(comps[0])
         for cs in comps:
             for x in (pcm_dev, meta_dev, words, best):
                 x.record_stream(cs)
-        comps[0].synchronize()
-        return out_w, out_b
+        # the device buffers stay referenced by the handle until the result has been collected
+        return PendingRecognition(out_w, out_b, done, (pcm_dev, meta_dev, words, best, ws, paths, meta_host, pcm_host))
 
     def _recognizer_struct(self):
         """lnasr_recognizer for the current device (cached; keeps the referenced structs alive)."""

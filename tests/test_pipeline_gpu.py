@@ -129,3 +129,22 @@ def test_recognizer_isolated_words(tmp_path):
     ref = AcousticPipeline(MFCC(), ModelBank(models, emission="exact")).recognize(sigs)
     assert words == [list(files)[i] for i in ref]
     assert r.recognize(sigs[2]) == words[2]
+
+
+def test_submit_host_keeps_batches_in_flight():
+    """AcousticPipeline.submit_host: several batches queued before any result is collected; every handle returns what the
+    synchronous call returns for its batch."""
+    import torch
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+    rng = np.random.default_rng(33)
+    pipe = AcousticPipeline(MFCC(), ModelBank(_models(rng, 5, 5, 4), emission="exact"))
+    batches = []
+    for _ in range(4):
+        pcm, off, _ = _batch(rng, [int(x) for x in rng.integers(3000, 15000, size=29)])
+        batches.append((torch.from_numpy(pcm).pin_memory(), off))
+    ref = [pipe.recognize_batch_host(p, o, n_chunks=3) for p, o in batches]
+    handles = [pipe.submit_host(p, o, n_chunks=5, want_paths=True) for p, o in batches]       # all four in flight
+    for h, (w_ref, b_ref) in zip(reversed(handles), reversed(ref)):                         # collected out of order
+        w, b = h.result()
+        assert h.done() and np.array_equal(w.numpy(), w_ref.numpy()) and np.array_equal(b.numpy(), b_ref.numpy())
