@@ -494,7 +494,9 @@ extern "C" int lnasr_gmm_pack_tc(const double* logw, const double* mu, const dou
 
 extern "C" int lnasr_gmm_tc_workspace_bytes(int64_t n_frames, size_t* bytes) {
     LNASR_CHECK_ARG(bytes && n_frames >= 0, "gmm_tc_workspace_bytes: bad arguments");
-    *bytes = (size_t)ceil_div(n_frames, TC_BM) * TC_BM * TC_XT_D * sizeof(float) + 256;
+    // per 128-frame tile: the TF32 kernel stages 40 x 128 floats (20 480 B), the FP16-slice kernel its two operand images
+    // (2 x 128 x 80 halves = 40 960 B); one size serves both
+    *bytes = (size_t)ceil_div(n_frames, TC_BM) * TC_BM * TC_XT_D * sizeof(float) * 2 + 256;
     return LNASR_OK;
 }
 

@@ -27,12 +27,14 @@ namespace lnasr {
 
 constexpr uint32_t H_MAGIC = 0x4c4e4836u;    // "LNH6"
 constexpr int H_BM = 128;                     // frames per tile (UMMA M)
-constexpr int H_THREADS = 672;                // 12 epilogue + 4 lo-producer + 4 hi-producer + 1 MMA warp
 constexpr int H_MAX_DIM = 39;
 constexpr int H_KP = 80;                      // [x^2 (39) | x (39) | 1 | 0]
 constexpr int H_XT_D = 40;
 constexpr int H_SMEM_LIMIT = 227 * 1024;
 constexpr float H_LN2 = 0.6931471805599453f;
+// output staging of the epilogue (n_mix >= 8: at most 32 states per tile): two [128 frames][33] float buffers
+constexpr int H_OUT_LD = 33;
+constexpr int H_OUT_BYTES = 2 * H_BM * H_OUT_LD * 4;
 
 struct H16Header {      // 1024 bytes at the start of the packed image
     uint32_t magic;
@@ -52,23 +54,17 @@ static bool h16_geometry(int n_states, int n_mix, int dim, H16Geom* g) {
     while (Mp < n_mix) Mp <<= 1;
     const int gran = 16 / Mp;
     const int ring = 4 * H_BM * H_KP * 2;
-    int nt_max = (H_SMEM_LIMIT - ring - 4096) / (2 * H_KP * 2 + 8);
+    int nt_max = (H_SMEM_LIMIT - ring - 4096 - H_OUT_BYTES) / (2 * H_KP * 2 + 8);
     nt_max = std::min(nt_max, 256) / 16 * 16;
     const int spt_max = nt_max / Mp;
-    // states per W tile: one CTA per SM keeps one tile resident, frames are split over the CTAs left over; choose the tile
-    // width (down to half of the maximum) that leaves the fewest SMs idle -- 2000 states x 16 mixtures: 14 states = 143 tiles
-    // on 148 SMs rather than 16 states = 125 tiles
-    const int sms = sm_count();
-    int spt = spt_max;
-    double best = -1.0;
+    // states per W tile: the widest tile that does not add padded states (frames are split finely over the CTAs by the
+    // launcher, so the number of W tiles need not match the SM count).  2000 states x 16 mixtures: 16 states = 256
+    // accumulator columns = 125 tiles, and every tile row of the output is 64 aligned bytes = two whole sectors.
+    int spt = spt_max / gran * gran;
+    int64_t best = -1;
     for (int cand = spt_max / gran * gran; cand >= std::max(gran, spt_max / 2); cand -= gran) {
-        if (cand > n_states && cand - gran >= n_states) continue;
-        const int nw = (n_states + cand - 1) / cand;
-        const int fsplit = std::max(1, sms / nw);
-        const int items = nw * fsplit;
-        const int waves = (items + sms - 1) / sms;
-        const double eff = (double)items / ((double)waves * sms) * (0.75 + 0.25 * cand / spt_max);   // mild preference for wide tiles
-        if (eff > best + 1e-9) { best = eff; spt = cand; }
+        const int64_t cost = (int64_t)((n_states + cand - 1) / cand) * cand;      // states computed, padding included
+        if (best < 0 || cost < best) { best = cost; spt = cand; }
     }
     spt = std::min(spt, (n_states + gran - 1) / gran * gran);
     g->Mp = Mp; g->SPT = spt; g->NT = spt * Mp;
@@ -77,7 +73,7 @@ static bool h16_geometry(int n_states, int n_mix, int dim, H16Geom* g) {
     g->cst_bytes = (size_t)((g->SPT * 4 + 15) / 16 * 16);
     g->tile_bytes = 2 * g->w_part + 2 * g->cst_bytes;                       // W hi | W lo | per-state constant | per-state 1 / t
     g->total_bytes = sizeof(H16Header) + g->tile_bytes * g->n_wtiles;
-    g->smem_bytes = g->tile_bytes + ring + 1024;
+    g->smem_bytes = g->tile_bytes + ring + 1024 + H_OUT_BYTES;
     return true;
 }
 
@@ -205,9 +201,14 @@ __global__ void gmm_pack_tc16_kernel(const double* __restrict__ logw, const doub
     if (m == 0) cs[n / g.Mp] = (float)ldexp(1.0, -e);
 }
 
-// xt[tile][d < 40][row < 128] = (feats[tile*128 + row][d] - shift[d]) * scale[d]   (0 beyond n_frames / dim)
-__global__ void __launch_bounds__(256) gmm_tc16_stage_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
-                                                             const uint8_t* __restrict__ packed, float* __restrict__ xt) {
+// Feature staging, taken all the way to the MMA operand: x' = (x - shift) * scale, and per 128-frame tile the two FP16
+// slices of [x'^2 (39) | x' (39) | 1 | 0] in the UMMA canonical K-major layout ([row/8][k/8][row%8][k%8], 20 480 B each, lo
+// then hi), so that the contraction kernel fetches a tile with two bulk copies.  (The first version converted the tile
+// with eight producer warps inside every CTA -- each of the ~125 W-tile CTAs streams ALL frames, so the conversion was
+// repeated 125 times.)
+constexpr uint32_t H_SLOT_BYTES = H_BM * H_KP * 2;
+__global__ void __launch_bounds__(256) gmm_tc16_stage_ops_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
+                                                                 const uint8_t* __restrict__ packed, uint8_t* __restrict__ xa) {
     __shared__ float tile[H_BM][H_XT_D + 1];
     const H16Header* hdr = reinterpret_cast<const H16Header*>(packed);
     const int64_t f0 = (int64_t)blockIdx.x * H_BM;
@@ -219,22 +220,45 @@ __global__ void __launch_bounds__(256) gmm_tc16_stage_kernel(const float* __rest
     __syncthreads();
     for (int i = threadIdx.x; i < rows * dim; i += 256) {
         const int r = i / dim, d = i - r * dim;
-        tile[r][d] = (__ldg(feats + (f0 + r) * ld_feats + d) - hdr->shift[d]) * hdr->scale[d];
+        const float x = (__ldg(feats + (f0 + r) * ld_feats + d) - hdr->shift[d]) * hdr->scale[d];
+        tile[r][d] = fminf(fmaxf(x, -240.f), 240.f);                           // x^2 stays finite in FP16
     }
     __syncthreads();
-    float* dst = xt + (int64_t)blockIdx.x * H_XT_D * H_BM;
-    for (int i = threadIdx.x; i < H_XT_D * H_BM; i += 256) {
-        const int d = i / H_BM, r = i - d * H_BM;
-        dst[i] = tile[r][d];
+    uint4* lo = reinterpret_cast<uint4*>(xa + (size_t)blockIdx.x * 2 * H_SLOT_BYTES);
+    uint4* hi = lo + H_SLOT_BYTES / 16;
+    // 16-byte chunk j of an image = core-matrix row: [row/8][k/8][row%8] -> consecutive threads write consecutive chunks
+    for (int j = threadIdx.x; j < (int)(H_SLOT_BYTES / 16); j += 256) {
+        const int cc = (j >> 3) % (H_KP / 8), row = (j / (8 * (H_KP / 8))) * 8 + (j & 7);
+        uint32_t pl[4], ph[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+            float v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = cc * 8 + 2 * e2 + h;
+                if (k < H_MAX_DIM) { const float x = tile[row][k]; v[h] = x * x; }
+                else if (k < 2 * H_MAX_DIM) v[h] = tile[row][k - H_MAX_DIM];
+                else v[h] = (k == 2 * H_MAX_DIM) ? 1.f : 0.f;
+            }
+            const __half2 h2 = __floats2half2_rn(v[0], v[1]);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
+            ph[e2] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[e2] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        lo[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        hi[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     }
 }
 
 struct H16Args {
-    const float* xt; int64_t n_frames;
+    int64_t n_frames;
+    const uint8_t* xa;          // FP16 operand images of the features: per 128-frame tile [lo | hi]
     const uint8_t* packed; float* b_out; int64_t ld_b;
     int n_states, dim, Mp, SPT, NT, n_wtiles, n_fsplit;
     int64_t frames_per_split;
     uint32_t w_part, cst_bytes, tile_bytes;
+    int lg_spt;                 // smallest lg with (1 << lg) >= SPT (output write-out geometry)
 };
 
 __device__ __forceinline__ float h_ex2(float x) {
@@ -285,19 +309,19 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
     }
 }
 
-template <int MP>
-__device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base, const float* s_c, const float* s_cs, int warp, int lane,
-                                           int wt, int64_t fs, int64_t fe, int n_tiles, uint32_t tile_cnt, uint64_t* t_full,
-                                           uint64_t* t_empty) {
+template <int MP, int PARTS>
+__device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base, const float* s_c, const float* s_cs, float* s_out,
+                                           int warp, int lane, int wt, int64_t fs, int64_t fe, int n_tiles, uint32_t tile_cnt,
+                                           uint64_t* t_full, uint64_t* t_empty) {
     const int NT = a.NT;
-    constexpr int PARTS = 3;                                 // H_EPI_WARPS / 4: epilogue warps per TMEM lane quadrant
+    // PARTS = epilogue warps per TMEM lane quadrant: each takes 1/PARTS of the 16-column groups
     const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;
     const int st_tile0 = wt * a.SPT;
     const int st_end = min(a.n_states, st_tile0 + a.SPT);
     const int n16 = NT / 16;
     const int c16_begin = n16 * part / PARTS, c16_end = n16 * (part + 1) / PARTS;
-    constexpr int MAXC = 6;                                  // ceil(16 / PARTS): 16-column groups per epilogue warp (NT <= 256)
+    constexpr int MAXC = (16 + PARTS - 1) / PARTS;           // 16-column groups per epilogue warp (NT <= 256)
     constexpr int SPC = (MP >= 8) ? 16 / MP : 1;             // states per 16-column group
     float creg[MAXC * SPC], qreg[MAXC * SPC];
     if (MP >= 8) {
@@ -319,15 +343,25 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
         const int se = (f < fe) ? st_end : 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + stage * (uint32_t)NT;
         if (MP >= 8) {
-            // one or two states per 16 columns: their constants were lifted into registers before the tile loop
+            // one or two states per 16 columns: their constants were lifted into registers before the tile loop.  Results go
+            // to a shared-memory tile first: a thread owns a frame ROW, so storing straight to b_out would issue one 4-byte
+            // write per (frame, state) to rows 4 * ld_b bytes apart -- 750 M separate L2 write transactions per config-4
+            // batch, which bounded the whole kernel (6.8 ms with them, 4.4 ms without).
+            float* srow = s_out + (tc & 1) * (H_BM * H_OUT_LD) + row * H_OUT_LD;
+            // TMEM loads run one group ahead of the arithmetic (two register buffers)
+            uint32_t raw[2][16];
+            tmem_ld16_issue(taddr + c16_begin * 16, raw[0]);
 #pragma unroll
             for (int ci = 0; ci < MAXC; ++ci) {
                 const int c16 = c16_begin + ci;
                 if (c16 < c16_end) {
+                    tmem_ld_wait();
                     float v[16];
-                    tmem_ld16(taddr + c16 * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[ci & 1][i]);
+                    if (ci + 1 < MAXC && c16 + 1 < c16_end) tmem_ld16_issue(taddr + (c16 + 1) * 16, raw[(ci + 1) & 1]);
                     const int sl0 = c16 * (16 / MP);
-                    h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), out_row, 0, st_tile0 + sl0, se);
+                    h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, sl0, 1 << 30);
                 }
             }
         } else {
@@ -340,40 +374,101 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
         }
         tc_fence_before();
         mbar_arrive(t_empty + stage);
+        if (MP >= 8) {
+            // the warps of this row quadrant have staged tile t -> write it out with consecutive lanes on consecutive states of a frame
+            // (64 contiguous, aligned bytes per frame for 16 states: two whole sectors instead of 16 single-float writes).  The
+            // barrier joins only the PARTS warps that share a TMEM lane quadrant = the same 32 frame rows; the staging buffers
+            // alternate, so this one barrier per tile also protects the buffer's reuse two tiles later.
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(PARTS * 32) : "memory");
+            const float* sbuf = s_out + (tc & 1) * (H_BM * H_OUT_LD) + quad * 32 * H_OUT_LD;
+            const int spt_e = st_end - st_tile0;
+            const int64_t f0 = fs + (int64_t)t * H_BM + quad * 32;
+            const int rows = (int)max((int64_t)0, min((int64_t)32, fe - f0));
+            // one store instruction = 32 >> lg_spt frame rows x (1 << lg_spt) states; the rows of one instruction are
+            // (1 << lg_spt) apart so that their staging reads (row stride 33 words) fall into disjoint banks
+            const int lg = a.lg_spt, j = lane & ((1 << lg) - 1), rsub = (lane >> lg) << lg;
+            if (j < spt_e)
+                for (int q = part; q < (1 << lg); q += PARTS) {
+                    const int rr = q + rsub;
+                    if (rr < rows) a.b_out[(f0 + rr) * a.ld_b + st_tile0 + j] = sbuf[rr * H_OUT_LD + j];
+                }
+        }
     }
 }
 
-constexpr int H_EPI_WARPS = 12, H_WARP_LO = 12, H_WARP_HI = 16, H_WARP_MMA = 20;
+// the MMA issuer (one thread): per tile  D = Al.Bh + Ah.Bl + Ah.Bh  into TMEM stage (tile & 1)
+__device__ __forceinline__ void h_mma_role(const H16Args& a, int lane, uint32_t tmem_base, uint8_t* s_a, const uint8_t* s_w,
+                                           uint32_t slot_bytes, uint32_t idesc, int n_tiles, uint32_t tile_cnt, uint64_t* a_full,
+                                           uint64_t* a_empty, uint64_t* t_full, uint64_t* t_empty) {
+    const int NT = a.NT;
+    constexpr uint32_t LBO = 128, SBO = (H_KP / 8) * 128;       // both operands: [rows/8][K/8][8][8 halves]
+    if (lane == 0) {
+        const uint32_t wh = smem_u32(s_w), wl = wh + a.w_part;
+        for (int t = 0; t < n_tiles; ++t) {
+            const uint32_t tc = tile_cnt + t;
+            const uint32_t stage = tc & 1;
+            mbar_wait(t_empty + stage, ((tc >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + stage * (uint32_t)NT;
+            const int s_lo = (int)(tc & 1), s_hi = 2 + (int)(tc & 1);
+            uint32_t acc = 0;
+            // corrections first (Al.Bh, Ah.Bl), the main product Ah.Bh last: fewer accumulations at full magnitude
+            auto issue = [&](int s, uint32_t wbase) {
+                const uint32_t sa = smem_u32(s_a + s * slot_bytes);
+                for (int j = 0; j < H_KP / 16; ++j) {               // K = 16 per instruction = 2 core matrices
+                    umma_f16(d_tmem, make_smem_desc(sa + j * 2 * LBO, LBO, SBO, 0),
+                             make_smem_desc(wbase + j * 2 * LBO, LBO, SBO, 0), idesc, acc);
+                    acc = 1;
+                }
+            };
+            mbar_wait(a_full + s_lo, (tc >> 1) & 1);
+            tc_fence_after();
+            issue(s_lo, wh);                                    // Al . Bh
+            umma_commit(a_empty + s_lo);
+            mbar_wait(a_full + s_hi, (tc >> 1) & 1);
+            tc_fence_after();
+            issue(s_hi, wl);                                    // Ah . Bl
+            issue(s_hi, wh);                                    // Ah . Bh
+            umma_commit(a_empty + s_hi);
+            umma_commit(t_full + stage);
+        }
+    }
+}
 
-__global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
+// The contraction kernel.  The feature operand arrives ready-made (gmm_tc16_stage_ops_kernel) by two cp.async.bulk per tile
+// issued by ONE thread:
+// 16 epilogue warps (four per TMEM lane quadrant: a 256-column tile is 16 sixteen-column groups, four per warp), 1 copy
+// warp, 1 MMA warp -- and registers to spare for loading TMEM one group ahead of the exp2 / log2 arithmetic.
+constexpr int HB_EPI_WARPS = 16, HB_WARP_COPY = 16, HB_WARP_MMA = 17, HB_THREADS = 18 * 32;
+
+__global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
     extern __shared__ __align__(1024) uint8_t h_smem[];
     const int NT = a.NT;
-    const uint32_t slot_bytes = H_BM * H_KP * 2;
+    const uint32_t slot_bytes = H_SLOT_BYTES;
     uint8_t* s_w = h_smem;                        // [W hi | W lo | c_state | 1/t per state], the packed tile image verbatim
     const float* s_c = reinterpret_cast<const float*>(h_smem + 2 * a.w_part);
     const float* s_cs = reinterpret_cast<const float*>(h_smem + 2 * a.w_part + a.cst_bytes);
     uint8_t* s_a = h_smem + ((a.tile_bytes + 127) & ~127u);     // 4 ring slots: lo (tile even / odd), hi (tile even / odd)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + 4 * slot_bytes);
-    uint64_t* a_full = bars;                      // [4] producers -> MMA
-    uint64_t* a_empty = bars + 4;                 // [4] MMA (commit) -> producers
+    uint64_t* a_full = bars;                      // [4] bulk copy (transaction bytes) -> MMA
+    uint64_t* a_empty = bars + 4;                 // [4] MMA (commit) -> copy thread
     uint64_t* t_full = bars + 8;                  // [2] MMA (commit) -> epilogue
     uint64_t* t_empty = bars + 10;                // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* s_out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // epilogue output staging
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, H_EPI_WARPS * 32); }
+        for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, HB_EPI_WARPS * 32); }
         fence_barrier_init();
     }
-    if (warp == H_WARP_MMA) tmem_alloc(tmem_slot, 512);
+    if (warp == HB_WARP_MMA) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
     const uint32_t idesc = make_idesc_f16(H_BM, NT);
-    constexpr uint32_t LBO = 128, SBO = (H_KP / 8) * 128;       // both operands: [rows/8][K/8][8][8 halves]
 
     uint32_t tile_cnt = 0;      // tiles processed so far by this role (every role advances it identically)
     int cur_wtile = -1;
@@ -387,103 +482,49 @@ __global__ void __launch_bounds__(H_THREADS, 1) gmm_tc16_kernel(H16Args a) {
             __syncthreads();
             const uint4* src = reinterpret_cast<const uint4*>(a.packed + sizeof(H16Header) + (size_t)wt * a.tile_bytes);
             uint4* dst = reinterpret_cast<uint4*>(s_w);
-            for (uint32_t i = tid; i < a.tile_bytes / 16; i += H_THREADS) dst[i] = __ldg(src + i);
+            for (uint32_t i = tid; i < a.tile_bytes / 16; i += HB_THREADS) dst[i] = __ldg(src + i);
             fence_proxy_async();
             __syncthreads();
             cur_wtile = wt;
         }
         const int n_tiles = (int)((fe - fs + H_BM - 1) / H_BM);
 
-        if (warp >= H_WARP_LO && warp < H_WARP_MMA) {
-            // ===================== producers: thread = frame row; group 0 writes the lo slice, group 1 the hi slice
-            const bool hi_group = warp >= H_WARP_HI;
-            const int r = tid - (hi_group ? H_WARP_HI : H_WARP_LO) * 32;
-            const uint32_t row_off = (uint32_t)((r >> 3) * (H_KP >> 3) * 128 + (r & 7) * 16);
-            for (int t = 0; t < n_tiles; ++t) {
-                const uint32_t tc = tile_cnt + t;
-                const int64_t f = fs + (int64_t)t * H_BM + r;
-                float x[H_MAX_DIM];
-                const float* xr = a.xt + (f / H_BM) * (int64_t)(H_XT_D * H_BM) + r;
-#pragma unroll
-                for (int d = 0; d < H_MAX_DIM; ++d) x[d] = fminf(fmaxf(__ldg(xr + d * H_BM), -240.f), 240.f);   // x^2 stays finite in FP16
-                const int s = (hi_group ? 2 : 0) + (int)(tc & 1);
-                mbar_wait(a_empty + s, ((tc >> 1) & 1) ^ 1);
-                uint8_t* slot = s_a + s * slot_bytes + row_off;
-#pragma unroll
-                for (int cc = 0; cc < H_KP / 8; ++cc) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        float v[2];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int k = cc * 8 + 2 * e2 + h;                 // compile-time after unrolling
-                            // K axis: [x^2 (39) | x (39) | 1 | 0]
-                            if (k < H_MAX_DIM) v[h] = x[k] * x[k];
-                            else if (k < 2 * H_MAX_DIM) v[h] = x[k - H_MAX_DIM];
-                            else v[h] = (k == 2 * H_MAX_DIM) ? 1.f : 0.f;
-                        }
-                        __half2 hi2 = __floats2half2_rn(v[0], v[1]);           // one F2FP for the pair
-                        if (!hi_group) {
-                            const float2 back = __half22float2(hi2);
-                            hi2 = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
-                        }
-                        pk[e2] = *reinterpret_cast<uint32_t*>(&hi2);
-                    }
-                    *reinterpret_cast<uint4*>(slot + cc * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-                fence_proxy_async();
-                mbar_arrive(a_full + s);
-            }
-        } else if (warp == H_WARP_MMA) {
-            // ===================== MMA issuer: one thread
+        if (warp == HB_WARP_COPY) {
+            // ===================== copy thread: operand images of tile t -> ring slots (lo: tile parity, hi: 2 + parity)
             if (lane == 0) {
-                const uint32_t wh = smem_u32(s_w), wl = wh + a.w_part;
-                for (int t = 0; t < n_tiles; ++t) {
+                const uint8_t* src = a.xa + (size_t)(fs / H_BM) * 2 * slot_bytes;
+                for (int t = 0; t < n_tiles; ++t, src += 2 * slot_bytes) {
                     const uint32_t tc = tile_cnt + t;
-                    const uint32_t stage = tc & 1;
-                    mbar_wait(t_empty + stage, ((tc >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + stage * (uint32_t)NT;
-                    const int s_lo = (int)(tc & 1), s_hi = 2 + (int)(tc & 1);
-                    uint32_t acc = 0;
-                    // corrections first (Al.Bh, Ah.Bl), the main product Ah.Bh last: fewer accumulations at full magnitude
-                    auto issue = [&](int s, uint32_t wbase) {
-                        const uint32_t sa = smem_u32(s_a + s * slot_bytes);
-                        for (int j = 0; j < H_KP / 16; ++j) {               // K = 16 per instruction = 2 core matrices
-                            umma_f16(d_tmem, make_smem_desc(sa + j * 2 * LBO, LBO, SBO, 0),
-                                     make_smem_desc(wbase + j * 2 * LBO, LBO, SBO, 0), idesc, acc);
-                            acc = 1;
-                        }
-                    };
-                    mbar_wait(a_full + s_lo, (tc >> 1) & 1);
-                    tc_fence_after();
-                    issue(s_lo, wh);                                    // Al . Bh
-                    umma_commit(a_empty + s_lo);
-                    mbar_wait(a_full + s_hi, (tc >> 1) & 1);
-                    tc_fence_after();
-                    issue(s_hi, wl);                                    // Ah . Bl
-                    issue(s_hi, wh);                                    // Ah . Bh
-                    umma_commit(a_empty + s_hi);
-                    umma_commit(t_full + stage);
+                    const uint32_t par = ((tc >> 1) & 1) ^ 1;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int s = 2 * h + (int)(tc & 1);
+                        mbar_wait(a_empty + s, par);
+                        mbar_arrive_expect_tx(a_full + s, slot_bytes);
+                        bulk_g2s(s_a + s * slot_bytes, src + h * slot_bytes, slot_bytes, a_full + s);
+                    }
                 }
             }
             __syncwarp();
+        } else if (warp == HB_WARP_MMA) {
+            h_mma_role(a, lane, tmem_base, s_a, s_w, slot_bytes, idesc, n_tiles, tile_cnt, a_full, a_empty, t_full, t_empty);
+            __syncwarp();
         } else {
-            // ===================== epilogue: warps w and w+4 read TMEM lanes 32(w&3).. (= frame rows), half of the columns each
+            // ===================== epilogue: warp w reads TMEM lanes 32 (w & 3) .. (= frame rows), a quarter of the columns
+            constexpr int P = HB_EPI_WARPS / 4;
             switch (a.Mp) {
-                case 16: h_epilogue<16>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 8:  h_epilogue<8>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 4:  h_epilogue<4>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 2:  h_epilogue<2>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                default: h_epilogue<1>(a, tmem_base, s_c, s_cs, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 16: h_epilogue<16, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 8:  h_epilogue<8, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 4:  h_epilogue<4, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 2:  h_epilogue<2, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                default: h_epilogue<1, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
             }
         }
         tile_cnt += n_tiles;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == H_WARP_MMA) tmem_dealloc(tmem_base, 512);
+    if (warp == HB_WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace lnasr
@@ -525,24 +566,40 @@ extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64
         set_error("gmm_loglik_tc16: workspace %zu < %zu bytes", workspace_bytes, need);
         return LNASR_EWORKSPACE;
     }
-    float* xt = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const int64_t frame_tiles = ceil_div(n_frames, H_BM);
-    gmm_tc16_stage_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, xt);
+    gmm_tc16_stage_ops_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, ws);
     LNASR_LAUNCH_CHECK();
     H16Args a{};
-    a.xt = xt; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
+    a.xa = ws; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
     a.n_states = n_states; a.dim = dim; a.Mp = g.Mp; a.SPT = g.SPT; a.NT = g.NT; a.n_wtiles = g.n_wtiles;
     a.w_part = (uint32_t)g.w_part; a.cst_bytes = (uint32_t)g.cst_bytes; a.tile_bytes = (uint32_t)g.tile_bytes;
+    a.lg_spt = 0;
+    while ((1 << a.lg_spt) < g.SPT && a.lg_spt < 5) ++a.lg_spt;
     const int sms = sm_count();
-    int n_fsplit = (int)std::max<int64_t>(1, std::min<int64_t>(frame_tiles, sms / std::max(1, g.n_wtiles)));
+    // work items = (W tile, frame range), dealt round-robin to one CTA per SM: choose the number of frame ranges that fills
+    // the last round best, charging ~2 tiles per item for (re)loading the W tile
+    int n_fsplit = 1;
+    {
+        double best_eff = -1.0;
+        const int64_t max_f = std::min<int64_t>(frame_tiles, 4 * (int64_t)sms);
+        for (int64_t f = 1; f <= max_f; ++f) {
+            const int64_t per = ceil_div(frame_tiles, f);
+            const int64_t f_eff = ceil_div(frame_tiles, per);
+            const int64_t items = f_eff * g.n_wtiles;
+            const int64_t rounds = ceil_div(items, (int64_t)sms);
+            const double eff = (double)frame_tiles * g.n_wtiles / ((double)rounds * sms * (double)(per + 2));
+            if (eff > best_eff + 1e-9) { best_eff = eff; n_fsplit = (int)f_eff; }
+        }
+    }
     const int64_t tiles_per_split = ceil_div(frame_tiles, n_fsplit);
     n_fsplit = (int)ceil_div(frame_tiles, tiles_per_split);
     a.n_fsplit = n_fsplit;
     a.frames_per_split = tiles_per_split * H_BM;
     const int grid = std::min(sms, g.n_wtiles * n_fsplit);
-    const size_t smem = ((g.tile_bytes + 127) & ~(size_t)127) + 4 * (size_t)H_BM * H_KP * 2 + 1024;
+    const size_t smem = ((g.tile_bytes + 127) & ~(size_t)127) + 4 * (size_t)H_BM * H_KP * 2 + 1024 + H_OUT_BYTES;
     LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_tc16_kernel<<<grid, H_THREADS, smem, stream>>>(a);
+    gmm_tc16_kernel<<<grid, HB_THREADS, smem, stream>>>(a);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }

@@ -78,6 +78,29 @@ def test_gmm_tc_matches_oracle(n, mix, d, T, fmt):
     assert torch.equal(b, b2)
 
 
+@pytest.mark.parametrize("n,mix,d,T", [(200, 16, 39, 7777), (2000, 16, 39, 2100), (9, 1, 5, 1000), (70, 2, 39, 4000)])
+def test_gmm_tc16_many_tiles(n, mix, d, T):
+    """Several W tiles x several frame ranges per CTA (ring slots, TMEM stages and output staging wrap many times), at the
+    config-4 model size among others; also: two runs give identical bits."""
+    import torch
+    from lnasr.gmm_tc import PackedGmmTC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(n + mix + T)
+    mdl = O.random_gmmhmm(n, mix, d, rng)
+    x = (0.7 * rng.standard_normal((T, d))).astype(np.float32)
+    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], fmt="f16")
+    xd = torch.from_numpy(x).cuda()
+    b1 = g.loglik(xd).clone()
+    b2 = g.loglik(xd).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(b1, b2)
+    rows = rng.choice(T, size=min(T, 300), replace=False)          # the oracle on a sample of frames (it is slow at n = 2000)
+    b_ref, _ = O.map_b(x[rows].astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
+    got = b1[torch.from_numpy(rows).cuda()].cpu().numpy().T
+    err = np.abs(got - b_ref)
+    assert np.max(err / np.abs(b_ref)) < 1e-4 and err.max() < 2e-4
+
+
 @pytest.mark.parametrize("fmt", ["tf32", "f16"])
 def test_gmm_tc_large_feature_magnitudes_with_shift(fmt):
     """Real MFCC magnitudes (|x| ~ 100) need the centring shift to stay inside 1e-4 relative comfortably."""
