@@ -348,20 +348,30 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
             // write per (frame, state) to rows 4 * ld_b bytes apart -- 750 M separate L2 write transactions per config-4
             // batch, which bounded the whole kernel (6.8 ms with them, 4.4 ms without).
             float* srow = s_out + (tc & 1) * (H_BM * H_OUT_LD) + row * H_OUT_LD;
-            // TMEM loads run one group ahead of the arithmetic (two register buffers)
-            uint32_t raw[2][16];
-            tmem_ld16_issue(taddr + c16_begin * 16, raw[0]);
+            if (MAXC == 4 && c16_end - c16_begin == 4) {
+                // the usual case (256-column tile, four warps per quadrant): this warp's 64 columns in two TMEM loads
 #pragma unroll
-            for (int ci = 0; ci < MAXC; ++ci) {
-                const int c16 = c16_begin + ci;
-                if (c16 < c16_end) {
-                    tmem_ld_wait();
-                    float v[16];
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t raw[32];
+                    tmem_ld32(taddr + (c16_begin + 2 * hh) * 16, raw);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[ci & 1][i]);
-                    if (ci + 1 < MAXC && c16 + 1 < c16_end) tmem_ld16_issue(taddr + (c16 + 1) * 16, raw[(ci + 1) & 1]);
-                    const int sl0 = c16 * (16 / MP);
-                    h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, sl0, 1 << 30);
+                    for (int cj = 0; cj < 2; ++cj) {
+                        const int ci = 2 * hh + cj;
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[cj * 16 + i]);
+                        h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, (c16_begin + ci) * (16 / MP), 1 << 30);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < MAXC; ++ci) {
+                    const int c16 = c16_begin + ci;
+                    if (c16 < c16_end) {
+                        float v[16];
+                        tmem_ld16(taddr + c16 * 16, v);
+                        h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, c16 * (16 / MP), 1 << 30);
+                    }
                 }
             }
         } else {
@@ -438,7 +448,7 @@ __device__ __forceinline__ void h_mma_role(const H16Args& a, int lane, uint32_t 
 // The contraction kernel.  The feature operand arrives ready-made (gmm_tc16_stage_ops_kernel) by two cp.async.bulk per tile
 // issued by ONE thread:
 // 16 epilogue warps (four per TMEM lane quadrant: a 256-column tile is 16 sixteen-column groups, four per warp), 1 copy
-// warp, 1 MMA warp -- and registers to spare for loading TMEM one group ahead of the exp2 / log2 arithmetic.
+// warp, 1 MMA warp.  (18 warps are allocated as 20, so a thread has at most 96 registers.)
 constexpr int HB_EPI_WARPS = 16, HB_WARP_COPY = 16, HB_WARP_MMA = 17, HB_THREADS = 18 * 32;
 
 __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
