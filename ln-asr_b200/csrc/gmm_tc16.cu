@@ -397,11 +397,13 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
             // one store instruction = 32 >> lg_spt frame rows x (1 << lg_spt) states; the rows of one instruction are
             // (1 << lg_spt) apart so that their staging reads (row stride 33 words) fall into disjoint banks
             const int lg = a.lg_spt, j = lane & ((1 << lg) - 1), rsub = (lane >> lg) << lg;
-            if (j < spt_e)
-                for (int q = part; q < (1 << lg); q += PARTS) {
-                    const int rr = q + rsub;
-                    if (rr < rows) a.b_out[(f0 + rr) * a.ld_b + st_tile0 + j] = sbuf[rr * H_OUT_LD + j];
-                }
+            if (j < spt_e) {
+                float* op = a.b_out + (f0 + rsub + part) * a.ld_b + st_tile0 + j;       // running pointers: one add per store
+                const float* sp = sbuf + (rsub + part) * H_OUT_LD + j;
+                const int64_t ostep = (int64_t)PARTS * a.ld_b;
+                for (int rr = rsub + part; rr < rsub + (1 << lg); rr += PARTS, op += ostep, sp += PARTS * H_OUT_LD)
+                    if (rr < rows) *op = *sp;
+            }
         }
     }
 }
