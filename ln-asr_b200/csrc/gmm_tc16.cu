@@ -14,10 +14,12 @@
 // absolute below, against column maxima of 2^12.  The per-state constant trick, the correction-first MMA order and the
 // TMEM epilogue are those of gmm_tc.cu.
 //
-// CTA = 21 warps, one CTA per SM: warps 12-15 produce the lo slice of A, 16-19 the hi slice (thread = frame row, straight
-// into the UMMA canonical K-major layout: core matrix = 8 rows x 16 bytes = 8 halves), warp 20 issues the MMAs, warps 0-11
-// run the epilogue (three per TMEM lane quadrant, a third of the columns each: with half the MMA time of the TF32 kernel the
-// exp2 / log2 epilogue is what has to be hidden).  Four ring slots of [128 x 80] halves: lo and hi each double-buffered over tiles.
+// CTA = 18 warps, one CTA per SM, one W tile (up to 256 accumulator columns) resident in shared memory while the CTA
+// streams frame tiles through it: gmm_tc16_stage_ops_kernel has already written the feature operand of every 128-frame tile
+// as two FP16 images in the UMMA canonical K-major layout (core matrix = 8 rows x 16 bytes = 8 halves), so warp 16 (one
+// thread) fetches a tile with two cp.async.bulk into a ring of four [128 x 80]-half slots (lo and hi, each double-buffered
+// over tiles), warp 17 (one thread) issues the MMAs into one of two TMEM stages, and warps 0-15 run the epilogue (four per
+// TMEM lane quadrant, a quarter of the columns each) and write the results out through a shared-memory staging tile.
 #include <algorithm>
 #include <cuda_fp16.h>
 #include "common.cuh"
