@@ -162,8 +162,10 @@ int lnasr_emit_gather(const double* logB /*[n_states, n_symbols]*/, const int32_
  * lists of the FINITE entries (ELL layout, built once per model by lnasr_trans_pack).
  * All trellis state is float64; emissions b may be float32 (tc path) or float64 (exact path).
  */
-/* max number of finite entries in any column / row of any model -> device int32[2] {max_in, max_out} */
-int lnasr_trans_degree(const double* logA, int32_t n_models, int32_t N, int32_t* deg_out /*device [2]*/, void* stream);
+/* structure of the finite transitions of a bank -> device int32[4] {max_in, max_out, max(j - i), max(i - j)}: the largest
+ * number of finite entries in any column / row of any model, and the longest forward / backward jump of a finite
+ * transition i -> j (max(i - j) = 0 and max(j - i) <= 2: left-to-right band, lnasr_hmm_bank.band = 1 + max(j - i)) */
+int lnasr_trans_degree(const double* logA, int32_t n_models, int32_t N, int32_t* deg_out /*device [4]*/, void* stream);
 /* pred_idx/val: [n_models, max_in, N]  (k-th finite predecessor i of state j, ascending i; pad idx=0,val=-inf)
  * succ_idx/val: [n_models, max_out, N] (k-th finite successor j of state i) */
 int lnasr_trans_pack(const double* logA, int32_t n_models, int32_t N, int32_t max_in, int32_t max_out,
@@ -176,6 +178,9 @@ typedef struct lnasr_hmm_bank {
     int32_t max_in, max_out; /* 0 when the ELL arrays are absent (N <= 32) */
     const int32_t* pred_idx; const double* pred_val;
     const int32_t* succ_idx; const double* succ_val;
+    int32_t band;            /* 0: general; else 1 + the largest j - i over the finite transitions i -> j of a bank in which all
+                              * of them satisfy 0 <= j - i <= 2 (left-to-right: self, next, skip) -- lnasr_trans_degree reports
+                              * it; selects the register-resident banded Viterbi kernel */
 } lnasr_hmm_bank;
 
 size_t lnasr_viterbi_workspace_bytes(int64_t total_frames, int32_t n_utt, int32_t n_models, int32_t N);

@@ -31,13 +31,17 @@ __global__ void trans_degree_kernel(const double* __restrict__ logA, int n_model
     if (idx >= (int64_t)n_models * N) return;
     const int k = (int)(idx / N), s = (int)(idx % N);
     const double* A = logA + (int64_t)k * N * N;
-    int cin = 0, cout = 0;
+    int cin = 0, cout = 0, fwd = 0, back = 0;
     for (int i = 0; i < N; ++i) {
-        cin += (A[(int64_t)i * N + s] != neg_inf());
+        const bool in = A[(int64_t)i * N + s] != neg_inf();          // transition i -> s
+        cin += in;
         cout += (A[(int64_t)s * N + i] != neg_inf());
+        if (in) { fwd = max(fwd, s - i); back = max(back, i - s); }
     }
     atomicMax(deg + 0, cin);
     atomicMax(deg + 1, cout);
+    atomicMax(deg + 2, fwd);      // largest j - i of a finite transition i -> j (0 if none goes forward)
+    atomicMax(deg + 3, back);     // largest i - j (0 for a left-to-right model)
 }
 
 __global__ void trans_pack_kernel(const double* __restrict__ logA, int n_models, int N, int max_in, int max_out,
@@ -507,6 +511,136 @@ trellis_reg_kernel(TrellisArgs a) {
     trellis_terminate<MODE>(prev, N, a, p, red_v, red_i);
 }
 
+// Banded Viterbi for left-to-right models (every finite transition i -> j has 0 <= j - i <= 2: self loop, next, skip --
+// the usual topology of large acoustic models, bank->band != 0).  A thread owns SPT CONSECUTIVE states and keeps their
+// trellis values in registers across time steps; the only values it needs from elsewhere are the two states below its
+// range, which the neighbouring thread publishes through a double-buffered shared-memory halo.  Per step and thread that
+// is one 16-byte shared load + store instead of 4 x SPT scattered 8-byte loads, one 16-byte backpointer store instead of
+// SPT 2-byte ones, and one barrier.  Ties resolve as in hmm.py:160-164 (np.argmax: lowest predecessor index).
+template <int SPT, typename BT, int PF>
+__global__ void __launch_bounds__(TG_THREADS, 2)
+trellis_band_kernel(TrellisArgs a) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    const int N = a.N;
+    const int n_pad = (N + 3) & ~3;
+    double* col = (double*)tg_smem;                               // [N] the last column, for the termination
+    double2* halo = reinterpret_cast<double2*>(col + n_pad);       // [2][TG_THREADS]: (v[j0 + SPT - 2], v[j0 + SPT - 1]) of every thread
+    BT* erow = reinterpret_cast<BT*>(halo + 2 * TG_THREADS);       // [PF][n_pad]
+    __shared__ double red_v[TG_THREADS / 32];
+    __shared__ int red_i[TG_THREADS / 32];
+    const int64_t p = blockIdx.x;
+    const int u = (int)(p / a.n_models), k = (int)(p % a.n_models);
+    const int64_t f0 = __ldg(a.frame_off + u);
+    const int T = (int)(__ldg(a.frame_off + u + 1) - f0);
+    if (T == 0) return;
+    const int64_t ncol = (int64_t)a.n_models * N;
+    const int64_t cbase = (int64_t)k * N;
+    const BT* b = (const BT*)a.b;
+    const int tid = threadIdx.x, j0 = tid * SPT;
+    const bool vec16 = (((size_t)a.ld_b * sizeof(BT)) % 16 == 0) && (((size_t)cbase * sizeof(BT)) % 16 == 0) &&
+                       (((size_t)N * sizeof(BT)) % 16 == 0) && (((uintptr_t)b) % 16 == 0);
+    auto issue_row = [&](int s) {
+        if (s < T) {
+            const BT* src = b + (f0 + s) * a.ld_b + cbase;
+            BT* dst = erow + (size_t)(s % PF) * n_pad;
+            if (vec16) {
+                constexpr int EPV = 16 / (int)sizeof(BT);
+                for (int i = tid * EPV; i < N; i += TG_THREADS * EPV) tr_cp_async(dst + i, src + i, 16);
+            } else {
+                for (int i = tid; i < N; i += TG_THREADS) tr_cp_async(dst + i, src + i, (int)sizeof(BT));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < PF - 1; ++s) issue_row(s);
+    // transitions into my states by distance: w[i][d] = log A[j - d, j], from the ELL predecessor lists
+    double w[SPT][3];
+    {
+        const int deg = a.max_in;
+        const int* eidx = a.pred_idx + (int64_t)k * deg * N;
+        const double* eval = a.pred_val + (int64_t)k * deg * N;
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) {
+            w[i][0] = w[i][1] = w[i][2] = neg_inf();
+            const int j = j0 + i;
+            if (j < N)
+                for (int d = 0; d < deg; ++d) {
+                    const double val = __ldg(eval + (int64_t)d * N + j);
+                    const int dist = j - __ldg(eidx + (int64_t)d * N + j);
+                    if (val != neg_inf()) {
+                        if (dist == 0) w[i][0] = val;
+                        else if (dist == 1) w[i][1] = val;
+                        else w[i][2] = val;
+                    }
+                }
+        }
+    }
+    double v[SPT];
+    // backpointer row segment of this thread: SPT consecutive uint16 -- one 16-byte store when SPT = 8 and aligned
+    uint16_t* btp = a.bt_ws ? a.bt_ws + f0 * ncol + cbase + j0 : nullptr;
+    const bool bt_vec = (SPT == 8) && a.bt_ws && ((ncol * sizeof(uint16_t)) % 16 == 0) && ((cbase * sizeof(uint16_t)) % 16 == 0) &&
+                        (((uintptr_t)a.bt_ws) % 16 == 0) && (j0 + SPT <= N);
+    for (int s = 0; s < T; ++s) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");     // row s has landed (my copies) ...
+        __syncthreads();                                                       // ... and everyone's; the halo of step s-1 is complete
+        issue_row(s + PF - 1);                                                 // its buffer was last read in step s-1
+        const BT* er = erow + (size_t)(s % PF) * n_pad + j0;
+        double e[SPT];
+        if (j0 + SPT <= n_pad) {
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) e[i] = (double)er[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) e[i] = (j0 + i < N) ? (double)er[i] : 0.0;
+        }
+        uint32_t arg[SPT];
+        if (s == 0) {
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                v[i] = (j0 + i < N) ? __ldg(a.logpi + cbase + j0 + i) + e[i] : neg_inf();
+                arg[i] = 0;
+            }
+        } else {
+            const double2 h = (tid > 0) ? halo[((s - 1) & 1) * TG_THREADS + tid - 1] : make_double2(neg_inf(), neg_inf());
+            // descending i: v[i] is overwritten after the states above it have read it
+#pragma unroll
+            for (int i = SPT - 1; i >= 0; --i) {
+                const double p2 = (i >= 2) ? v[i - 2] : (i == 1 ? h.y : h.x);
+                const double p1 = (i >= 1) ? v[i - 1] : h.y;
+                double best = p2 + w[i][2];
+                int dist = 2;
+                const double c1 = p1 + w[i][1];
+                if (c1 > best) { best = c1; dist = 1; }
+                const double c0 = v[i] + w[i][0];
+                if (c0 > best) { best = c0; dist = 0; }
+                arg[i] = (best == neg_inf()) ? 0u : (uint32_t)(j0 + i - dist);  // no finite predecessor: np.argmax gives 0
+                v[i] = best + e[i];
+            }
+        }
+        halo[(s & 1) * TG_THREADS + tid] = make_double2(v[SPT - 2], v[SPT - 1]);
+        if (btp) {
+            if (bt_vec) {
+                uint4 pk;
+                pk.x = arg[0] | (arg[1] << 16); pk.y = arg[2] | (arg[3] << 16);
+                pk.z = arg[4] | (arg[5] << 16); pk.w = arg[6] | (arg[7] << 16);
+                *reinterpret_cast<uint4*>(btp) = pk;
+            } else {
+#pragma unroll
+                for (int i = 0; i < SPT; ++i)
+                    if (j0 + i < N) btp[i] = (uint16_t)arg[i];
+            }
+            btp += ncol;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < SPT; ++i)
+        if (j0 + i < N) col[j0 + i] = v[i];
+    __syncthreads();
+    trellis_terminate<MODE_VITERBI>(col, N, a, p, red_v, red_i);
+}
+
 template <typename BT, int MODE>
 __global__ void __launch_bounds__(TG_THREADS)
 trellis_general_kernel(TrellisArgs a) {
@@ -681,6 +815,19 @@ static int launch_reg(const TrellisArgs& a, cudaStream_t stream) {
     return LNASR_OK;
 }
 
+template <int SPT, typename BT>
+static int launch_band(const TrellisArgs& a, cudaStream_t stream) {
+    constexpr int PF = (sizeof(BT) == 4) ? 8 : 4;            // emission rows in flight
+    const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
+    const size_t n_pad = ((size_t)a.N + 3) & ~(size_t)3;
+    const size_t smem = n_pad * sizeof(double) + 2 * TG_THREADS * sizeof(double2) + (size_t)PF * n_pad * sizeof(BT);
+    if (smem > 48 * 1024)
+        LNASR_CUDA(cudaFuncSetAttribute(trellis_band_kernel<SPT, BT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trellis_band_kernel<SPT, BT, PF><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 template <int MODE>
 static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, cudaStream_t stream) {
     a.n_models = bank->n_models; a.N = bank->N; a.logA = bank->logA; a.logpi = bank->logpi;
@@ -691,6 +838,12 @@ static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, c
     const bool have = (MODE == MODE_BACKWARD) ? (a.succ_idx && a.succ_val && a.max_out > 0) : (a.pred_idx && a.pred_val && a.max_in > 0);
     if (!have) { set_error("trellis: N=%d > 32 needs the packed transition lists (lnasr_trans_pack)", a.N); return LNASR_EINVAL; }
     const int deg = (MODE == MODE_BACKWARD) ? a.max_out : a.max_in;
+    // left-to-right band (bank->band = 1 + the largest j - i of a finite transition i -> j, all within 0..2): the decode
+    // path proper -- Viterbi without the API-parity outputs -- keeps the trellis column in registers
+    if (MODE == MODE_VITERBI && bank->band >= 1 && bank->band <= 3 && !a.full_out && !a.bt_out && a.N <= 8 * TG_THREADS) {
+        if (a.N <= 4 * TG_THREADS) return f32 ? launch_band<4, float>(a, stream) : launch_band<4, double>(a, stream);
+        return f32 ? launch_band<8, float>(a, stream) : launch_band<8, double>(a, stream);
+    }
     if (deg <= TR_DEG && a.N <= 4 * TG_THREADS)
         return f32 ? launch_reg<4, float, MODE>(a, stream) : launch_reg<4, double, MODE>(a, stream);
     if (deg <= TR_DEG && a.N <= 8 * TG_THREADS)
@@ -715,7 +868,7 @@ using namespace lnasr;
 extern "C" int lnasr_trans_degree(const double* logA, int32_t n_models, int32_t N, int32_t* deg_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LNASR_CHECK_ARG(logA && deg_out && n_models >= 1 && N >= 1, "trans_degree: bad arguments");
-    LNASR_CUDA(cudaMemsetAsync(deg_out, 0, 2 * sizeof(int32_t), stream));
+    LNASR_CUDA(cudaMemsetAsync(deg_out, 0, 4 * sizeof(int32_t), stream));
     const int64_t n = (int64_t)n_models * N;
     trans_degree_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(logA, n_models, N, deg_out);
     LNASR_LAUNCH_CHECK();

@@ -35,7 +35,7 @@ class HmmBank(C.Structure):
     """lnasr_hmm_bank (include/lnasr_b200.h)."""
     _fields_ = [
         ("n_models", i32), ("N", i32), ("logA", vp), ("logpi", vp), ("max_in", i32), ("max_out", i32),
-        ("pred_idx", vp), ("pred_val", vp), ("succ_idx", vp), ("succ_val", vp),
+        ("pred_idx", vp), ("pred_val", vp), ("succ_idx", vp), ("succ_val", vp), ("band", i32),
     ]
 
 

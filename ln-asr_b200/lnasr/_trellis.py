@@ -28,12 +28,16 @@ class TransitionBank:
         self.logA = _dev.to_dev(logA, t.float64)
         self.logpi = _dev.to_dev(logpi, t.float64)
         self.max_in = self.max_out = 0
+        self.band = 0
         self.pred_idx = self.pred_val = self.succ_idx = self.succ_val = None
         if self.N > SMALL_N:
-            deg = _dev.zeros((2,), t.int32)
+            deg = _dev.zeros((4,), t.int32)
             _capi.check(lib.lnasr_trans_degree(_capi.ptr(self.logA), self.K, self.N, _capi.ptr(deg), _capi.stream_ptr()),
                         "trans_degree")
-            self.max_in, self.max_out = (max(1, int(v)) for v in deg.cpu().tolist())
+            d_in, d_out, fwd, back = (int(v) for v in deg.cpu().tolist())
+            self.max_in, self.max_out = max(1, d_in), max(1, d_out)
+            # left-to-right band (self loop, next, skip): the decode path keeps the trellis column in registers
+            self.band = 1 + fwd if (back == 0 and fwd <= 2) else 0
             self.pred_idx = _dev.empty((self.K, self.max_in, self.N), t.int32)
             self.pred_val = _dev.empty((self.K, self.max_in, self.N), t.float64)
             self.succ_idx = _dev.empty((self.K, self.max_out, self.N), t.int32)
@@ -48,7 +52,7 @@ class TransitionBank:
             pred_idx=0 if self.pred_idx is None else self.pred_idx.data_ptr(),
             pred_val=0 if self.pred_val is None else self.pred_val.data_ptr(),
             succ_idx=0 if self.succ_idx is None else self.succ_idx.data_ptr(),
-            succ_val=0 if self.succ_val is None else self.succ_val.data_ptr())
+            succ_val=0 if self.succ_val is None else self.succ_val.data_ptr(), band=self.band)
 
     @property
     def ncol(self):

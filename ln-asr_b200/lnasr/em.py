@@ -46,7 +46,7 @@ class EmTrainer:
         self.packed = _dev.empty((int(lib.lnasr_gmm_exact_packed_doubles(self.n, self.m, self.d)),), t.float64)
         self.acc = _dev.zeros((int(lib.lnasr_em_acc_doubles(self.n, self.m, self.d)),), t.float64)
         self._bank = _capi.HmmBank(n_models=1, N=self.n, logA=self.logA.data_ptr(), logpi=self.logpi.data_ptr(),
-                                   max_in=0, max_out=0, pred_idx=0, pred_val=0, succ_idx=0, succ_val=0)
+                                   max_in=0, max_out=0, pred_idx=0, pred_val=0, succ_idx=0, succ_val=0, band=0)
         self._x = None
 
     def load_batch(self, feats, frame_offsets):

@@ -114,6 +114,47 @@ def test_trellis_batch_against_oracle(n, ltr):
             assert_paths_equal_ties_aside(p32[sl], O.viterbi(pi, A, bb)[2], pi, A, bb, what=f"path32[{u}]")
 
 
+@pytest.mark.parametrize("n,skip", [(40, True), (250, False), (1030, True), (1100, True), (2000, True)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_banded_viterbi_large_n(n, skip, dtype):
+    """Left-to-right banks (self / next / skip transitions) take the register-resident banded kernel on the decode path
+    (paths + scores, no v / bt outputs): 4 and 8 states per thread, state counts that do not fill the last thread, both
+    emission dtypes, ragged lengths from 1 frame, an impossible emission, and an entry state other than 0."""
+    import torch
+    from lnasr._trellis import TransitionBank
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(7 * n + (1 if skip else 0))
+    mdl = O.random_gmmhmm(n, 1, 1, rng, left_to_right=True)
+    A = mdl["A"].copy()
+    if not skip:
+        for i in range(n - 2):
+            A[i, i + 2] = -np.inf
+    pi = np.full(n, -np.inf)
+    pi[0] = np.log(0.7)
+    pi[3] = np.log(0.3)
+    lens = [1, 2, 45, 9, 30]
+    bs = [(-5.0 * rng.random((n, T)) - 0.5).astype(dtype).astype(np.float64) for T in lens]
+    bs[2][rng.integers(0, n), 7] = -np.inf
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    b_cat = np.ascontiguousarray(np.concatenate([b.T for b in bs], axis=0)).astype(dtype)
+    bank = TransitionBank(A, pi)
+    assert bank.band == (3 if skip else 2)
+    off_d = torch.from_numpy(off).cuda()
+    total = int(off[-1])
+    r = bank.viterbi(torch.from_numpy(b_cat).cuda(), off_d, len(lens), total, want_path=True, want_score=True)
+    path = r["path"][0].cpu().numpy()
+    score = r["score"].cpu().numpy()
+    # the general kernel (API-parity outputs requested) must agree bit for bit on the scores
+    r_gen = bank.viterbi(torch.from_numpy(b_cat).cuda(), off_d, len(lens), total, want_path=True, want_score=True, want_v=True)
+    assert np.array_equal(score, r_gen["score"].cpu().numpy())
+    with np.errstate(all="ignore"):
+        for u, b in enumerate(bs):
+            sl = slice(off[u], off[u + 1])
+            v_ref, _, p_ref = O.viterbi(pi, A, b)
+            assert_paths_equal_ties_aside(path[sl], p_ref, pi, A, b, what=f"path[{u}]")
+            assert_close(score[u, 0], np.max(v_ref[-1]), 1e-12, f"score[{u}]")
+
+
 def test_exact_ties_take_lowest_index():
     """np.argmax semantics (hmm.py:166,169): uniform model, constant emissions -> every argmax is index 0."""
     from lnasr.hmm import HMM
