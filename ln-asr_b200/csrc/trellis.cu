@@ -4,14 +4,17 @@
 // Replaces, from /root/reference/lnasr/hmm.py: _forward (63-100), _backward (102-131), _viterbi (133-172),
 // calc_prob (268-274), decode (276-283).
 //
-// Two kernels, both persistent over the time axis of their utterance with the trellis column held
-// on chip in float64:
-//   * small  (N <= 32): a group of G=2^k lanes owns one (utterance, model) pair, lane = state; the
-//     predecessor column of log A lives in registers, the previous trellis column is exchanged with
-//     warp shuffles, max / log-sum-exp over predecessors are register loops.  32/G pairs per warp.
-//   * general (any N): one CTA per (utterance, model) pair, trellis column double-buffered in shared
-//     memory, transitions walked as ELL lists of the FINITE entries of log A (left-to-right
-//     topologies have 2-3 per state), one __syncthreads per frame.
+// Four kernels, all persistent over the time axis of their utterance with the trellis column held on chip in float64:
+//   * small   (N <= 32): a group of G lanes (G = N for N <= 8, else 16 / 32) owns one (utterance, model) pair, lane =
+//     state; the predecessor column of log A lives in registers, the previous trellis column is exchanged with warp
+//     shuffles, max / log-sum-exp over predecessors are register loops, the backtrace is fused.
+//   * band    (32 < N <= 2048, Viterbi decode of left-to-right banks: every finite transition i -> j has 0 <= j - i <= 2):
+//     one CTA per pair, a thread owns 4 or 8 CONSECUTIVE states with their values and transition weights in registers and
+//     gets the two values below its range through a shared-memory halo.
+//   * reg     (32 < N <= 2048, <= 4 finite predecessors / successors per state, any topology, all three recursions): one CTA
+//     per pair, the transition lists of a thread's states in registers, the column double-buffered in shared memory.
+//   * general (any N): as reg, with the ELL lists of the FINITE entries of log A read from memory.
+//   The last three read emission rows with cp.async several steps ahead and use one __syncthreads per frame.
 // Backpointers go to HBM as uint16 state indices; the backtrace (hmm.py:168-171) is a separate
 // one-thread-per-pair pointer chase so that it runs for all pairs concurrently.
 //
