@@ -5,17 +5,23 @@
 
 Metric (BASELINE.json): frames/sec through MFCC + GMM log-likelihood + Viterbi.  One "step" = one pass of the hot
 path over one batch of synthetic 16 kHz utterances with random-init GMM-HMMs:
-  c2 (default, BASELINE configs[1]): isolated-word models, 10 words x 5 states x 4 mixtures x 39 dims, 4096
-      utterances of 0.5-1.5 s per GPU; the word is the argmax over models of the Viterbi score.
-  c4 (BASELINE configs[3] shape): one 2000-state x 16-mixture x 39-dim left-to-right model, tensor-core emissions.
+  c4 (default; BASELINE configs[3], the configuration the north star's 1e8 frames/s target is quoted on): one
+      2000-state x 16-mixture x 39-dim left-to-right model, tensor-core emissions, 1250 utterances of 3 s per GPU (the
+      per-GPU shard of 10 000 utterances on 8 GPUs); the decode result is the Viterbi state path.
+  c2 (BASELINE configs[1]): isolated-word models, 10 words x 5 states x 4 mixtures x 39 dims, 4096 utterances of
+      0.5-1.5 s per GPU; the word is the argmax over models of the Viterbi score.
   c3 (BASELINE configs[2]): one Baum-Welch EM iteration, 3 states x 8 mixtures x 39 dims, 1000 utterances per GPU,
       accumulators all-reduced over NCCL (lnasr.em.EmTrainer).
+The default run measures c4 as the line's headline and adds short c2 and c3 measurements under "secondary" (same process
+group, same N; --no-secondary skips them).
 `value` is timed with the PCM already in HBM; `e2e` goes through the public API from pinned host buffers with the
-host->device copy and the device->host read of the decoded words inside the timed region.  Multi-GPU: one process
-per GPU (torchrun), utterances sharded by rank, no data-path collective ("weak" scaling: per-GPU batch fixed).
+host->device copy and the device->host read of the decode result (c4: state paths + scores; c2: words + scores) inside
+the timed region.  Multi-GPU: one process per GPU (torchrun), utterances sharded by rank, no data-path collective
+("weak" scaling: per-GPU batch fixed).
 
---impl reference times the CPU restatement of the reference algorithm (oracle/lnasr_oracle.py; the reference itself
-is pure Python/numpy and /root/reference does not exist on the GPU box) on all host cores, on a bounded sample.
+--impl reference times the UNMODIFIED reference (MFCC.calc_mfcc -> GMMHMM._viterbi(obs, True), staged by oracle/build_ref.py
+into oracle/_ref/lnasr_reference.zip, which travels to the GPU box) on all host cores, on a bounded sample of the same
+utterances; the numpy port (oracle/lnasr_oracle.py) is the fallback when the archive is absent (`kind` says which).
 """
 from __future__ import annotations
 
@@ -38,15 +44,20 @@ UNIT = "frames/s"
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-def synth_batch(seed: int, n_utt: int, min_s: int, max_s: int):
-    """SURVEY.md 8(d) synthetic audio: int16 = clip(round(3000 N(0,1)) + 2000 sin(2 pi f0 t)), f0 ~ U(80,400)."""
+def synth_batch(seed: int, n_utt: int, min_s: int, max_s: int, n_draw: int = None):
+    """SURVEY.md 8(d) synthetic audio: int16 = clip(round(3000 N(0,1)) + 2000 sin(2 pi f0 t)), f0 ~ U(80,400).
+    n_draw: size of the batch the lengths are drawn for (the first n_utt utterances of it are generated: the noise is drawn
+    per utterance from its own stream, so a prefix of a batch is identical to the start of the full batch)."""
     rng = np.random.default_rng(seed)
-    lens = rng.integers(min_s, max_s + 1, size=n_utt)
+    n_draw = n_draw or n_utt
+    lens = rng.integers(min_s, max_s + 1, size=n_draw)[:n_utt]
+    f0 = rng.uniform(80.0, 400.0, size=n_draw)[:n_utt]
     off = np.zeros(n_utt + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     total = int(off[-1])
-    pcm = np.round(3000.0 * rng.standard_normal(total, dtype=np.float32))
-    f0 = rng.uniform(80.0, 400.0, size=n_utt)
+    pcm = np.empty(total, dtype=np.float32)
+    for u in range(n_utt):
+        pcm[off[u]:off[u + 1]] = np.round(3000.0 * np.random.default_rng((seed, u)).standard_normal(int(lens[u]), dtype=np.float32))
     for u in range(n_utt):
         t = np.arange(lens[u], dtype=np.float32) / 16000.0
         pcm[off[u]:off[u + 1]] += 2000.0 * np.sin(2 * np.pi * f0[u] * t)
@@ -124,42 +135,105 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-_CPU_MODELS = None
+_CPU_MODELS = None          # built in the parent before the fork: the c4 model's full si is 390 MB, shared copy-on-write
+_CPU_REF = None
+_CPU_KIND = "port"
 
 
-def _cpu_init(workload):
-    """Per-worker set-up: single-threaded BLAS, models built once (not pickled with every job)."""
-    global _CPU_MODELS
-    os.environ["OMP_NUM_THREADS"] = "1"
+def _full_si(var):
+    """[n,m,d] variances -> the reference's [n,m,d,d] covariance array (diagonal)."""
+    n, m, d = var.shape
+    si = np.zeros((n, m, d, d))
+    idx = np.arange(d)
+    si[:, :, idx, idx] = var
+    return si
+
+
+def _cpu_prepare(workload):
+    """Decide which CPU implementation runs (the staged unmodified reference if its archive is there, else the numpy port)
+    and build the models once in the parent."""
+    global _CPU_MODELS, _CPU_KIND
+    from oracle import ref_loader
+    _CPU_KIND = "reference" if ref_loader.available() else "port"
     _CPU_MODELS = make_models(workload)
+    if _CPU_KIND == "reference":
+        for m in _CPU_MODELS:
+            m["si"] = _full_si(m["var"])
+
+
+def _cpu_init():
+    """Per-worker set-up (forked): single-threaded BLAS; the reference is imported as `lnasr` in the worker only."""
+    global _CPU_REF
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+    np.seterr(all="ignore")
+    if _CPU_KIND == "reference":
+        import warnings
+        warnings.filterwarnings("ignore")
+        from oracle import ref_loader
+        R = ref_loader.load()
+        mfcc = R["mfcc"].MFCC()
+        hmms = [R["gmmhmm"].GMMHMM(m["w"].shape[0], m["w"].shape[1], 39, A=m["A"], pi=m["pi"], w=m["w"], mu=m["mu"], si=m["si"])
+                for m in _CPU_MODELS]
+        _CPU_REF = (mfcc, hmms)
 
 
 def _cpu_worker(pcm):
-    """One utterance through the CPU restatement: MFCC -> emissions of every model -> Viterbi -> word."""
+    """One utterance through the CPU path: MFCC -> emissions of every model -> Viterbi -> best model / state path."""
+    if _CPU_KIND == "reference":
+        mfcc, hmms = _CPU_REF
+        F = mfcc.calc_mfcc(pcm)[2]                                  # mfcc.py:108-175
+        best = None
+        for g in hmms:
+            v, _, path = g._viterbi(F, True)                        # hmm.py:133-172 (what decode() runs, hmm.py:276-283)
+            sc = float(np.max(v[-1]))
+            if best is None or sc > best[0]:
+                best = (sc, path)
+        return F.shape[0]
     from oracle import lnasr_oracle as O
     _, _, F = O.mfcc(pcm)
     O.score_words_viterbi(F, _CPU_MODELS)
     return F.shape[0]
 
 
-def cpu_arm(workload: str, n_utt_sample: int, cores: int):
-    """Frames/s of the CPU port on `cores` single-threaded worker processes (faster than threaded BLAS on these
-    shapes)."""
-    import multiprocessing as mp
+def cpu_sample(workload: str, n_utt_sample: int):
+    """The first n utterances of rank 0's GPU batch (same seed, same lengths)."""
     cfg = WORKLOADS[workload]
-    if workload == "c4":
-        # N=2000: ~20 frames/s/core in the reference; bound the sample to short utterances
-        pcm, off = synth_batch(99, n_utt_sample, 2640, 2640)      # 15 frames each
-    else:
-        pcm, off = synth_batch(99, n_utt_sample, cfg["min_s"], cfg["max_s"])
-    jobs = [pcm[off[u]:off[u + 1]] for u in range(n_utt_sample)]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(workload,)) as pool:
-        pool.map(_cpu_worker, jobs[:2 * cores], chunksize=1)        # warm the workers (imports, first-call costs)
+    pcm, off = synth_batch(1000, n_utt_sample, cfg["min_s"], cfg["max_s"], n_draw=cfg["n_utt"])
+    return [pcm[off[u]:off[u + 1]] for u in range(n_utt_sample)]
+
+
+class CpuArm:
+    """`cores` single-threaded worker processes (faster than threaded BLAS on these shapes)."""
+
+    def __init__(self, workload, cores):
+        import multiprocessing as mp
+        _cpu_prepare(workload)
+        self.kind, self.cores, self.workload = _CPU_KIND, cores, workload
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+
+    def run(self, jobs):
         t0 = time.perf_counter()
-        frames = sum(pool.map(_cpu_worker, jobs, chunksize=max(1, n_utt_sample // (8 * cores))))
-        dt = time.perf_counter() - t0
-    return frames / dt, frames, dt
+        frames = sum(self.pool.map(_cpu_worker, jobs, chunksize=max(1, len(jobs) // (8 * self.cores))))
+        return frames, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self):
+        return ("unmodified reference (oracle/_ref/lnasr_reference.zip): MFCC.calc_mfcc + GMMHMM._viterbi(obs, True) per model"
+                if self.kind == "reference" else "numpy port of the reference (oracle/lnasr_oracle.py)")
+
+
+def cpu_sample_size(workload, cores):
+    # c4: ~11 s per 3 s utterance in the reference (32 000 x det/inv of a 39 x 39 covariance + T x N Python-level Viterbi
+    # steps) -> one utterance per core and step; c2: ~0.3 s per utterance
+    return cores if workload == "c4" else max(32 * cores, 64)
 
 
 def _em_cpu_worker(job):
@@ -212,25 +286,37 @@ def run_reference(args):
     if args.workload == "c3":
         return run_reference_em(args)
     cores = os.cpu_count() or 1
-    per_step = max(32 * cores, 64) if args.workload == "c2" else cores
+    per_step = cpu_sample_size(args.workload, cores)
+    jobs = cpu_sample(args.workload, per_step)
+    arm = CpuArm(args.workload, cores)
+    budget = float(args.cpu_budget_s)                       # the whole run must end within a few minutes
     vals = []
     t_all = time.perf_counter()
+    n_warm = 0
+    warm = args.warmup
     for i in range(args.warmup + args.steps):
-        v, frames, dt = cpu_arm(args.workload, per_step, cores)
-        if i >= args.warmup:
-            vals.append((v, frames, dt))
-        if time.perf_counter() - t_all > 240:
+        frames, dt = arm.run(jobs)
+        if dt > 5.0:
+            warm = min(warm, 1)                                 # a pass this long is warm after one repetition
+        if i >= warm or (time.perf_counter() - t_all) + 2 * dt > budget:
+            vals.append((frames, dt))                           # out of budget: the remaining passes are all timed ones
+        else:
+            n_warm += 1
+        if len(vals) >= args.steps or (time.perf_counter() - t_all) + dt > budget:
             break
-    frames = sum(x[1] for x in vals)
-    dt = sum(x[2] for x in vals)
+    arm.close()
+    frames = sum(x[0] for x in vals)
+    dt = sum(x[1] for x in vals)
     value = frames / dt
+    sample = (f"{per_step} utterances/step (the first {per_step} of rank 0's GPU batch, {frames // len(vals)} frames) x {len(vals)} timed steps "
+              f"after {n_warm} warm-up; {arm.describe()}; one single-threaded process per core")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
+        "warmup": n_warm, "ms_per_step": 1e3 * dt / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "sample_utts_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} utterances/step x {len(vals)} steps, one single-threaded process per core"},
+        "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "sample_utts_per_step": per_step,
+                   "steps_requested": args.steps, "warmup_requested": args.warmup, "wall_budget_s": budget},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -238,27 +324,72 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+class Ctx:
+    """Process-group context shared by the workloads of one run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.numa = None
+        if self.world > 1 and not args.no_numa_bind:
+            from lnasr.dist import bind_to_gpu_numa_node
+            self.numa = bind_to_gpu_numa_node(self.local)           # before the pinned host buffers are allocated
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm_peak = float(self.peaks.get("hbm_gbs", 6650.0))
+        self.peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in self.peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        import torch
+        import torch.distributed as dist
+        v = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    def sum_over_ranks(self, x):
+        import torch
+        import torch.distributed as dist
+        v = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return float(v.item())
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def run_ours(args, ctx, workload, steps, warmup, with_cpu=True, load_s=1.5):
+    """One decode workload (c2 / c4) on this rank's shard; every rank calls it, rank 0 gets the JSON dict back."""
     import torch
-    import torch.distributed as dist
     from lnasr.bank import AcousticPipeline, ModelBank
     from lnasr.mfcc import MFCC
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    numa = None
-    if world > 1 and not args.no_numa_bind:
-        from lnasr.dist import bind_to_gpu_numa_node
-        numa = bind_to_gpu_numa_node(local)           # before the pinned host buffers are allocated
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = dict(WORKLOADS[args.workload])
+    rank, world, local = ctx.rank, ctx.world, ctx.local
+    cfg = dict(WORKLOADS[workload])
     if cfg["emission"] == "tc" and args.tc_format == "f16":
         cfg["emission"] = "tc16"
         cfg["desc"] = cfg["desc"].replace("TC emissions", "tensor-core emissions (2 FP16 slices)")
-    models = make_models(args.workload)
+    models = make_models(workload)
     pipe = AcousticPipeline(MFCC(), ModelBank(models, emission=cfg["emission"]))
     # every rank owns its own shard of utterances (weak scaling: per-GPU batch fixed)
     pcm_np, off = synth_batch(1000 + rank, cfg["n_utt"], cfg["min_s"], cfg["max_s"])
@@ -266,158 +397,160 @@ def run_ours(args):
     pcm_host = torch.from_numpy(pcm_np).pin_memory()
     pcm_dev = pcm_host.cuda()
     want_paths = True
+    # what the caller gets back: one large model -> the state path IS the decode result; a bank of word models -> the word
+    return_paths = pipe.bank.K == 1
 
     def step_device():
         res, mb = pipe.recognize_batch(pcm_dev, off, want_paths=want_paths)
         return res, mb
 
-    def step_e2e():
-        # public host-facing API: pinned PCM in, decoded words + scores out; the H2D copy is chunked and overlapped
-        return pipe.recognize_batch_host(pcm_host, off, n_chunks=args.e2e_chunks, want_paths=want_paths,
-                                         n_compute_streams=args.e2e_streams, taper=not args.e2e_uniform)
+    e2e_kw = dict(n_chunks=args.e2e_chunks, want_paths=want_paths, n_compute_streams=args.e2e_streams, taper=not args.e2e_uniform,
+                  return_paths=return_paths)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step_e2e():
+        # public host-facing API: pinned PCM in, decode result out; the H2D copy is chunked and overlapped
+        return pipe.recognize_batch_host(pcm_host, off, **e2e_kw)
 
     res, mb = step_device()
     torch.cuda.synchronize()
     frames = int(mb.frame_offsets_host[-1])
     words0 = res.words.cpu().numpy().copy()
+    paths0 = res.paths.cpu().numpy().copy() if return_paths else None
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
-        barrier()
+        ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1))
 
     # clocks are sampled from before the warm-up until the sampler has seen >= 1.5 s of load (nvidia-smi needs a few
     # hundred ms to produce its first line; the timed region of a short run is over before that)
     sampler = ClockSampler(local) if rank == 0 else None
     t_load0 = time.perf_counter()
-    ms_dev = timed(step_device, args.steps, args.warmup)
-    ms_e2e_sync = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    ms_dev = timed(step_device, steps, warmup)
+    ms_e2e_sync = timed(step_e2e, steps, max(3, warmup // 2))
     # streaming form of the same public API: two batches in flight (submit batch i+1, then collect batch i); every step still
-    # copies its PCM from pinned host memory and reads its words back
+    # copies its PCM from pinned host memory and reads its result back
     pend = [None]
+    last = [None]
+
+    def collect(h):
+        out = h.result()
+        last[0] = (out[0], h.paths() if return_paths else None)
 
     def step_e2e_pipelined():
-        nxt = pipe.submit_host(pcm_host, off, n_chunks=args.e2e_chunks, want_paths=want_paths, n_compute_streams=args.e2e_streams,
-                               taper=not args.e2e_uniform)
+        nxt = pipe.submit_host(pcm_host, off, **e2e_kw)
         if pend[0] is not None:
-            pend[0].result()
+            collect(pend[0])
         pend[0] = nxt
 
     def timed_pipelined(steps, warmup):
         for _ in range(warmup):
             step_e2e_pipelined()
-        pend[0].result()
+        collect(pend[0])
         pend[0] = None
-        barrier()
+        ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step_e2e_pipelined()
-        w_last, _ = pend[0].result()                       # the last batch's words are on the host
+        collect(pend[0])                                   # the last batch's result is on the host
         pend[0] = None
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        assert np.array_equal(w_last.numpy(), words0), "pipelined e2e path decoded different words"
-        return float(ms.item())
+        ctx.barrier()
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        assert np.array_equal(last[0][0].numpy(), words0), "pipelined e2e path decoded different words"
+        if return_paths:
+            assert np.array_equal(last[0][1].numpy(), paths0), "pipelined e2e path decoded different state paths"
+        return ms
 
-    ms_e2e = timed_pipelined(args.steps, 3)
-    while time.perf_counter() - t_load0 < 1.5:
+    ms_e2e = timed_pipelined(steps, 3)
+    while time.perf_counter() - t_load0 < load_s:
         step_device()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    assert np.array_equal(step_e2e()[0].numpy(), words0), "e2e path decoded different words"
+    chk = step_e2e()
+    assert np.array_equal(chk[0].numpy(), words0), "e2e path decoded different words"
+    if return_paths:
+        assert np.array_equal(chk[2].numpy(), paths0), "e2e path decoded different state paths"
 
-    total_frames = frames * world if world == 1 else None
-    fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
-    total_frames = float(fr.item())
-    value = total_frames / (ms_dev / 1e3 / args.steps)
-    e2e_value = total_frames / (ms_e2e / 1e3 / args.steps)
-    e2e_sync_value = total_frames / (ms_e2e_sync / 1e3 / args.steps)
+    total_frames = ctx.sum_over_ranks(frames)
+    value = total_frames / (ms_dev / 1e3 / steps)
+    e2e_value = total_frames / (ms_e2e / 1e3 / steps)
+    e2e_sync_value = total_frames / (ms_e2e_sync / 1e3 / steps)
+    d2h = n_utt * 12 + (4 * pipe.bank.K * frames if return_paths else 0)
 
     # ---- per-kernel shares + roofline of the dominant kernel (rank 0, CUDA events around each C-ABI call)
     line = None
     if rank == 0:
-        stages = stage_times(pipe, pcm_dev, off, want_paths, reps=max(3, args.steps // 2))
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        stages = stage_times(pipe, pcm_dev, off, want_paths, reps=max(3, steps // 2))
         fp64 = fp64_peaks()
         if cfg["emission"] == "tc":
             fp64["tf32_tflops"] = tf32_peak()
         top = max(stages, key=lambda k: stages[k]["ms"])
-        roof = roofline_for(top, stages[top], frames, cfg, models, hbm_peak, peaks, fp64)
+        roof = roofline_for(top, stages[top], frames, cfg, models, ctx.hbm_peak, ctx.peaks, fp64)
         roof["kernel"] = top
-        if args.workload == "c2" and frames == NCU_TRAFFIC_C2["frames"]:
-            roof["traffic"] = NCU_TRAFFIC_C2[top]
-            roof["traffic_note"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/); algorithmic = %d" % (
-                roof.get("algorithmic_bytes_per_frame", 0) * frames)
-        roof["peak_source"] = peak_src
+        tr = ncu_traffic(workload, frames, top)
+        if tr is not None:
+            roof["traffic"] = tr["bytes"]
+            roof["traffic_note"] = ("bytes per launch of %s (ncu dram__bytes_read.sum + dram__bytes_write.sum, %s); algorithmic = %d" % (
+                tr["kernel"], tr["source"], roof.get("algorithmic_bytes_per_frame", 0) * frames))
+        roof["peak_source"] = ctx.peak_src
         roof["stage_ms"] = {k: round(v["ms"], 4) for k, v in stages.items()}
         roof["all_stages"] = {}
         for k in stages:
-            r = roofline_for(k, stages[k], frames, cfg, models, hbm_peak, peaks, fp64)
+            r = roofline_for(k, stages[k], frames, cfg, models, ctx.hbm_peak, ctx.peaks, fp64)
             roof["all_stages"][k] = {"bound": r["bound"], "achieved": round(r["achieved"], 3), "peak": round(r["peak"], 1),
                                      "unit": r["unit"], "frac": round(r["frac"], 4)}
             if "fp64_alu" in r:
                 roof["all_stages"][k]["fp64_alu_frac"] = round(r["fp64_alu"]["frac"], 4)
+            if "executed_frac" in r:
+                roof["all_stages"][k]["executed_frac"] = round(r["executed_frac"], 4)
         roof["fp64_peaks_measured"] = {k: round(v, 2) for k, v in fp64.items()}
         cores = os.cpu_count() or 1
-        cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "skipped (--no-cpu)"}
-        if world == 1 and not args.no_cpu:
+        cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "skipped"}
+        if world == 1 and with_cpu and not args.no_cpu:
             os.environ["OMP_NUM_THREADS"] = "1"
-            n_s = max(64 * cores, 128) if args.workload == "c2" else cores
-            v, f_s, dt = cpu_arm(args.workload, n_s, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_s} utterances ({f_s} frames) in {dt:.1f} s, one single-threaded numpy process per core"}
+            n_s = cpu_sample_size(workload, cores)
+            jobs = cpu_sample(workload, n_s)
+            arm = CpuArm(workload, cores)
+            if workload != "c4":
+                arm.run(jobs[:2 * cores])                   # warm the workers (imports, first-call costs)
+            f_s, dt = arm.run(jobs)
+            arm.close()
+            cpu = {"value": f_s / dt, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                   "sample": f"the first {n_s} utterances of this batch ({f_s} frames) in {dt:.1f} s; {arm.describe()}; "
+                             "one single-threaded process per core"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if cfg["emission"] == "exact" else ("f64 MFCC + trellis / 3xTF32 emissions" if cfg["emission"] == "tc"
                                                                 else "f64 MFCC + trellis / 2xFP16-slice emissions (fp32 accumulate)"),
             "data": "synthetic",
-            "config": {"workload": args.workload + ": " + cfg["desc"], "utts_per_gpu": n_utt, "frames_per_gpu_step": frames,
+            "config": {"workload": workload + ": " + cfg["desc"], "utts_per_gpu": n_utt, "frames_per_gpu_step": frames,
                        "pcm_bytes_per_gpu_step": int(pcm_np.nbytes), "l2": "inputs larger than L2 (PCM + intermediates > 126 MB per step)",
                        "parallelism": f"utterance-sharded x{world}, no data-path collective", "viterbi_paths": want_paths,
-                       "host_numa_binding": numa},
+                       "host_numa_binding": ctx.numa},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(pcm_np.nbytes) + int(off.nbytes) * 2, "d2h_bytes_per_step": n_utt * 12,
-                    "api": "AcousticPipeline.submit_host / PendingRecognition.result, two batches in flight",
-                    "one_batch_at_a_time": {"value": e2e_sync_value, "ms_per_step": ms_e2e_sync / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": int(pcm_np.nbytes) + int(off.nbytes) * 2, "d2h_bytes_per_step": d2h,
+                    "result": ("Viterbi state paths int32 [1, frames] + score per utterance" if return_paths
+                               else "word index + score per utterance"),
+                    "api": "AcousticPipeline.submit_host / PendingRecognition.result (+ .paths), two batches in flight",
+                    "one_batch_at_a_time": {"value": e2e_sync_value, "ms_per_step": ms_e2e_sync / steps,
                                             "api": "AcousticPipeline.recognize_batch_host"}},
-            "gpu_launches": launches_per_step(pipe, want_paths) * args.steps,
+            "gpu_launches": launches_per_step(pipe, want_paths) * steps,
             "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
-
+    del pipe, pcm_dev, pcm_host, res, mb
+    torch.cuda.empty_cache()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ EM arm (c3)
@@ -430,21 +563,15 @@ def synth_feats(seed, n_utt, min_t, max_t, d=39):
     return x, off
 
 
-def run_em(args):
+def run_em(args, ctx, steps, warmup, load_steps=400):
     """BASELINE configs[2]: one Baum-Welch iteration over the rank's shard of utterances; the packed float64 accumulator is
     all-reduced over NCCL; every rank finalises the same M-step.  value = frames of ALL ranks / time of one iteration."""
     import torch
-    import torch.distributed as dist
     from lnasr.dist import make_reduce_fn
     from lnasr.em import EmTrainer
     from oracle import lnasr_oracle as O
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world, local = ctx.rank, ctx.world, ctx.local
     cfg = WORKLOADS["c3"]
     mdl = O.random_gmmhmm(3, 8, 39, np.random.default_rng(7))
     x_np, off = synth_feats(2000 + rank, cfg["n_utt"], cfg["min_t"], cfg["max_t"])
@@ -460,68 +587,82 @@ def run_em(args):
         tr._x.copy_(x_host, non_blocking=True)            # features from pinned host memory every iteration
         return float(tr.iterate(reduce_fn).item())       # log-likelihood read back
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
-        barrier()
+        ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1))
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev = timed(step, args.steps, args.warmup)
-    ms_e2e = timed(step_e2e, args.steps, 3)
-    for _ in range(400):                                  # ~1 s more load for the clock sampler; a FIXED count on every
+    ms_dev = timed(step, steps, warmup)
+    ms_e2e = timed(step_e2e, steps, 3)
+    for _ in range(load_steps):                           # ~1 s more load for the clock sampler; a FIXED count on every
         step()                                            # rank (each step holds a collective -- never loop on wall time)
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    fr = torch.tensor([frames], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
-    total_frames = float(fr.item())
+    total_frames = ctx.sum_over_ranks(frames)
+    line = None
     if rank == 0:
         n, m, d = 3, 8, 39
         per = 16 * n + 4 * d + 8 * n * m          # b fwd + alpha w/r + b bwd + x + bm
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        sec = ms_dev / 1e3 / args.steps
+        sec = ms_dev / 1e3 / steps
         ach = per * frames / sec / 1e9
         line = {
             "metric": "frames/sec (Baum-Welch EM iteration)", "value": total_frames / sec, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "c3: " + cfg["desc"], "utts_per_gpu": cfg["n_utt"], "frames_per_gpu_step": frames,
                        "l2": "x + b + bm + alpha = %.0f MB per step" % (frames * (4 * d + 8 * (2 * n + n * m)) / 1e6),
                        "parallelism": f"utterance-sharded x{world}, one all-reduce of {tr.acc.numel()} float64 per iteration"},
             "clocks": clocks,
-            "e2e": {"value": total_frames / (ms_e2e / 1e3 / args.steps), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+            "e2e": {"value": total_frames / (ms_e2e / 1e3 / steps), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": 8},
-            "gpu_launches": 7 * args.steps,       # pack x2 (SIMT + DMMA image), loglik, forward, fb_accumulate, mstep (+ memset)
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                         "algorithmic_bytes_per_frame": per, "kernel": "whole iteration"},
+            "gpu_launches": 7 * steps,       # pack x2 (SIMT + DMMA image), loglik, forward, backward, em_statistics, mstep (+ memset)
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": ach / ctx.hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_frame": per, "kernel": "whole iteration", "peak_source": ctx.peak_src},
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "not run for c3"},
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    del tr
+    torch.cuda.empty_cache()
+    return line
+
+
+def compact(line):
+    """What a secondary workload contributes to the headline's JSON line."""
+    if line is None:
+        return None
+    keep = {k: line[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "dtype")}
+    keep["workload"] = line["config"]["workload"]
+    keep["frames_per_gpu_step"] = line["config"]["frames_per_gpu_step"]
+    keep["parallelism"] = line["config"]["parallelism"]
+    keep["e2e"] = {k: line["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    keep["gpu_launches"] = line["gpu_launches"]
+    r = line["roofline"]
+    keep["roofline"] = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "stage_ms", "all_stages",
+                                          "fp64_alu", "fp64_peaks_measured") if k in r}
+    return keep
+
+
+def ncu_traffic(workload, frames, stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's dominant kernel, from the committed summary of an
+    `ncu --set full` capture of THIS workload at THIS size (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the
+    capture's raw page).  None when there is no capture of this shape -- never a constant carried in the source."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+    ent = tab.get(workload)
+    if not ent or int(ent.get("frames", -1)) != int(frames) or stage not in ent.get("stages", {}):
+        return None
+    st = ent["stages"][stage]
+    return {"bytes": float(st["dram_read_bytes"]) + float(st["dram_write_bytes"]), "kernel": st["kernel"], "source": ent.get("source", "profiles/")}
+
 
 def launches_per_step(pipe, want_paths):
     """Kernels of liblnasr_b200.so launched by one device-resident step."""
@@ -599,11 +740,6 @@ def tf32_peak():
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of each stage, from the `ncu --set full`
-# captures of THIS workload size (c2, 403 867 frames): profiles/r1_mfcc_v4_ncu_full.txt, r1_gmm_dmma_resident_ncu_full.txt,
-# r1_trellis_small_ncu_full.txt.  Reported only when the run has exactly that shape.
-NCU_TRAFFIC_C2 = {"frames": 403867, "mfcc": 137.72e6 + 15.88e6, "gmm": 64.24e6 + 107.22e6, "viterbi": 161.88e6 + 29.87e6}
-
 MFCC_FP64_FLOPS_PER_FRAME = 18300     # 256-pt complex FFT 10.2k + split/power 4.1k + pre-emphasis/window 1.2k + mel 0.9k + log 0.8k + DCT 1.0k
 
 
@@ -660,8 +796,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="headline workload only (no short c2 / c3 measurements)")
+    ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="--impl reference: wall-clock bound of the whole run")
     ap.add_argument("--tc-format", default="f16", choices=["f16", "tf32"],
                     help="c4: operand slices of the tensor-core emission kernel (two FP16 slices, or 3xTF32)")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA node")
@@ -673,9 +811,23 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    ctx = Ctx(args)
     if args.workload == "c3":
-        return run_em(args)
-    return run_ours(args)
+        line = run_em(args, ctx, args.steps, args.warmup)
+    else:
+        line = run_ours(args, ctx, args.workload, args.steps, args.warmup)
+    if not args.no_secondary and args.workload == "c4":
+        # every rank takes part (c2 shards by rank, c3 all-reduces); short runs, no CPU leg
+        st = min(args.steps, 10)
+        sec = {"c2": compact(run_ours(args, ctx, "c2", st, 3, with_cpu=False, load_s=0.0)),
+               "c3": compact(run_em(args, ctx, st, 3, load_steps=0))}
+        if line is not None:
+            line["secondary"] = sec
+            line["gpu_launches_note"] = "gpu_launches counts the headline workload's timed steps; each secondary entry carries its own"
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    return 0
 
 
 if __name__ == "__main__":

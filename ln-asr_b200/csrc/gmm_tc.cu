@@ -100,7 +100,7 @@ struct TcHeader {       // 512 bytes at the start of the packed image
 };
 static_assert(sizeof(TcHeader) == 512, "TcHeader must be 512 bytes");
 
-struct TcGeom { int Mp, Kp, SPT, NT, n_wtiles; size_t tile_bytes, total_bytes, smem_bytes; };
+struct TcGeom { int Mp, Kp, SPT, NT, n_wtiles; size_t tile_bytes, tail_off, total_bytes, smem_bytes; };
 
 static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     if (n_states < 1 || n_mix < 1 || n_mix > 16 || dim < 1 || dim > TC_MAX_DIM) return false;
@@ -120,9 +120,97 @@ static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     g->Mp = Mp; g->Kp = Kp; g->SPT = spt; g->NT = spt * Mp;
     g->n_wtiles = (n_states + spt - 1) / spt;
     g->tile_bytes = (size_t)2 * g->NT * Kp * 4 + (size_t)((g->SPT * 4 + 15) / 16 * 16);   // W hi | W lo | per-state constant
-    g->total_bytes = sizeof(TcHeader) + g->tile_bytes * g->n_wtiles;
+    g->tail_off = (sizeof(TcHeader) + g->tile_bytes * g->n_wtiles + 15) / 16 * 16;       // exact tail (tc_common.cuh)
+    g->total_bytes = g->tail_off + tc_tail_bytes(n_states, n_mix, dim);
     g->smem_bytes = g->tile_bytes + ring + 1024;
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------ exact tail + fix-up
+__global__ void tc_pack_tail_kernel(const double* __restrict__ logw, const double* __restrict__ mu, const double* __restrict__ var,
+                                    int64_t n_gauss, int dim, double* __restrict__ tail) {
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_gauss) return;
+    double c = (double)dim * 1.8378770664093453;
+    for (int d = 0; d < dim; ++d) {
+        const double v = var[gi * dim + d];
+        c += log(v);
+        tail[n_gauss + gi * dim + d] = mu[gi * dim + d];
+        tail[n_gauss + n_gauss * dim + gi * dim + d] = -0.5 / v;
+    }
+    tail[gi] = logw[gi] - 0.5 * c;
+}
+
+int tc_pack_tail(const double* logw, const double* mu, const double* var, int n_states, int n_mix, int dim, double* tail, cudaStream_t stream) {
+    const int64_t n_gauss = (int64_t)n_states * n_mix;
+    tc_pack_tail_kernel<<<(unsigned)ceil_div(n_gauss, 128), 128, 0, stream>>>(logw, mu, var, n_gauss, dim, tail);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+// one block per 128-frame tile; returns at once unless the staging kernel flagged a frame of the tile
+__global__ void __launch_bounds__(256) tc_fixup_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames,
+                                                       const uint8_t* __restrict__ flags, const double* __restrict__ tail, int n_states,
+                                                       int n_mix, int dim, float* __restrict__ b_out, int64_t ld_b) {
+    __shared__ int s_list[128];
+    __shared__ int s_n;
+    __shared__ double s_x[64];
+    const int64_t f0 = (int64_t)blockIdx.x * 128;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (threadIdx.x < 128 && f0 + threadIdx.x < n_frames && flags[f0 + threadIdx.x]) s_list[atomicAdd(&s_n, 1)] = threadIdx.x;
+    __syncthreads();
+    const int n_flagged = s_n;
+    if (n_flagged == 0) return;
+    const int64_t n_gauss = (int64_t)n_states * n_mix;
+    const double* t_mu = tail + n_gauss;
+    const double* t_nh = tail + n_gauss + n_gauss * dim;
+    for (int q = 0; q < n_flagged; ++q) {
+        const int64_t f = f0 + s_list[q];
+        __syncthreads();
+        if (threadIdx.x < dim) s_x[threadIdx.x] = (double)feats[f * ld_feats + threadIdx.x];
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_states; j += 256) {
+            // log sum_m exp(cst + quad) with the reference's conventions: NaN in -> NaN out, every mixture -inf -> -inf
+            double mx = neg_inf();
+            bool is_nan = false;
+            for (int m = 0; m < n_mix; ++m) {
+                const int64_t gi = (int64_t)j * n_mix + m;
+                double v = tail[gi];
+                for (int d = 0; d < dim; ++d) {
+                    const double dx = s_x[d] - t_mu[gi * dim + d];
+                    v = fma(t_nh[gi * dim + d], dx * dx, v);
+                }
+                is_nan |= (v != v);
+                mx = fmax(mx, v);
+            }
+            double r;
+            if (is_nan) r = __longlong_as_double(0x7ff8000000000000LL);
+            else if (mx == neg_inf()) r = mx;
+            else {
+                double sum = 0.0;
+                for (int m = 0; m < n_mix; ++m) {
+                    const int64_t gi = (int64_t)j * n_mix + m;
+                    double v = tail[gi];
+                    for (int d = 0; d < dim; ++d) {
+                        const double dx = s_x[d] - t_mu[gi * dim + d];
+                        v = fma(t_nh[gi * dim + d], dx * dx, v);
+                    }
+                    sum += exp(v - mx);
+                }
+                r = mx + log(sum);
+            }
+            b_out[f * ld_b + j] = (float)r;
+        }
+    }
+}
+
+int tc_fixup(const float* feats, int ld_feats, int64_t n_frames, const uint8_t* flags, const double* tail, int n_states, int n_mix,
+             int dim, float* b_out, int64_t ld_b, cudaStream_t stream) {
+    tc_fixup_kernel<<<(unsigned)ceil_div(n_frames, 128), 256, 0, stream>>>(feats, ld_feats, n_frames, flags, tail, n_states, n_mix, dim,
+                                                                           b_out, ld_b);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
 }
 
 // byte offset of element (row n, k) inside one K-major no-swizzle image of `rows` x `K` fp32:
@@ -205,9 +293,13 @@ __global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double
 // useful one out of L2.  One cheap pass to this tile-transposed copy (L2-resident: 160 B/frame) makes the
 // producers' loads perfectly coalesced.
 constexpr int TC_XT_D = 40;
+constexpr float TC_X_LIMIT = 4096.f;      // |x - shift| beyond this (or inf / NaN): the frame goes to the exact fix-up path
 __global__ void __launch_bounds__(256) gmm_tc_stage_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
-                                                           const uint8_t* __restrict__ packed, float* __restrict__ xt) {
+                                                           const uint8_t* __restrict__ packed, float* __restrict__ xt,
+                                                           uint8_t* __restrict__ flags) {
     __shared__ float tile[TC_BM][TC_XT_D + 1];
+    __shared__ int s_flag[TC_BM];
+    if (threadIdx.x < TC_BM) s_flag[threadIdx.x] = 0;
     const TcHeader* hdr = reinterpret_cast<const TcHeader*>(packed);
     const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
     const int rows = (int)min((int64_t)TC_BM, n_frames - f0);
@@ -229,10 +321,16 @@ __global__ void __launch_bounds__(256) gmm_tc_stage_kernel(const float* __restri
         }
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < rows * dim; i += 256) {
+        const int r = i / dim, d = i - r * dim;
+        if (!(fabsf(tile[r][d]) <= TC_X_LIMIT)) s_flag[r] = 1;              // also inf and NaN
+    }
+    __syncthreads();
+    if (threadIdx.x < rows) flags[f0 + threadIdx.x] = (uint8_t)s_flag[threadIdx.x];
     float* dst = xt + (int64_t)blockIdx.x * TC_XT_D * TC_BM;
     for (int i = threadIdx.x; i < TC_XT_D * TC_BM; i += 256) {
         const int d = i / TC_BM, r = i - d * TC_BM;
-        dst[i] = tile[r][d];
+        dst[i] = s_flag[r] ? 0.f : tile[r][d];
     }
 }
 
@@ -489,14 +587,15 @@ extern "C" int lnasr_gmm_pack_tc(const double* logw, const double* mu, const dou
     gmm_pack_tc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, shift, g,
                                                                                      (uint8_t*)packed);
     LNASR_LAUNCH_CHECK();
-    return LNASR_OK;
+    return tc_pack_tail(logw, mu, var, n_states, n_mix, dim, reinterpret_cast<double*>((uint8_t*)packed + g.tail_off), (cudaStream_t)stream);
 }
 
 extern "C" int lnasr_gmm_tc_workspace_bytes(int64_t n_frames, size_t* bytes) {
     LNASR_CHECK_ARG(bytes && n_frames >= 0, "gmm_tc_workspace_bytes: bad arguments");
     // per 128-frame tile: the TF32 kernel stages 40 x 128 floats (20 480 B), the FP16-slice kernel its two operand images
     // (2 x 128 x 80 halves = 40 960 B); one size serves both
-    *bytes = (size_t)ceil_div(n_frames, TC_BM) * TC_BM * TC_XT_D * sizeof(float) * 2 + 256;
+    // + one flag byte per frame (frames handed to the exact fix-up path)
+    *bytes = (size_t)ceil_div(n_frames, TC_BM) * TC_BM * TC_XT_D * sizeof(float) * 2 + 256 + tc_flag_bytes(n_frames);
     return LNASR_OK;
 }
 
@@ -517,7 +616,8 @@ extern "C" int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t
     }
     float* xt = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const int64_t frame_tiles = ceil_div(n_frames, TC_BM);
-    gmm_tc_stage_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, xt);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(xt) + (size_t)frame_tiles * TC_BM * TC_XT_D * sizeof(float) * 2;
+    gmm_tc_stage_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, xt, flags);
     LNASR_LAUNCH_CHECK();
     TcArgs a{};
     a.xt = xt; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
@@ -533,5 +633,6 @@ extern "C" int lnasr_gmm_loglik_tc(const float* feats, int32_t ld_feats, int64_t
     LNASR_CUDA(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
     gmm_tc_kernel<<<grid, TC_THREADS, g.smem_bytes, stream>>>(a);
     LNASR_LAUNCH_CHECK();
-    return LNASR_OK;
+    return tc_fixup(feats, ld_feats, n_frames, flags, reinterpret_cast<const double*>((const uint8_t*)packed + g.tail_off), n_states, n_mix,
+                    dim, b_out, ld_b, stream);
 }

@@ -48,7 +48,7 @@ struct H16Header {      // 1024 bytes at the start of the packed image
 };
 static_assert(sizeof(H16Header) == 1024, "H16Header must be 1024 bytes");
 
-struct H16Geom { int Mp, SPT, NT, n_wtiles; size_t w_part, cst_bytes, tile_bytes, total_bytes, smem_bytes; };
+struct H16Geom { int Mp, SPT, NT, n_wtiles; size_t w_part, cst_bytes, tile_bytes, tail_off, total_bytes, smem_bytes; };
 
 static bool h16_geometry(int n_states, int n_mix, int dim, H16Geom* g) {
     if (n_states < 1 || n_mix < 1 || n_mix > 16 || dim < 1 || dim > H_MAX_DIM) return false;
@@ -74,7 +74,8 @@ static bool h16_geometry(int n_states, int n_mix, int dim, H16Geom* g) {
     g->w_part = (size_t)g->NT * H_KP * 2;
     g->cst_bytes = (size_t)((g->SPT * 4 + 15) / 16 * 16);
     g->tile_bytes = 2 * g->w_part + 2 * g->cst_bytes;                       // W hi | W lo | per-state constant | per-state 1 / t
-    g->total_bytes = sizeof(H16Header) + g->tile_bytes * g->n_wtiles;
+    g->tail_off = (sizeof(H16Header) + g->tile_bytes * g->n_wtiles + 15) / 16 * 16;      // exact tail (tc_common.cuh)
+    g->total_bytes = g->tail_off + tc_tail_bytes(n_states, n_mix, dim);
     g->smem_bytes = g->tile_bytes + ring + 1024 + H_OUT_BYTES;
     return true;
 }
@@ -208,10 +209,17 @@ __global__ void gmm_pack_tc16_kernel(const double* __restrict__ logw, const doub
 // then hi), so that the contraction kernel fetches a tile with two bulk copies.  (The first version converted the tile
 // with eight producer warps inside every CTA -- each of the ~125 W-tile CTAs streams ALL frames, so the conversion was
 // repeated 125 times.)
+//
+// A frame with |x'| > 240 in any dimension (x'^2 would overflow FP16; the model's own reach is +-32), or with inf / NaN, is
+// not clamped: its operand rows are zeroed, its flag byte is set and tc_fixup re-scores it exactly after the contraction.
 constexpr uint32_t H_SLOT_BYTES = H_BM * H_KP * 2;
+constexpr float H_X_LIMIT = 240.f;
 __global__ void __launch_bounds__(256) gmm_tc16_stage_ops_kernel(const float* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
-                                                                 const uint8_t* __restrict__ packed, uint8_t* __restrict__ xa) {
+                                                                 const uint8_t* __restrict__ packed, uint8_t* __restrict__ xa,
+                                                                 uint8_t* __restrict__ flags) {
     __shared__ float tile[H_BM][H_XT_D + 1];
+    __shared__ int s_flag[H_BM];
+    if (threadIdx.x < H_BM) s_flag[threadIdx.x] = 0;
     const H16Header* hdr = reinterpret_cast<const H16Header*>(packed);
     const int64_t f0 = (int64_t)blockIdx.x * H_BM;
     const int rows = (int)min((int64_t)H_BM, n_frames - f0);
@@ -223,9 +231,11 @@ __global__ void __launch_bounds__(256) gmm_tc16_stage_ops_kernel(const float* __
     for (int i = threadIdx.x; i < rows * dim; i += 256) {
         const int r = i / dim, d = i - r * dim;
         const float x = (__ldg(feats + (f0 + r) * ld_feats + d) - hdr->shift[d]) * hdr->scale[d];
-        tile[r][d] = fminf(fmaxf(x, -240.f), 240.f);                           // x^2 stays finite in FP16
+        tile[r][d] = x;
+        if (!(fabsf(x) <= H_X_LIMIT)) s_flag[r] = 1;                           // out of FP16's range for x^2, inf or NaN
     }
     __syncthreads();
+    if (threadIdx.x < rows) flags[f0 + threadIdx.x] = (uint8_t)s_flag[threadIdx.x];
     uint4* lo = reinterpret_cast<uint4*>(xa + (size_t)blockIdx.x * 2 * H_SLOT_BYTES);
     uint4* hi = lo + H_SLOT_BYTES / 16;
     // 16-byte chunk j of an image = core-matrix row: [row/8][k/8][row%8] -> consecutive threads write consecutive chunks
@@ -241,6 +251,7 @@ __global__ void __launch_bounds__(256) gmm_tc16_stage_ops_kernel(const float* __
                 if (k < H_MAX_DIM) { const float x = tile[row][k]; v[h] = x * x; }
                 else if (k < 2 * H_MAX_DIM) v[h] = tile[row][k - H_MAX_DIM];
                 else v[h] = (k == 2 * H_MAX_DIM) ? 1.f : 0.f;
+                if (s_flag[row]) v[h] = 0.f;
             }
             const __half2 h2 = __floats2half2_rn(v[0], v[1]);
             const float2 back = __half22float2(h2);
@@ -562,7 +573,7 @@ extern "C" int lnasr_gmm_pack_tc16(const double* logw, const double* mu, const d
     gmm_pack_tc16_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(logw, mu, var, n_states, n_mix, dim, shift, scale, g,
                                                                                        (uint8_t*)packed);
     LNASR_LAUNCH_CHECK();
-    return LNASR_OK;
+    return tc_pack_tail(logw, mu, var, n_states, n_mix, dim, reinterpret_cast<double*>((uint8_t*)packed + g.tail_off), (cudaStream_t)stream);
 }
 
 extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64_t n_frames, const void* packed, int32_t n_states,
@@ -582,7 +593,8 @@ extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64
     }
     uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const int64_t frame_tiles = ceil_div(n_frames, H_BM);
-    gmm_tc16_stage_ops_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, ws);
+    uint8_t* flags = ws + (size_t)frame_tiles * 2 * H_SLOT_BYTES;
+    gmm_tc16_stage_ops_kernel<<<(unsigned)frame_tiles, 256, 0, stream>>>(feats, ld_feats, n_frames, dim, (const uint8_t*)packed, ws, flags);
     LNASR_LAUNCH_CHECK();
     H16Args a{};
     a.xa = ws; a.n_frames = n_frames; a.packed = (const uint8_t*)packed; a.b_out = b_out; a.ld_b = ld_b;
@@ -615,5 +627,6 @@ extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64
     LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_tc16_kernel<<<grid, HB_THREADS, smem, stream>>>(a);
     LNASR_LAUNCH_CHECK();
-    return LNASR_OK;
+    return tc_fixup(feats, ld_feats, n_frames, flags, reinterpret_cast<const double*>((const uint8_t*)packed + g.tail_off), n_states, n_mix,
+                    dim, b_out, ld_b, stream);
 }

@@ -30,19 +30,39 @@ class BankResult(NamedTuple):
 
 
 class PendingRecognition:
-    """Handle of an asynchronous `AcousticPipeline.submit_host`: `.result()` -> (words int32 [n], best float64 [n]) on the host."""
+    """Handle of an asynchronous `AcousticPipeline.submit_host`: `.result()` -> (words int32 [n], best float64 [n]) on the host;
+    `.paths()` -> the Viterbi state paths [K, total_frames] int32 on the host (submitted with return_paths=True)."""
 
-    def __init__(self, words, best, event, keep):
+    def __init__(self, words, best, event, keep, paths=None, path_blocks=None, n_models=1):
         self._words, self._best, self._event, self._keep = words, best, event, keep
+        self._paths, self._path_blocks, self._K = paths, path_blocks, n_models
 
     def done(self) -> bool:
         return self._event is None or self._event.query()
 
-    def result(self):
+    def _wait(self):
         if self._event is not None:
             self._event.synchronize()
             self._event, self._keep = None, ()
+
+    def result(self):
+        self._wait()
         return self._words, self._best
+
+    def paths(self):
+        """[K, total_frames] int32 CPU tensor (hmm.py:168-171 per utterance and model), frames in batch order.  The device
+        writes one [K, frames of the group] block per utterance group; with one model (large-vocabulary scoring) that IS the
+        batch-order path, with several the blocks are re-joined here."""
+        if self._paths is None:
+            raise _capi.LnasrError("submit_host(..., return_paths=True) was not requested for this batch")
+        self._wait()
+        if self._K == 1:
+            return self._paths.view(1, -1)
+        t = _dev.torch()
+        out = t.empty((self._K, self._paths.numel() // self._K), dtype=t.int32)
+        for f0, f1 in self._path_blocks:
+            out[:, f0:f1] = self._paths[self._K * f0:self._K * f1].view(self._K, f1 - f0)
+        return out
 
 
 class ModelBank:
@@ -116,13 +136,16 @@ class AcousticPipeline:
         return res, mb
 
     def recognize_batch_host(self, pcm_host, sample_offsets, n_chunks: int = 6, want_paths: bool = False,
-                             n_compute_streams: int = 2, taper: bool = False, _timeline=None):
-        """Synchronous form of `submit_host`: (words int32 [n], best float64 [n]) as CPU tensors."""
-        return self.submit_host(pcm_host, sample_offsets, n_chunks=n_chunks, want_paths=want_paths,
-                                n_compute_streams=n_compute_streams, taper=taper, _timeline=_timeline).result()
+                             n_compute_streams: int = 2, taper: bool = False, _timeline=None, return_paths: bool = False):
+        """Synchronous form of `submit_host`: (words int32 [n], best float64 [n]) as CPU tensors, plus the state paths
+        [K, total_frames] int32 when return_paths is set."""
+        h = self.submit_host(pcm_host, sample_offsets, n_chunks=n_chunks, want_paths=want_paths, n_compute_streams=n_compute_streams,
+                             taper=taper, _timeline=_timeline, return_paths=return_paths)
+        return h.result() + ((h.paths(),) if return_paths else ())
 
     def submit_host(self, pcm_host, sample_offsets, n_chunks: int = 6, want_paths: bool = False,
-                    n_compute_streams: int = 2, taper: bool = False, _timeline=None) -> "PendingRecognition":
+                    n_compute_streams: int = 2, taper: bool = False, _timeline=None,
+                    return_paths: bool = False) -> "PendingRecognition":
         """Asynchronous end-to-end entry point for HOST audio; returns a handle whose `.result()` waits for the words.
         Consecutive submissions pipeline: the copies of batch i+1 start while the last groups of batch i are still being
         decoded (a streaming server keeps two batches in flight).
@@ -132,12 +155,15 @@ class AcousticPipeline:
         host->device copies are queued up front on a copy stream (one event per group), so the copy engine streams
         the PCM without waiting for the host; MFCC / GMM / Viterbi of group i (compute stream) start when its copy
         has landed and overlap the copies of the later groups.  Offsets of every group travel in ONE pinned upload.
-        Returns (words int32 [n], best float64 [n]) as CPU tensors."""
+        Returns (words int32 [n], best float64 [n]) as CPU tensors.  return_paths=True also brings the Viterbi state paths
+        of every model back to the host (`PendingRecognition.paths()`): for one large model the path IS the decode result."""
         t = _dev.torch()
+        want_paths = want_paths or return_paths
         off = np.asarray(sample_offsets, dtype=np.int64)
         n_utt = len(off) - 1
         if n_utt <= 0:
-            return PendingRecognition(t.empty((0,), dtype=t.int32), t.empty((0,), dtype=t.float64), None, ())
+            return PendingRecognition(t.empty((0,), dtype=t.int32), t.empty((0,), dtype=t.float64), None, (),
+                                      paths=t.empty((0,), dtype=t.int32) if return_paths else None, path_blocks=[], n_models=self.bank.K)
         n_chunks = max(1, min(n_chunks, n_utt))
         # group boundaries at utterance borders.  Tapered sizes (1, 3, 4, .., 4, 3, 1): copy and compute are nearly balanced,
         # so the time to the first result (first copy) and the tail after the last copy (last group's compute) are what is
@@ -207,11 +233,15 @@ class AcousticPipeline:
         _capi.check(lib.lnasr_recognize_workspace_bytes(max_frames, max_utt, C.byref(rec), int(want_paths), C.byref(need)),
                     "recognize_workspace_bytes")
         ws, paths = [], []
+        total_frames = int(n_fr.sum())
+        f_start = np.concatenate([[0], np.cumsum([int(p[2][-1]) for p in plan])])
+        with t.cuda.stream(comps[0]):
+            paths_all = t.empty((K * total_frames,), dtype=t.int32, device=dev) if return_paths else None
         for cs in comps:
             with t.cuda.stream(cs):
                 cs.wait_stream(comps[0])
                 ws.append(t.empty((need.value,), dtype=t.uint8, device=dev))
-                paths.append(t.empty((K * max_frames,), dtype=t.int32, device=dev) if want_paths else None)
+                paths.append(t.empty((K * max_frames,), dtype=t.int32, device=dev) if (want_paths and not return_paths) else None)
         isz = pcm_dev.element_size()
         code = _dev.np_dtype_code(pcm_dev.dtype)
         for i, ((lo, hi), (p0, p1, f_rel), ev) in enumerate(zip(bounds, plan, events)):
@@ -222,7 +252,8 @@ class AcousticPipeline:
             _capi.check(lib.lnasr_recognize_batch(
                 C.c_void_p(pcm_dev.data_ptr() + s0 * isz), code, C.c_void_p(meta_dev.data_ptr() + 8 * p0),
                 C.c_void_p(meta_dev.data_ptr() + 8 * p1), nu, int(f_rel[-1]), C.byref(rec),
-                C.c_void_p(words.data_ptr() + 4 * lo), C.c_void_p(best.data_ptr() + 8 * lo), _capi.ptr(paths[i % len(comps)]),
+                C.c_void_p(words.data_ptr() + 4 * lo), C.c_void_p(best.data_ptr() + 8 * lo),
+                C.c_void_p(paths_all.data_ptr() + 4 * K * int(f_start[i])) if return_paths else _capi.ptr(paths[i % len(comps)]),
                 _capi.ptr(ws[i % len(comps)]), need.value, C.c_void_p(cs.cuda_stream)), "recognize_batch")
             if _timeline is not None:                      # diagnostic: (copy-done event, compute-done event) per group
                 done = t.cuda.Event(enable_timing=True)
@@ -235,13 +266,19 @@ class AcousticPipeline:
             out_b = t.empty((n_utt,), dtype=t.float64, pin_memory=True)
             out_w.copy_(words, non_blocking=True)
             out_b.copy_(best, non_blocking=True)
+            out_p = None
+            if return_paths:
+                out_p = t.empty((K * total_frames,), dtype=t.int32, pin_memory=True)
+                out_p.copy_(paths_all, non_blocking=True)
             done = t.cuda.Event()
             done.record(comps[0])
         for cs in comps:
-            for x in (pcm_dev, meta_dev, words, best):
+            for x in (pcm_dev, meta_dev, words, best) + ((paths_all,) if return_paths else ()):
                 x.record_stream(cs)
         # the device buffers stay referenced by the handle until the result has been collected
-        return PendingRecognition(out_w, out_b, done, (pcm_dev, meta_dev, words, best, ws, paths, meta_host, pcm_host))
+        blocks = [(int(f_start[i]), int(f_start[i + 1])) for i in range(len(plan))]
+        return PendingRecognition(out_w, out_b, done, (pcm_dev, meta_dev, words, best, ws, paths, paths_all, meta_host, pcm_host),
+                                  paths=out_p, path_blocks=blocks, n_models=K)
 
     def _recognizer_struct(self):
         """lnasr_recognizer for the current device (cached; keeps the referenced structs alive)."""

@@ -39,7 +39,9 @@ class PackedGmmTC:
             mm, vv = mu[finite], var[finite]
             if shift is None:
                 shift = 0.5 * (mm.min(axis=0) + mm.max(axis=0)) if len(mm) else np.zeros(self.dim)
-            shift = np.asarray(shift, dtype=np.float64)
+            # the staging kernel subtracts the shift in float32: use a float32-representable centre so that the weights
+            # (float64 on the host) are built about exactly the same origin
+            shift = np.asarray(shift, dtype=np.float32).astype(np.float64)
             reach = (np.abs(mm - shift) + 4.0 * np.sqrt(vv)).max(axis=0) if len(mm) else np.ones(self.dim)
             scale = np.exp2(np.floor(np.log2(32.0 / np.maximum(reach, 1e-30))))
             self.shift, self.scale = shift, scale
@@ -51,7 +53,7 @@ class PackedGmmTC:
             return
         _capi.check(lib.lnasr_gmm_tc_packed_bytes(self.n_states, self.n_mix, self.dim, C.byref(nbytes)), "gmm_tc_packed_bytes")
         self.packed = _dev.zeros((nbytes.value,), t.uint8)
-        sh = None if shift is None else _dev.to_dev(np.asarray(shift, dtype=np.float64), t.float64)
+        sh = None if shift is None else _dev.to_dev(np.asarray(shift, dtype=np.float32).astype(np.float64), t.float64)
         _capi.check(lib.lnasr_gmm_pack_tc(_capi.ptr(lw), _capi.ptr(m), _capi.ptr(v), self.n_states, self.n_mix, self.dim,
                                           _capi.ptr(sh), _capi.ptr(self.packed), _capi.stream_ptr()), "gmm_pack_tc")
 

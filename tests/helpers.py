@@ -2,11 +2,13 @@
 import numpy as np
 
 
-def assert_close(actual, ref, rel=1e-4, what=""):
-    """|actual - ref| <= rel * (|ref| + rms(ref)) elementwise, NaN / inf patterns identical.
+def assert_close(actual, ref, rel=1e-4, what="", per_column=None):
+    """|actual - ref| <= rel * (|ref| + rms) elementwise, NaN / inf patterns identical.
 
-    'within 1e-4 relative' (BASELINE.json) read against the scale of the array: entries of a mean-normalised
-    feature column pass through zero, where a pure per-element relative error is meaningless."""
+    'within 1e-4 relative' (BASELINE.json) read against a scale: entries of a mean-normalised feature column pass through
+    zero, where a pure per-element relative error is meaningless.  For 2-D arrays the rms is taken PER COLUMN (default): the
+    columns of a feature matrix differ by two orders of magnitude (c1 ~ 50, a delta-delta ~ 1), and one global rms would
+    hold the small columns to the tolerance of the large ones."""
     actual = np.asarray(actual, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert actual.shape == ref.shape, f"{what}: shape {actual.shape} != {ref.shape}"
@@ -15,7 +17,14 @@ def assert_close(actual, ref, rel=1e-4, what=""):
     assert np.array_equal(actual[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)]), f"{what}: inf pattern differs"
     if not fin.any():
         return
-    scale = np.sqrt(np.mean(ref[fin] ** 2))
+    if per_column is None:
+        per_column = ref.ndim == 2
+    if per_column and ref.ndim == 2:
+        sq = np.where(fin, ref, 0.0) ** 2
+        cnt = np.maximum(fin.sum(axis=0), 1)
+        scale = np.broadcast_to(np.sqrt(sq.sum(axis=0) / cnt)[None, :], ref.shape)[fin]
+    else:
+        scale = np.sqrt(np.mean(ref[fin] ** 2))
     err = np.abs(actual[fin] - ref[fin])
     bound = rel * (np.abs(ref[fin]) + scale)
     worst = np.argmax(err - bound)

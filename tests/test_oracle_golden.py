@@ -1,7 +1,11 @@
 """Pin the numpy oracle (oracle/lnasr_oracle.py) to fixtures produced by the unmodified reference
 (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from oracle import lnasr_oracle as O
 
@@ -157,3 +161,36 @@ def test_gauss_density(golden):
     g = golden("gmm")
     np.testing.assert_allclose(O.gauss_logpdf_full(g["x"], g["mu"], g["Sigma"]), g["gmlog"], **TIGHT)
     np.testing.assert_allclose(np.exp(O.gauss_logpdf_full(g["x"], g["mu"], g["Sigma"])), g["gm"], **TIGHT)
+
+
+def test_port_agrees_with_the_staged_reference_in_a_worker():
+    """oracle/_ref/lnasr_reference.zip (the unmodified reference staged by oracle/build_ref.py, what `bench.py --impl reference`
+    times) against the numpy port, from PCM, in a separate process (the reference must be imported as `lnasr` there)."""
+    import subprocess
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference archive not staged (run python oracle/build_ref.py where /root/reference exists)")
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+np.seterr(all="ignore")
+from oracle import ref_loader, lnasr_oracle as O
+R = ref_loader.load()
+rng = np.random.default_rng(5)
+x = np.clip(np.round(3000 * rng.standard_normal(9000)), -32767, 32767).astype(np.int16)
+F = R["mfcc"].MFCC().calc_mfcc(x)[2]
+assert np.array_equal(F, O.mfcc(x)[2])
+m = O.random_gmmhmm(6, 3, 39, rng)
+m["mu"] *= 100.0; m["var"] *= 400.0
+si = m["var"][..., None] * np.eye(39)
+g = R["gmmhmm"].GMMHMM(6, 3, 39, A=m["A"], pi=m["pi"], w=m["w"], mu=m["mu"], si=si)
+v, bt, path = g._viterbi(F, True)
+b, _ = O.map_b(F, m["w"], m["mu"], m["var"])
+v2, bt2, path2 = O.viterbi(m["pi"], m["A"], b)
+assert np.array_equal(path, path2) and np.allclose(v, v2, rtol=1e-10, atol=1e-8)
+assert abs(g.calc_prob(F) - O.lse(O.forward(m["pi"], m["A"], b)[-1])) < 1e-8
+print("ok")
+''' % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]

@@ -150,3 +150,61 @@ def test_bank_with_tc_emissions_decodes_like_oracle(emission):
             d_lp = res.logprob.cpu().numpy()[u, 0] - lp_ref
             print(f"{emission} utt T={lens[u]}: viterbi score err {d_v:+.3e}, log-prob err {d_lp:+.3e}")
             assert abs(d_v) < 1e-3 and abs(d_lp) < 1e-3              # BASELINE.json: 1e-3 absolute per utterance
+
+
+@pytest.mark.parametrize("fmt", ["tf32", "f16"])
+def test_out_of_range_and_non_finite_frames_take_the_exact_path(fmt):
+    """No silent clamp: a frame whose features leave the operand format's range, or hold inf / NaN (the log energy of an
+    all-zero frame is -inf, mfcc.py:158-160, and the deltas next to it are NaN), is flagged by the staging kernel and re-scored
+    by the float64 fix-up kernel with the reference's own conventions: finite far-away values, -inf for inf, NaN for NaN."""
+    import torch
+    from lnasr.gmm_tc import PackedGmmTC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(17)
+    n, mix, d, T = 40, 16, 39, 300
+    mdl = O.random_gmmhmm(n, mix, d, rng)
+    mdl["mu"] = mdl["mu"] * 100.0
+    mdl["var"] = mdl["var"] * 400.0
+    x = (20.0 * rng.standard_normal((T, d))).astype(np.float32)
+    far, minf, nan, both = 5, 130, 131, 299
+    x[far, 3] = 2.0e4                      # 1000 sigma away: |x'| > 240 (f16) and |x - shift| > 4096 (tf32)
+    x[17, 0] = 9000.0
+    x[minf, 12] = -np.inf
+    x[nan, 25] = np.nan
+    x[both, 12], x[both, 38] = -np.inf, np.nan
+    with np.errstate(all="ignore"):
+        b_ref, _ = O.map_b(x.astype(np.float64), mdl["w"], mdl["mu"], mdl["var"])
+    b = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], fmt=fmt).loglik(torch.from_numpy(x).cuda()).cpu().numpy().T.astype(np.float64)
+    assert np.array_equal(np.isnan(b), np.isnan(b_ref)) and np.isnan(b[:, nan]).all() and np.isnan(b[:, both]).all()
+    assert np.array_equal(np.isneginf(b), np.isneginf(b_ref)) and np.isneginf(b[:, minf]).all()
+    fin = np.isfinite(b_ref)
+    rel = np.abs(b[fin] - b_ref[fin]) / np.abs(b_ref[fin])
+    assert rel.max() < 1e-4
+    for t in (far, 17):                    # the exact path: only the float32 rounding of the result is left
+        assert np.max(np.abs(b[:, t] - b_ref[:, t]) / np.abs(b_ref[:, t])) < 2e-7
+    assert np.all(b[:, far] < -1e5)        # and nothing like the finite value a clamp to +-240 would have produced
+
+
+@pytest.mark.parametrize("emission", ["tc", "tc16"])
+def test_all_zero_frames_through_the_pipeline(emission):
+    """PCM with a silent (all-zero) stretch: energy -inf, NaN deltas (the `_zero` case of the MFCC goldens) -> the tensor-core
+    banks produce the same -inf / NaN emission pattern as the float64 bank, and the same finite values elsewhere."""
+    import torch
+    from lnasr.bank import ModelBank
+    from lnasr.mfcc import MFCC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(3)
+    pcm = np.clip(np.round(3000.0 * rng.standard_normal(16000)), -32767, 32767).astype(np.int16)
+    pcm[6000:8000] = 0
+    mb = MFCC().calc_mfcc_batch([pcm])
+    feats = mb.feats
+    assert torch.isinf(feats[:, 12]).any() and torch.isnan(feats).any()
+    mdl = O.random_gmmhmm(48, 8, 39, rng)
+    mdl["mu"] = mdl["mu"] * 100.0
+    mdl["var"] = mdl["var"] * 400.0
+    b64 = ModelBank([mdl], emission="exact").emissions(feats).cpu().numpy()
+    b = ModelBank([mdl], emission=emission).emissions(feats).double().cpu().numpy()
+    assert np.array_equal(np.isnan(b), np.isnan(b64)) and np.array_equal(np.isneginf(b), np.isneginf(b64))
+    fin = np.isfinite(b64)
+    assert fin.any() and (~fin).any()
+    assert np.max(np.abs(b[fin] - b64[fin]) / np.abs(b64[fin])) < 1e-4
