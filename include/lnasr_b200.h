@@ -286,6 +286,12 @@ int lnasr_debug_fp64_peak(int kind, double* scratch, double* tflops_out /*host*/
 int lnasr_debug_set_gmm_simt(int on);
 /* bring-up switch: exchange the LBO / SBO fields of the descriptors lnasr_gmm_loglik_tc builds (0 = as documented) */
 int lnasr_debug_set_umma_swap(int swap);
+/* bring-up / test switch for the banded Viterbi decode: 2 = trellis_band2_kernel (barrier-free, 2-bit backpointers, fused
+ * backtrace; default), 1 = trellis_band_kernel + backtrace_kernel */
+int lnasr_debug_set_band_kernel(int version);
+/* lnasr_debug_umma_probe issues a second, accumulating MMA on the K chunks `byte_offset` further into both images
+ * (0 = single MMA): measures how the fp32 TMEM accumulator rounds (tools/probe_umma_rounding.py) */
+int lnasr_debug_set_probe_second_mma(uint32_t byte_offset);
 
 #ifdef __cplusplus
 }

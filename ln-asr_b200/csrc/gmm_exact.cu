@@ -629,6 +629,47 @@ static int launch_mma(const void* feats, int ld_feats, int64_t n_frames, const d
 
 extern "C" int lnasr_debug_set_gmm_simt(int on) { g_force_simt = (on == 1); g_force_stream = (on == 2); return LNASR_OK; }
 
+// A frame with an inf or NaN feature (the log energy of an all-zero frame is -inf, mfcc.py:158-160, and the deltas next to it
+// are NaN): the reference evaluates (x - mu) Sigma^-1 (x - mu)^T with the FULL matrix product (gmm.py:59-68), where the zero
+// off-diagonal entries of a diagonal Sigma^-1 meet the infinite difference as 0 * inf = NaN -- every Gaussian of such a frame is
+// NaN there.  The expansion the kernels above evaluate would give -inf, +inf or NaN depending on the signs of mu, so those
+// rows are overwritten here.  One block per 128 frames; it reads the features once and returns unless a frame is flagged.
+template <typename FeatT, typename OutT>
+__global__ void __launch_bounds__(256) gmm_nonfinite_rows_kernel(const FeatT* __restrict__ feats, int ld_feats, int64_t n_frames, int dim,
+                                                                 int n_states, int n_mix, OutT* __restrict__ b_out, int64_t ld_b,
+                                                                 double* __restrict__ bm_out) {
+    __shared__ int s_flag[128];
+    __shared__ int s_any;
+    const int64_t f0 = (int64_t)blockIdx.x * 128;
+    const int rows = (int)min((int64_t)128, n_frames - f0);
+    if (threadIdx.x < 128) s_flag[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * dim; i += 256) {
+        const int r = i / dim, d = i - r * dim;
+        const double x = (double)feats[(f0 + r) * ld_feats + d];
+        if (!(fabs(x) <= 1.7976931348623157e308)) { s_flag[r] = 1; s_any = 1; }
+    }
+    __syncthreads();
+    if (!s_any) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int r = 0; r < rows; ++r) {
+        if (!s_flag[r]) continue;
+        for (int j = threadIdx.x; j < n_states; j += 256) b_out[(f0 + r) * ld_b + j] = (OutT)qnan;
+        if (bm_out)
+            for (int64_t j = threadIdx.x; j < (int64_t)n_states * n_mix; j += 256) bm_out[(f0 + r) * (int64_t)n_states * n_mix + j] = qnan;
+    }
+}
+
+template <typename FeatT, typename OutT>
+static int launch_nonfinite(const void* feats, int ld_feats, int64_t n_frames, int dim, int n_states, int n_mix, void* b_out, int64_t ld_b,
+                            double* bm_out, cudaStream_t stream) {
+    gmm_nonfinite_rows_kernel<FeatT, OutT><<<(unsigned)ceil_div(n_frames, 128), 256, 0, stream>>>(
+        (const FeatT*)feats, ld_feats, n_frames, dim, n_states, n_mix, (OutT*)b_out, ld_b, bm_out);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 extern "C" int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype, int32_t ld_feats, int64_t n_frames,
                                       const double* packed, int32_t n_states, int32_t n_mix, int32_t dim,
                                       void* b_out, int b_dtype, int64_t ld_b, double* bm_out, void* stream_) {
@@ -641,16 +682,23 @@ extern "C" int lnasr_gmm_loglik_exact(const void* feats, int feats_dtype, int32_
     const bool f32 = feats_dtype == LNASR_DT_F32, f64 = feats_dtype == LNASR_DT_F64;
     const bool o32 = b_dtype == LNASR_DT_F32, o64 = b_dtype == LNASR_DT_F64;
     LNASR_CHECK_ARG((f32 || f64) && (o32 || o64), "gmm_loglik_exact: dtypes must be float32 or float64");
+    int rc;
     if (gm_supported(n_mix, dim) && !g_force_simt) {
-        if (f32 && o32) return launch_mma<float, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
-        if (f32 && o64) return launch_mma<float, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
-        if (f64 && o32) return launch_mma<double, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
-        return launch_mma<double, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        if (f32 && o32) rc = launch_mma<float, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        else if (f32 && o64) rc = launch_mma<float, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        else if (f64 && o32) rc = launch_mma<double, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        else rc = launch_mma<double, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+    } else {
+        if (f32 && o32) rc = launch_exact<float, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        else if (f32 && o64) rc = launch_exact<float, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        else if (f64 && o32) rc = launch_exact<double, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+        else rc = launch_exact<double, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
     }
-    if (f32 && o32) return launch_exact<float, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
-    if (f32 && o64) return launch_exact<float, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
-    if (f64 && o32) return launch_exact<double, float>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
-    return launch_exact<double, double>(feats, ld_feats, n_frames, packed, n_states, n_mix, dim, b_out, ld_b, bm_out, stream);
+    if (rc) return rc;
+    if (f32 && o32) return launch_nonfinite<float, float>(feats, ld_feats, n_frames, dim, n_states, n_mix, b_out, ld_b, bm_out, stream);
+    if (f32 && o64) return launch_nonfinite<float, double>(feats, ld_feats, n_frames, dim, n_states, n_mix, b_out, ld_b, bm_out, stream);
+    if (f64 && o32) return launch_nonfinite<double, float>(feats, ld_feats, n_frames, dim, n_states, n_mix, b_out, ld_b, bm_out, stream);
+    return launch_nonfinite<double, double>(feats, ld_feats, n_frames, dim, n_states, n_mix, b_out, ld_b, bm_out, stream);
 }
 
 template <typename FeatT, typename OutT>

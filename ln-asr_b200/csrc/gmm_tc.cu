@@ -45,7 +45,8 @@ __device__ __forceinline__ float tf32_round(float x) {
 // One tcgen05.mma (shape from idesc) on caller-provided shared-memory images; D [128 lanes, 128 columns] is returned.
 __global__ void __launch_bounds__(128) umma_probe_kernel(const float* __restrict__ a_img, int a_bytes, const float* __restrict__ b_img,
                                                          int b_bytes, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
-                                                         uint32_t layout_type, uint32_t idesc, float* __restrict__ d_out) {
+                                                         uint32_t layout_type, uint32_t idesc, float* __restrict__ d_out,
+                                                         uint32_t second_off) {
     extern __shared__ __align__(1024) uint8_t probe_smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -65,6 +66,13 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const float* __restrict
         const uint64_t ad = make_smem_desc(smem_u32(sa), a_lbo, a_sbo, layout_type);
         const uint64_t bd = make_smem_desc(smem_u32(sb), b_lbo, b_sbo, layout_type);
         umma_tf32(tmem_base, ad, bd, idesc, 0u);
+        if (second_off) {
+            // a second, ACCUMULATING MMA on the K chunks that start `second_off` bytes further into both images: shows how the
+            // fp32 accumulator in TMEM takes in a small addend (rounding mode, guard bits) -- tools/probe_umma_rounding.py
+            const uint64_t ad2 = make_smem_desc(smem_u32(sa) + second_off, a_lbo, a_sbo, layout_type);
+            const uint64_t bd2 = make_smem_desc(smem_u32(sb) + second_off, b_lbo, b_sbo, layout_type);
+            umma_tf32(tmem_base, ad2, bd2, idesc, 1u);
+        }
         umma_commit(&bar);
     }
     mbar_wait(&bar, 0);
@@ -170,6 +178,14 @@ __global__ void __launch_bounds__(256) tc_fixup_kernel(const float* __restrict__
         __syncthreads();
         if (threadIdx.x < dim) s_x[threadIdx.x] = (double)feats[f * ld_feats + threadIdx.x];
         __syncthreads();
+        bool finite = true;
+        for (int d = 0; d < dim; ++d) finite = finite && (fabs(s_x[d]) <= 1.7976931348623157e308);
+        if (!finite) {
+            // inf or NaN feature: every Gaussian of the frame is NaN in the reference (0 * inf in its full-matrix quadratic form,
+            // gmm.py:59-68; see gmm_nonfinite_rows_kernel in gmm_exact.cu)
+            for (int j = threadIdx.x; j < n_states; j += 256) b_out[f * ld_b + j] = __int_as_float(0x7fc00000);
+            continue;
+        }
         for (int j = threadIdx.x; j < n_states; j += 256) {
             // log sum_m exp(cst + quad) with the reference's conventions: NaN in -> NaN out, every mixture -inf -> -inf
             double mx = neg_inf();
@@ -549,12 +565,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
 }
 
 static uint32_t g_umma_swap = 0;
+static uint32_t g_probe_second_off = 0;
 
 }  // namespace lnasr
 
 using namespace lnasr;
 
 extern "C" int lnasr_debug_set_umma_swap(int swap) { g_umma_swap = swap ? 1u : 0u; return LNASR_OK; }
+extern "C" int lnasr_debug_set_probe_second_mma(uint32_t byte_offset) { g_probe_second_off = byte_offset; return LNASR_OK; }
 
 extern "C" int lnasr_debug_umma_probe(const float* a_image, int32_t a_bytes, const float* b_image, int32_t b_bytes, uint32_t a_lbo,
                                       uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t layout_type, uint32_t idesc,
@@ -565,7 +583,7 @@ extern "C" int lnasr_debug_umma_probe(const float* a_image, int32_t a_bytes, con
     const size_t smem = (size_t)((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023) + 1024;
     LNASR_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a_image, a_bytes, b_image, b_bytes, a_lbo, a_sbo, b_lbo, b_sbo,
-                                                             layout_type, idesc, d_out);
+                                                             layout_type, idesc, d_out, g_probe_second_off);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }

@@ -136,8 +136,9 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 //   cst[G] | mu[G * dim] | nh[G * dim]      (G = n_states * n_mix, cst = log w - (dim ln 2pi + sum ln var) / 2, nh = -1 / (2 var)).
 // A frame whose (centred, scaled) features leave the range the operand format can carry -- or hold inf / NaN, e.g. the log
 // energy of an all-zero frame (mfcc.py:158-160) and the deltas next to it -- is FLAGGED by the staging kernel (its operand
-// rows are zeroed, one byte per frame in the workspace) and re-scored by tc_fixup after the contraction with the direct
-// form  cst - sum (x - mu)^2 / (2 var)  in float64: the reference's own arithmetic (gmm.py:59-68), including its -inf / NaN.
+// rows are zeroed, one byte per frame in the workspace) and re-scored by tc_fixup after the contraction: finite features with
+// the direct form  cst - sum (x - mu)^2 / (2 var)  in float64, inf / NaN features as the reference's NaN (gmm.py:59-68: its
+// full-matrix quadratic form meets 0 * inf).
 inline size_t tc_tail_bytes(int n_states, int n_mix, int dim) { return (size_t)n_states * n_mix * (1 + 2 * (size_t)dim) * sizeof(double); }
 inline size_t tc_flag_bytes(int64_t n_frames) { return (size_t)((n_frames + 255) / 256 * 256); }
 int tc_pack_tail(const double* logw, const double* mu, const double* var, int n_states, int n_mix, int dim, double* tail, cudaStream_t stream);

@@ -20,6 +20,7 @@
 //
 // Tie rule: np.argmax takes the first maximum (hmm.py:166,169) -> strict '>' while scanning ascending i.
 #include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 
 namespace lnasr {
@@ -644,6 +645,233 @@ trellis_band_kernel(TrellisArgs a) {
     trellis_terminate<MODE_VITERBI>(col, N, a, p, red_v, red_i);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Banded Viterbi, second form: the decode kernel of large left-to-right banks (config 4).  Same ownership as
+// trellis_band_kernel (a thread keeps SPT consecutive states, their trellis values and their three transition weights in
+// registers), with everything that made a time step slow taken out of it:
+//   * NO block barrier in the time loop.  A thread needs the two values below its range: inside a warp they come by
+//     __shfl_up, across warps through a small shared-memory ring with a producer / consumer counter pair, so warp w runs one
+//     step behind warp w-1 in a skewed pipeline and only ever waits for its neighbour (bar.sync made all eight warps wait
+//     for the slowest one every frame).
+//   * emission rows are PRIVATE: every thread cp.asyncs exactly the SPT values it will consume (PF rows ahead), so
+//     cp.async.wait_group alone makes them visible -- no barrier, and no second pass over shared memory.
+//   * backpointers are 2-BIT distance codes (0 / 1 / 2 = j - i of the chosen predecessor, 3 = "state 0", np.argmax over an
+//     all -inf column, hmm.py:166): one uint16 per thread and frame (SPT = 8) instead of eight -- 0.5 kB per frame for 2000
+//     states instead of 4 kB.
+//   * the backtrace (hmm.py:168-171) is FUSED: when the forward pass is done the CTA pulls its own backpointer rows back
+//     (L2-resident, 64 rows at a time) into the shared memory the emission ring occupied, one thread chases the pointers
+//     there (a shared-memory load per frame instead of a dependent global load), and the path leaves as coalesced rows.
+// Needs: band topology, N % SPT == 0, 16-byte aligned emission rows (else trellis_band_kernel + backtrace_kernel run).
+constexpr int TB2_RING = 8;      // halo ring depth: how far a warp may run ahead of its successor
+constexpr int TB2_CH = 64;       // backpointer rows per backtrace chunk
+
+__device__ __forceinline__ int tb2_ld_flag(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tb2_st_flag(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+template <int SPT, typename BT, int PF>
+__global__ void __launch_bounds__(TG_THREADS, 2)
+trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    constexpr int EPC = 16 / (int)sizeof(BT);                 // emission values per 16-byte chunk
+    constexpr int CPT = SPT / EPC;                             // chunks per thread and row
+    constexpr int NW = TG_THREADS / 32;
+    typedef typename std::conditional<SPT == 8, uint16_t, uint8_t>::type CodeT;      // SPT 2-bit codes
+    static_assert(SPT % EPC == 0 && CPT >= 1, "a thread's emission values must be whole 16-byte chunks");
+    // shared memory: emission ring [PF][CPT][TG_THREADS] 16-byte chunks (re-used by the termination column and the backtrace)
+    uint4* ering = reinterpret_cast<uint4*>(tg_smem);
+    __shared__ double2 halo[TB2_RING][NW];
+    __shared__ int prod[NW], cons[NW];
+    __shared__ double red_v[NW];
+    __shared__ int red_i[NW];
+    __shared__ int s_last;
+    const int N = a.N;
+    const int64_t p = blockIdx.x;
+    const int u = (int)(p / a.n_models), k = (int)(p % a.n_models);
+    const int64_t f0 = __ldg(a.frame_off + u);
+    const int T = (int)(__ldg(a.frame_off + u + 1) - f0);
+    if (T == 0) return;
+    const int64_t cbase = (int64_t)k * N;
+    const BT* b = (const BT*)a.b;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, j0 = tid * SPT;
+    const bool own = j0 < N;                                   // N % SPT == 0: an owning thread owns SPT states
+    const int n_wp = ((N / SPT) + 31) >> 5;                    // warps that own states
+    if (tid < NW) { prod[tid] = 0; cons[tid] = 0; }
+    __syncthreads();
+    // backpointer rows: row (f0 + s) * n_models + k, bt_pitch bytes, thread t's SPT codes at t * sizeof(CodeT)
+    uint8_t* bt_rows = a.bt_ws ? reinterpret_cast<uint8_t*>(a.bt_ws) + ((int64_t)f0 * a.n_models + k) * bt_pitch : nullptr;
+    const int64_t bt_step = (int64_t)a.n_models * bt_pitch;
+    double v[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) v[i] = neg_inf();
+    if (wp < n_wp) {
+        const BT* src = b + f0 * a.ld_b + cbase + j0;
+        auto issue_row = [&](int s) {
+            if (own && s < T) {
+                const BT* g = src + (int64_t)s * a.ld_b;
+                uint4* dst = ering + ((s % PF) * CPT) * TG_THREADS + tid;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) tr_cp_async(dst + c * TG_THREADS, g + c * EPC, 16);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int s = 0; s < PF - 1; ++s) issue_row(s);
+        // transitions into my states by distance: w[i][d] = log A[j - d, j], from the ELL predecessor lists
+        double w[SPT][3];
+        {
+            const int deg = a.max_in;
+            const int* eidx = a.pred_idx + (int64_t)k * deg * N;
+            const double* eval = a.pred_val + (int64_t)k * deg * N;
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                w[i][0] = w[i][1] = w[i][2] = neg_inf();
+                const int j = j0 + i;
+                if (own)
+                    for (int d = 0; d < deg; ++d) {
+                        const double val = __ldg(eval + (int64_t)d * N + j);
+                        const int dist = j - __ldg(eidx + (int64_t)d * N + j);
+                        if (val != neg_inf()) {
+                            if (dist == 0) w[i][0] = val;
+                            else if (dist == 1) w[i][1] = val;
+                            else w[i][2] = val;
+                        }
+                    }
+            }
+        }
+        CodeT* btp = bt_rows ? reinterpret_cast<CodeT*>(bt_rows) + tid : nullptr;
+        const bool publish = (lane == 31) && (wp + 1 < n_wp);
+        for (int s = 0; s < T; ++s) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");     // my chunks of row s have landed
+            issue_row(s + PF - 1);                                                 // into the slot I read in step s - 1
+            double e[SPT];
+            {
+                const uint4* er = ering + ((s % PF) * CPT) * TG_THREADS + tid;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const uint4 q = own ? er[c * TG_THREADS] : make_uint4(0u, 0u, 0u, 0u);
+                    if (sizeof(BT) == 4) {
+                        e[c * EPC + 0] = (double)__uint_as_float(q.x); e[c * EPC + 1] = (double)__uint_as_float(q.y);
+                        e[c * EPC + 2] = (double)__uint_as_float(q.z); e[c * EPC + 3] = (double)__uint_as_float(q.w);
+                    } else {
+                        e[c * EPC + 0] = __hiloint2double((int)q.y, (int)q.x);
+                        e[c * EPC + (EPC > 1 ? 1 : 0)] = __hiloint2double((int)q.w, (int)q.z);
+                    }
+                }
+            }
+            uint32_t code = 0;
+            if (s == 0) {
+#pragma unroll
+                for (int i = 0; i < SPT; ++i) v[i] = own ? __ldg(a.logpi + cbase + j0 + i) + e[i] : neg_inf();
+            } else {
+                // the two values below my range at step s - 1: my left neighbour's top two states
+                double2 h;
+                h.x = __shfl_up_sync(0xffffffffu, v[SPT - 2], 1);
+                h.y = __shfl_up_sync(0xffffffffu, v[SPT - 1], 1);
+                if (lane == 0) {
+                    if (wp > 0) {
+                        while (tb2_ld_flag(&prod[wp - 1]) < s) { }                 // warp wp-1 has published step s - 1
+                        h = halo[(s - 1) % TB2_RING][wp - 1];
+                        tb2_st_flag(&cons[wp], s);                                 // slot (s - 1) % RING may be overwritten
+                    } else {
+                        h = make_double2(neg_inf(), neg_inf());
+                    }
+                }
+                __syncwarp();
+                // descending i: v[i] is overwritten after the states above it have read it
+#pragma unroll
+                for (int i = SPT - 1; i >= 0; --i) {
+                    const double p2 = (i >= 2) ? v[i - 2] : (i == 1 ? h.y : h.x);
+                    const double p1 = (i >= 1) ? v[i - 1] : h.y;
+                    double best = p2 + w[i][2];
+                    uint32_t dist = 2;
+                    const double c1 = p1 + w[i][1];
+                    if (c1 > best) { best = c1; dist = 1; }                        // ascending predecessor index: first max
+                    const double c0 = v[i] + w[i][0];
+                    if (c0 > best) { best = c0; dist = 0; }
+                    if (__double2hiint(best) == (int)0xfff00000 && __double2loint(best) == 0) dist = 3;   // all -inf: np.argmax gives 0
+                    code |= dist << (2 * i);
+                    v[i] = best + e[i];
+                }
+            }
+            if (publish) {
+                while (tb2_ld_flag(&cons[wp + 1]) < s - TB2_RING + 1) { }          // the slot's previous content has been read
+                halo[s % TB2_RING][wp] = make_double2(v[SPT - 2], v[SPT - 1]);
+                tb2_st_flag(&prod[wp], s + 1);
+            }
+            if (btp && own) {
+                *btp = (CodeT)code;
+                btp = reinterpret_cast<CodeT*>(reinterpret_cast<uint8_t*>(btp) + bt_step);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                                           // the ring is free; every backpointer store has been issued
+    double* col = reinterpret_cast<double*>(tg_smem);
+    if (own) {
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) col[j0 + i] = v[i];
+    }
+    __syncthreads();
+    {   // termination (hmm.py:169): max and FIRST argmax over the last column
+        double best = neg_inf();
+        int arg = 0x7fffffff;
+        for (int j = tid; j < N; j += TG_THREADS) {
+            const double c = col[j];
+            if (c > best) { best = c; arg = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = shfl_d(best, lane ^ o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (lane == 0) { red_v[wp] = best; red_i[wp] = arg; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < NW; ++q)
+                if (red_v[q] > best || (red_v[q] == best && red_i[q] < arg)) { best = red_v[q]; arg = red_i[q]; }
+            if (arg == 0x7fffffff) arg = 0;                    // all -inf: np.argmax gives 0
+            if (a.score_out) a.score_out[p] = best;
+            if (a.last_state) a.last_state[p] = arg;
+            s_last = arg;
+        }
+        __syncthreads();
+    }
+    if (!a.path_out || !bt_rows) return;
+    // ---- fused backtrace: path[T-1] = argmax v[T-1]; path[t] = bt[t+1, path[t+1]]                    (hmm.py:168-171)
+    uint32_t* out = a.path_out + (int64_t)k * a.total_frames + f0;
+    uint8_t* stage = tg_smem;                                  // [TB2_CH][bt_pitch]
+    uint32_t* pst = reinterpret_cast<uint32_t*>(tg_smem + (size_t)TB2_CH * bt_pitch);   // [TB2_CH] states of frames lo-1 .. hi-1
+    int st = s_last;                                           // state at frame hi (thread 0 carries it across chunks)
+    if (tid == 0) out[T - 1] = (uint32_t)st;
+    const int vec_per_row = bt_pitch / 16;
+    for (int hi = T - 1; hi >= 1; hi -= TB2_CH) {
+        const int lo = max(1, hi - TB2_CH + 1), nrows = hi - lo + 1;
+        __syncthreads();                                       // the previous chunk's staging has been consumed
+        for (int i = tid; i < nrows * vec_per_row; i += TG_THREADS) {
+            const int r = i / vec_per_row, c = i - r * vec_per_row;
+            reinterpret_cast<uint4*>(stage)[i] = __ldcg(reinterpret_cast<const uint4*>(bt_rows + (int64_t)(lo + r) * bt_step) + c);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int r = hi; r >= lo; --r) {
+                const CodeT cw = reinterpret_cast<const CodeT*>(stage + (size_t)(r - lo) * bt_pitch)[st / SPT];
+                const int code = ((int)cw >> (2 * (st % SPT))) & 3;
+                st = (code == 3) ? 0 : st - code;
+                pst[r - lo] = (uint32_t)st;                    // the state of frame r - 1
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nrows; i += TG_THREADS) out[lo - 1 + i] = pst[i];
+    }
+}
+
 template <typename BT, int MODE>
 __global__ void __launch_bounds__(TG_THREADS)
 trellis_general_kernel(TrellisArgs a) {
@@ -831,6 +1059,37 @@ static int launch_band(const TrellisArgs& a, cudaStream_t stream) {
     return LNASR_OK;
 }
 
+// backpointer row pitch of trellis_band2_kernel: one code word per owning thread, rounded up to whole 16-byte vectors
+static inline int band2_pitch(int N, int spt) { return ((N / spt) * (spt / 4) + 15) / 16 * 16; }
+static int g_band_version = 2;                                   // lnasr_debug_set_band_kernel: 1 = trellis_band_kernel + backtrace_kernel
+
+// does the decode of this call run on trellis_band2_kernel (which also backtraces)?
+static bool band2_eligible(const void* b, int b_dtype, int64_t ld_b, const lnasr_hmm_bank* bank, bool plain_decode) {
+    if (g_band_version != 2 || !plain_decode) return false;
+    const int N = bank->N;
+    if (!(bank->band >= 1 && bank->band <= 3) || N <= 32 || N > 8 * TG_THREADS) return false;
+    if (!bank->pred_idx || !bank->pred_val || bank->max_in < 1) return false;
+    const int spt = (N <= 4 * TG_THREADS) ? 4 : 8;
+    const size_t esz = (b_dtype == LNASR_DT_F32) ? 4 : 8;
+    if (N % spt) return false;
+    return ((size_t)ld_b * esz) % 16 == 0 && ((size_t)N * esz) % 16 == 0 && ((uintptr_t)b) % 16 == 0;
+}
+
+template <int SPT, typename BT>
+static int launch_band2(const TrellisArgs& a, cudaStream_t stream) {
+    constexpr int PF = (sizeof(BT) == 4) ? 8 : 4;            // emission rows in flight
+    const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
+    const int pitch = band2_pitch(a.N, SPT);
+    size_t smem = (size_t)PF * (SPT * sizeof(BT)) * TG_THREADS;                    // the private emission ring
+    smem = std::max(smem, (size_t)a.N * sizeof(double));                             // termination column
+    smem = std::max(smem, (size_t)TB2_CH * pitch + TB2_CH * sizeof(uint32_t));       // backtrace staging
+    if (smem > 48 * 1024)
+        LNASR_CUDA(cudaFuncSetAttribute(trellis_band2_kernel<SPT, BT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trellis_band2_kernel<SPT, BT, PF><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a, pitch);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 template <int MODE>
 static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, cudaStream_t stream) {
     a.n_models = bank->n_models; a.N = bank->N; a.logA = bank->logA; a.logpi = bank->logpi;
@@ -843,6 +1102,10 @@ static int run_trellis(TrellisArgs a, int b_dtype, const lnasr_hmm_bank* bank, c
     const int deg = (MODE == MODE_BACKWARD) ? a.max_out : a.max_in;
     // left-to-right band (bank->band = 1 + the largest j - i of a finite transition i -> j, all within 0..2): the decode
     // path proper -- Viterbi without the API-parity outputs -- keeps the trellis column in registers
+    if (MODE == MODE_VITERBI && band2_eligible(a.b, b_dtype, a.ld_b, bank, !a.full_out && !a.bt_out)) {
+        if (a.N <= 4 * TG_THREADS) return f32 ? launch_band2<4, float>(a, stream) : launch_band2<4, double>(a, stream);
+        return f32 ? launch_band2<8, float>(a, stream) : launch_band2<8, double>(a, stream);
+    }
     if (MODE == MODE_VITERBI && bank->band >= 1 && bank->band <= 3 && !a.full_out && !a.bt_out && a.N <= 8 * TG_THREADS) {
         if (a.N <= 4 * TG_THREADS) return f32 ? launch_band<4, float>(a, stream) : launch_band<4, double>(a, stream);
         return f32 ? launch_band<8, float>(a, stream) : launch_band<8, double>(a, stream);
@@ -867,6 +1130,8 @@ static int check_common(const void* b, int b_dtype, int64_t ld_b, const int64_t*
 }  // namespace lnasr
 
 using namespace lnasr;
+
+extern "C" int lnasr_debug_set_band_kernel(int version) { g_band_version = (version == 1) ? 1 : 2; return LNASR_OK; }
 
 extern "C" int lnasr_trans_degree(const double* logA, int32_t n_models, int32_t N, int32_t* deg_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -922,7 +1187,8 @@ extern "C" int lnasr_viterbi_batch(const void* b, int b_dtype, int64_t ld_b, con
     }
     rc = run_trellis<MODE_VITERBI>(a, b_dtype, bank, stream);
     if (rc) return rc;
-    if (path_out && bank->N > 32) {        // the small kernel (N <= 32) backtraces in place
+    // the small kernel (N <= 32) and the banded decode kernel backtrace in place
+    if (path_out && bank->N > 32 && !band2_eligible(b, b_dtype, ld_b, bank, !v_out && !bt_out)) {
         backtrace_kernel<<<(unsigned)ceil_div(n_pairs, 64), 64, 0, stream>>>(a.bt_ws, a.last_state, frame_offsets, n_utt,
                                                                           bank->n_models, bank->N, total_frames, path_out);
         LNASR_LAUNCH_CHECK();

@@ -190,3 +190,56 @@ def test_model_bank_scores_and_words():
         for k in range(10):
             b, _ = O.map_b(x, models[k]["w"], models[k]["mu"], models[k]["var"])
             assert_paths_equal_ties_aside(paths[k, off[u]:off[u + 1]], paths_ref[k], models[k]["pi"], models[k]["A"], b)
+
+
+@pytest.mark.parametrize("n", [64, 1024, 2000, 2048])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_banded_decode_kernel_against_first_form_and_oracle(n, dtype):
+    """trellis_band2_kernel (barrier-free warps, 2-bit backpointers, backtrace fused, 64 rows per chunk) against
+    trellis_band_kernel + backtrace_kernel bit for bit, and against the oracle: utterance lengths around the backtrace chunk
+    size (1, 2, 63, 64, 65, 129, 300 frames), 4 and 8 states per thread, both emission dtypes, a bank of two models, an
+    impossible emission and an unreachable stretch of states (backpointer code 3 = np.argmax of an all -inf column)."""
+    import torch
+    from lnasr import _capi
+    from lnasr._trellis import TransitionBank
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(11 * n)
+    K = 2
+    As, pis = [], []
+    for k in range(K):
+        mdl = O.random_gmmhmm(n, 1, 1, rng, left_to_right=True)
+        A = mdl["A"].copy()
+        if k == 1:
+            A[n // 2 - 1, n // 2] = A[n // 2 - 1, n // 2 + 1] = A[n // 2 - 2, n // 2] = -np.inf     # states >= n/2 unreachable
+        pi = np.full(n, -np.inf)
+        pi[0], pi[2] = np.log(0.6), np.log(0.4)
+        As.append(A)
+        pis.append(pi)
+    lens = [1, 2, 63, 64, 65, 129, 300]
+    total = sum(lens)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    b = (-6.0 * rng.random((total, K * n)) - 0.5).astype(dtype)
+    b[off[4] + 7, rng.integers(0, n)] = -np.inf
+    bank = TransitionBank(np.stack(As), np.stack(pis))
+    assert bank.band == 3
+    bd, off_d = torch.from_numpy(b).cuda(), torch.from_numpy(off).cuda()
+    lib = _capi.lib()
+    r2 = bank.viterbi(bd, off_d, len(lens), total, want_path=True, want_score=True)
+    try:
+        lib.lnasr_debug_set_band_kernel(1)
+        r1 = bank.viterbi(bd, off_d, len(lens), total, want_path=True, want_score=True)
+    finally:
+        lib.lnasr_debug_set_band_kernel(2)
+    assert torch.equal(r1["score"], r2["score"]) and torch.equal(r1["path"], r2["path"])
+    s_only = bank.viterbi(bd, off_d, len(lens), total, want_path=False, want_score=True)       # no workspace, no backtrace
+    assert torch.equal(s_only["score"], r2["score"])
+    path, score = r2["path"].cpu().numpy(), r2["score"].cpu().numpy()
+    b64 = b.astype(np.float64)
+    check = range(len(lens)) if n <= 1024 else (0, 1, 4)                                        # the oracle is slow at N = 2000
+    with np.errstate(all="ignore"):
+        for k in range(K):
+            for u in check:
+                bb = b64[off[u]:off[u + 1], k * n:(k + 1) * n].T
+                v_ref, _, p_ref = O.viterbi(pis[k], As[k], bb)
+                assert_paths_equal_ties_aside(path[k, off[u]:off[u + 1]], p_ref, pis[k], As[k], bb, what=f"model {k} utt {u}")
+                assert_close(score[u, k], np.max(v_ref[-1]), 1e-12, f"score[{u},{k}]")
