@@ -404,7 +404,11 @@ def run_ours(args, ctx, workload, steps, warmup, with_cpu=True, load_s=1.5):
         res, mb = pipe.recognize_batch(pcm_dev, off, want_paths=want_paths)
         return res, mb
 
-    e2e_kw = dict(n_chunks=args.e2e_chunks, want_paths=want_paths, n_compute_streams=args.e2e_streams, taper=not args.e2e_uniform,
+    # utterance groups of the host path: a copy-bound workload (c2: 2.4 ms of copies against 1.7 ms of compute) wants several
+    # groups so that compute hides behind the copies of one batch; a compute-bound one (c4: 2.3 ms against 7 ms) wants whole
+    # batches -- full waves for the per-utterance trellis CTAs -- with the NEXT batch's copy in flight (tools/e2e_sweep.py)
+    n_chunks = args.e2e_chunks or (1 if workload == "c4" else 6)
+    e2e_kw = dict(n_chunks=n_chunks, want_paths=want_paths, n_compute_streams=args.e2e_streams, taper=not args.e2e_uniform,
                   return_paths=return_paths)
 
     def step_e2e():
@@ -543,6 +547,7 @@ def run_ours(args, ctx, workload, steps, warmup, with_cpu=True, load_s=1.5):
                     "result": ("Viterbi state paths int32 [1, frames] + score per utterance" if return_paths
                                else "word index + score per utterance"),
                     "api": "AcousticPipeline.submit_host / PendingRecognition.result (+ .paths), two batches in flight",
+                    "utterance_groups_per_batch": n_chunks,
                     "one_batch_at_a_time": {"value": e2e_sync_value, "ms_per_step": ms_e2e_sync / steps,
                                             "api": "AcousticPipeline.recognize_batch_host"}},
             "gpu_launches": launches_per_step(pipe, want_paths) * steps,
@@ -805,7 +810,8 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--e2e-uniform", action="store_true", help="equal utterance groups instead of tapered ones")
     ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams the utterance groups alternate between")
-    ap.add_argument("--e2e-chunks", type=int, default=6, help="utterance groups the host->device copy is pipelined over")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="utterance groups the host->device copy is pipelined over (0 = by workload: c4 1, c2 6)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -252,6 +252,22 @@ int lnasr_em_statistics(const void* feats, int feats_dtype, int32_t ld_feats, co
                         const double* alpha, const double* beta, const int64_t* frame_offsets, int32_t n_utt,
                         int64_t total_frames, const double* logA, const double* logw, const double* mu, int32_t N,
                         int32_t n_mix, int32_t dim, double* acc /*in/out*/, double* gamma_out /*or NULL*/, void* stream);
+/* The same statistics for ANY number of states (GMMHMM._estimate gmmhmm.py:69-156 / HMM._baumwelch hmm.py:174-200 at the model
+ * sizes the trellis kernels decode): N <= 32 forwards to lnasr_em_statistics; larger models run frame-parallel kernels over a
+ * compact list of the finite transitions with the accumulators in global memory.  alpha / beta come from lnasr_forward_batch /
+ * lnasr_backward_batch.  workspace: lnasr_em_statistics_workspace_bytes(total_frames, N). */
+size_t lnasr_em_statistics_workspace_bytes(int64_t total_frames, int32_t N);
+int lnasr_em_statistics_ws(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
+                           const double* alpha, const double* beta, const int64_t* frame_offsets, int32_t n_utt,
+                           int64_t total_frames, const double* logA, const double* logw, const double* mu, int32_t N,
+                           int32_t n_mix, int32_t dim, double* acc, double* gamma_out /*[T,N] log or NULL*/, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* discrete emissions, any N (HMM._estimate hmm.py:202-225): acc layout of lnasr_hmm_fb_accumulate */
+int lnasr_hmm_em_statistics_ws(const double* b, const double* alpha, const double* beta, const int32_t* obs,
+                               const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames, const double* logA,
+                               int32_t N, int32_t n_symbols, double* acc, double* gamma_out, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* M-step from (all-reduced) statistics; writes the new model in place of the old device arrays */
 int lnasr_mstep_finalize(const double* acc, int32_t N, int32_t n_mix, int32_t dim, double min_std,
                          double* logA, double* logpi, double* logw, double* mu, double* var, void* stream);

@@ -712,7 +712,7 @@ static int launch_stats_ab(const FbArgs& a, const double* beta, int64_t total_fr
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
     const int64_t n_tiles = ceil_div(total_frames, ES_TILE);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm));
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(em_stats_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     em_stats_ab_kernel<<<grid, ES_THREADS, smem, stream>>>(a, beta, total_frames);
     LNASR_LAUNCH_CHECK();
@@ -743,7 +743,7 @@ static int launch_fb_split(const FbArgs& a, int64_t total_frames, double* lgamma
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / smem));
     const int64_t n_tiles = ceil_div(total_frames, ES_TILE);
     const int grid_s = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm));
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(em_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     em_stats_kernel<<<grid_s, ES_THREADS, smem, stream>>>(a, lgamma, total_frames);
     LNASR_LAUNCH_CHECK();
@@ -768,7 +768,7 @@ static int launch_fb(const FbArgs& a, cudaStream_t stream) {
     if (grid < 1) grid = 1;
 #define LNASR_FB_CASE(GG)                                                                                              \
     case GG:                                                                                                           \
-        if (smem > 48 * 1024)                                                                                          \
+        if (smem > 32 * 1024)                                                                                          \
             LNASR_CUDA(cudaFuncSetAttribute(fb_accum_kernel<GG, GMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         fb_accum_kernel<GG, GMM><<<grid, EM_THREADS, smem, stream>>>(a);                                               \
         break;
@@ -780,6 +780,249 @@ static int launch_fb(const FbArgs& a, cudaStream_t stream) {
         default: set_error("fb_accumulate: N=%d > 32 is not built yet", a.N); return LNASR_EINVAL;
     }
 #undef LNASR_FB_CASE
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// General form (any N; used for N > 32): the same statistics with NOTHING resident per model -- accumulators in global
+// memory (float64 atomics, one flush per block and entry), transitions as a compact list of the finite entries of log A,
+// every kernel frame-parallel over alpha and beta from the trellis passes (lnasr_forward_batch / lnasr_backward_batch run
+// any N through the ELL lists).  Large models are sparse (left-to-right: <= 3 successors), so the xi pass costs
+// T x nnz(A), not T x N^2, and the reference's xi [T,N,N] / [N,M,T,D,D] arrays still never exist.
+//   em_translist_kernel : (i, j, log a_ij) of the finite transitions, rows in arbitrary order, sorted by j inside a row
+//   em_z_kernel         : warp per frame: Z_t = lse_j(alpha + beta)  (== lse_{i,j} of the xi numerator, hmm.py:190-197);
+//                         log P(O) at last frames (hmm.py:274), pi statistics at first frames (gmmhmm.py:86), gamma output
+//   em_xi_kernel        : thread = transition, grid-stride over frames: sum_t exp(alpha[t,i] + a_ij + b[t+1,j] + beta[t+1,j] - Z_t)
+//   em_moments_kernel   : block = 32 Gaussians x a frame range: occupancies (gmmhmm.py:89-106) staged per 32 frames, S0 / S1 / S2c
+//                         (gmmhmm.py:117-147) in registers, flushed once
+//   em_discrete_kernel  : discrete emissions (hmm.py:202-225): gamma_sum and B numerators
+struct EmGen {
+    const double* alpha; const double* beta; const double* b; const int64_t* frame_off; int n_utt; int64_t total; int N;
+    double* z;          // [T] Z_t (-inf / NaN possible)
+    double* zx;         // [T] Z_t for the transition statistics: +inf at the last frame of an utterance and where Z_t is unusable
+    int* count; int* ti; int* tj; double* ta;
+};
+
+__global__ void __launch_bounds__(256) em_translist_kernel(const double* __restrict__ logA, int N, int* __restrict__ count,
+                                                           int* __restrict__ ti, int* __restrict__ tj, double* __restrict__ ta) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int row_base = 0;                                              // finite entries of row i seen so far
+    for (int j0 = 0; j0 < N; j0 += 256) {
+        const int j = j0 + tid;
+        const double a = (j < N) ? logA[(int64_t)i * N + j] : neg_inf();
+        const bool fin = (a != neg_inf()) && (a == a);
+        const unsigned m = __ballot_sync(0xffffffffu, fin);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) before += s_warp[w]; tot += s_warp[w]; }
+        if (tid == 0) s_base = tot ? atomicAdd(count, tot) : 0;
+        __syncthreads();
+        if (fin) {
+            const int pos = s_base + before + __popc(m & ((1u << lane) - 1));
+            ti[pos] = i; tj[pos] = j; ta[pos] = a;
+        }
+        row_base += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) em_z_kernel(EmGen g, double* __restrict__ pi_occ, double* __restrict__ loglik,
+                                                   double* __restrict__ n_utt_acc, double* __restrict__ gamma_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= g.total) return;
+    const int N = g.N;
+    const double* al = g.alpha + t * N;
+    const double* be = g.beta + t * N;
+    double mx = neg_inf();
+    for (int j = lane; j < N; j += 32) mx = fmax(mx, al[j] + be[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_d(mx, lane ^ o));
+    double sum = 0.0;
+    if (mx != neg_inf())
+        for (int j = lane; j < N; j += 32) { const double v = al[j] + be[j]; sum += (v == neg_inf()) ? 0.0 : exp(v - mx); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += shfl_d(sum, lane ^ o);
+    const double Z = (mx == neg_inf()) ? mx : mx + log(sum);
+    const int u = find_utt(g.frame_off, g.n_utt, t);
+    const bool first = (t == __ldg(g.frame_off + u)), last = (t == __ldg(g.frame_off + u + 1) - 1);
+    const bool usable = (Z == Z) && (Z != neg_inf());
+    if (lane == 0) {
+        g.z[t] = Z;
+        g.zx[t] = (last || !usable) ? __longlong_as_double(0x7ff0000000000000LL) : Z;
+        if (last && Z == Z) { atomicAdd(loglik, Z); atomicAdd(n_utt_acc, 1.0); }      // beta[T-1] = 0: Z = log P(O)
+    }
+    if (gamma_out || (first && !last && usable))
+        for (int j = lane; j < N; j += 32) {
+            const double ab = al[j] + be[j];
+            const double g2 = (ab == neg_inf() || !usable) ? neg_inf() : ab - Z;
+            if (gamma_out) gamma_out[t * N + j] = last ? neg_inf() : g2;               // hmm.py:199
+            if (first && !last && g2 != neg_inf()) atomicAdd(pi_occ + j, exp(g2));       // pi' = gamma[0]
+        }
+}
+
+__global__ void __launch_bounds__(256) em_xi_kernel(EmGen g, double* __restrict__ xi_sum) {
+    __shared__ __align__(16) double2 log_tab[128];
+    __shared__ double exp_tab[64];
+    fill_log_exp_tables(log_tab, exp_tab, threadIdx.x, 256);
+    __syncthreads();
+    const int e = blockIdx.y * 256 + threadIdx.x;
+    if (e >= *g.count) return;
+    const int i = g.ti[e], j = g.tj[e], N = g.N;
+    const double a = g.ta[e];
+    double sx = 0.0;
+    for (int64_t t = blockIdx.x; t + 1 < g.total; t += gridDim.x) {
+        const double zx = g.zx[t];
+        if (zx > 1e308) continue;                                    // last frame of its utterance / impossible utterance
+        const double al = g.alpha[t * N + i];
+        const double x = al + a + (g.b[(t + 1) * N + j] + g.beta[(t + 1) * N + j]) - zx;
+        sx += fast_exp_neg(x, exp_tab);                             // -inf / NaN -> 0
+    }
+    if (sx != 0.0) atomicAdd(xi_sum + (int64_t)i * N + j, sx);
+}
+
+constexpr int EMG_GT = 32;      // Gaussians per block
+constexpr int EMG_FT = 32;      // frames staged per round
+constexpr int EMG_MAXP = 8;     // (Gaussian, dim) pairs per thread: 32 * dim <= 256 * 8  ->  dim <= 64
+
+__global__ void __launch_bounds__(256) em_moments_kernel(EmGen g, const void* __restrict__ feats, int feats_f64, int ld_feats,
+                                                         const double* __restrict__ bm, const double* __restrict__ logw,
+                                                         const double* __restrict__ mu, int M, int D, int64_t frames_per_block,
+                                                         double* __restrict__ acc) {
+    __shared__ __align__(16) double2 log_tab[128];
+    __shared__ double exp_tab[64];
+    __shared__ double occ_s[EMG_FT][EMG_GT];
+    __shared__ double x_s[EMG_FT][64];
+    const int tid = threadIdx.x, N = g.N, NM = N * M;
+    fill_log_exp_tables(log_tab, exp_tab, tid, 256);
+    const int jm0 = blockIdx.y * EMG_GT;
+    const int ng = min(EMG_GT, NM - jm0);
+    const int64_t t_begin = (int64_t)blockIdx.x * frames_per_block, t_end = min(g.total, t_begin + frames_per_block);
+    double s1[EMG_MAXP], s2[EMG_MAXP], m0[EMG_MAXP];
+#pragma unroll
+    for (int k = 0; k < EMG_MAXP; ++k) {
+        const int pr = tid + 256 * k, gq = pr / D, d = pr - gq * D;
+        s1[k] = s2[k] = 0.0;
+        m0[k] = (gq < ng) ? mu[(int64_t)(jm0 + gq) * D + d] : 0.0;
+    }
+    double s0 = 0.0;
+    __syncthreads();
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += EMG_FT) {
+        const int nt = (int)min((int64_t)EMG_FT, t_end - t0);
+        // mixture occupancies for ALL t (gmmhmm.py:98-100): exp(alpha + beta - Z + log w + bm - b)
+        for (int i = tid; i < EMG_FT * EMG_GT; i += 256) {
+            const int tt = i / EMG_GT, gq = i - tt * EMG_GT;
+            double o = 0.0;
+            if (tt < nt && gq < ng) {
+                const int64_t t = t0 + tt;
+                const int jm = jm0 + gq, j = jm / M;
+                const double ab = g.alpha[t * N + j] + g.beta[t * N + j], Z = g.z[t], bj = g.b[t * N + j];
+                if (ab != neg_inf() && Z != neg_inf() && Z == Z && bj != neg_inf())
+                    o = fast_exp_neg(ab - Z + logw[jm] + bm[t * NM + jm] - bj, exp_tab);
+            }
+            occ_s[tt][gq] = o;
+        }
+        for (int i = tid; i < nt * D; i += 256) {
+            const int r = i / D, d = i - r * D;
+            const int64_t row = t0 + r;
+            x_s[r][d] = feats_f64 ? ((const double*)feats)[row * ld_feats + d] : (double)((const float*)feats)[row * ld_feats + d];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < EMG_MAXP; ++k) {
+            const int pr = tid + 256 * k, gq = pr / D, d = pr - gq * D;
+            if (gq < ng) {
+                double a1 = 0.0, a2 = 0.0;
+                for (int tt = 0; tt < nt; ++tt) {
+                    const double o = occ_s[tt][gq], x = x_s[tt][d], df = x - m0[k];
+                    a1 = fma(o, x, a1);
+                    a2 = fma(o * df, df, a2);
+                }
+                s1[k] += a1;
+                s2[k] += a2;
+            }
+        }
+        if (tid < ng)
+            for (int tt = 0; tt < nt; ++tt) s0 += occ_s[tt][tid];
+        __syncthreads();
+    }
+    double* S0 = acc;
+    double* S1 = acc + NM;
+    double* S2 = S1 + (int64_t)NM * D;
+#pragma unroll
+    for (int k = 0; k < EMG_MAXP; ++k) {
+        const int pr = tid + 256 * k, gq = pr / D, d = pr - gq * D;
+        if (gq < ng) {
+            if (s1[k] != 0.0) atomicAdd(S1 + (int64_t)(jm0 + gq) * D + d, s1[k]);
+            if (s2[k] != 0.0) atomicAdd(S2 + (int64_t)(jm0 + gq) * D + d, s2[k]);
+        }
+    }
+    if (tid < ng && s0 != 0.0) atomicAdd(S0 + jm0 + tid, s0);
+}
+
+// discrete emissions: gamma_sum[i] += exp gamma[t,i], B_sum[i, obs[t]] += exp gamma[t,i] for t < T-1 (hmm.py:202-225)
+__global__ void __launch_bounds__(256) em_discrete_kernel(EmGen g, const int32_t* __restrict__ obs, int n_symbols,
+                                                          double* __restrict__ gamma_sum, double* __restrict__ B_sum) {
+    const int N = g.N;
+    const int64_t t0 = (int64_t)blockIdx.x * 64;
+    const int nt = (int)min((int64_t)64, g.total - t0);
+    for (int i = threadIdx.x; i < N; i += 256) {
+        double gs = 0.0;
+        for (int tt = 0; tt < nt; ++tt) {
+            const int64_t t = t0 + tt;
+            const double zx = g.zx[t];
+            if (zx > 1e308) continue;                                // hmm.py:199: gamma[T-1] = -inf
+            const double ab = g.alpha[t * N + i] + g.beta[t * N + i];
+            if (ab == neg_inf()) continue;
+            const double v = exp(ab - zx);
+            gs += v;
+            const int o = obs[t];
+            if (o >= 0 && o < n_symbols && v != 0.0) atomicAdd(B_sum + (int64_t)i * n_symbols + o, v);
+        }
+        if (gs != 0.0) atomicAdd(gamma_sum + i, gs);
+    }
+}
+
+static size_t em_general_ws_bytes(int64_t total_frames, int N) {
+    return (size_t)2 * total_frames * sizeof(double) + 256 + (size_t)N * N * (2 * sizeof(int) + sizeof(double)) + 256;
+}
+
+static int em_general_prepare(EmGen& g, const double* logA, void* workspace, size_t workspace_bytes, const char* who, cudaStream_t stream) {
+    const size_t need = em_general_ws_bytes(g.total, g.N);
+    if (!workspace || workspace_bytes < need) {
+        set_error("%s: N = %d > 32 needs a workspace of %zu bytes (got %zu)", who, g.N, need, workspace_bytes);
+        return LNASR_EWORKSPACE;
+    }
+    char* w = reinterpret_cast<char*>(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
+    g.z = reinterpret_cast<double*>(w); w += g.total * sizeof(double);
+    g.zx = reinterpret_cast<double*>(w); w += g.total * sizeof(double);
+    g.count = reinterpret_cast<int*>(w); w += 16;
+    g.ta = reinterpret_cast<double*>(w); w += (size_t)g.N * g.N * sizeof(double);
+    g.ti = reinterpret_cast<int*>(w); w += (size_t)g.N * g.N * sizeof(int);
+    g.tj = reinterpret_cast<int*>(w);
+    LNASR_CUDA(cudaMemsetAsync(g.count, 0, sizeof(int), stream));
+    em_translist_kernel<<<g.N, 256, 0, stream>>>(logA, g.N, g.count, g.ti, g.tj, g.ta);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+// z / pi / loglik, then the transition statistics
+static int em_general_common(const EmGen& g, double* xi_sum, double* pi_occ, double* loglik, double* n_utt_acc, double* gamma_out,
+                             cudaStream_t stream) {
+    em_z_kernel<<<(unsigned)ceil_div(g.total, 8), 256, 0, stream>>>(g, pi_occ, loglik, n_utt_acc, gamma_out);
+    LNASR_LAUNCH_CHECK();
+    // thread = transition (at most N*N of them; the launch covers the worst case, blocks past the count exit at once),
+    // frames grid-strided so that the grid has a few waves whatever the sparsity
+    const int64_t chunks = ceil_div((int64_t)g.N * g.N, 256);
+    const int64_t chunks_sparse = ceil_div((int64_t)g.N * 4, 256);                 // the usual case: a few successors per state
+    int64_t gx = std::max<int64_t>(1, std::min<int64_t>(g.total, (int64_t)sm_count() * 16 / std::max<int64_t>(1, chunks_sparse)));
+    gx = std::min<int64_t>(gx, 65535);
+    dim3 grid((unsigned)gx, (unsigned)std::min<int64_t>(chunks, 65535));
+    em_xi_kernel<<<grid, 256, 0, stream>>>(g, xi_sum);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }
@@ -808,7 +1051,8 @@ extern "C" int lnasr_fb_accumulate(const void* feats, int feats_dtype, int32_t l
                                    size_t workspace_bytes, void* stream) {
     LNASR_CHECK_ARG(feats && b && bm && alpha && frame_offsets && logA && logw && mu && acc, "fb_accumulate: null pointer");
     LNASR_CHECK_ARG(feats_dtype == LNASR_DT_F32 || feats_dtype == LNASR_DT_F64, "fb_accumulate: feats must be float32/float64");
-    LNASR_CHECK_ARG(N >= 1 && N <= 32, "fb_accumulate: the fused kernel is built for 1 <= N <= 32 (got %d)", N);
+    LNASR_CHECK_ARG(N >= 1 && N <= 32, "fb_accumulate: the backward-fused kernels are built for 1 <= N <= 32 (got %d); larger models run "
+                    "lnasr_backward_batch + lnasr_em_statistics_ws", N);
     LNASR_CHECK_ARG(n_mix >= 1 && dim >= 1 && ld_feats >= dim && n_utt >= 0, "fb_accumulate: bad shape");
     if (n_utt == 0 || total_frames == 0) return LNASR_OK;
     FbArgs a{};
@@ -842,6 +1086,65 @@ extern "C" int lnasr_em_statistics(const void* feats, int feats_dtype, int32_t l
     return launch_stats_ab(a, beta, total_frames, (cudaStream_t)stream);
 }
 
+extern "C" size_t lnasr_em_statistics_workspace_bytes(int64_t total_frames, int32_t N) {
+    return N <= 32 ? 256 : em_general_ws_bytes(total_frames, N);
+}
+
+extern "C" int lnasr_em_statistics_ws(const void* feats, int feats_dtype, int32_t ld_feats, const double* b, const double* bm,
+                                      const double* alpha, const double* beta, const int64_t* frame_offsets, int32_t n_utt,
+                                      int64_t total_frames, const double* logA, const double* logw, const double* mu, int32_t N,
+                                      int32_t n_mix, int32_t dim, double* acc, double* gamma_out, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
+    if (N <= 32)
+        return lnasr_em_statistics(feats, feats_dtype, ld_feats, b, bm, alpha, beta, frame_offsets, n_utt, total_frames, logA, logw, mu,
+                                   N, n_mix, dim, acc, gamma_out, stream_);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LNASR_CHECK_ARG(feats && b && bm && alpha && beta && frame_offsets && logA && logw && mu && acc, "em_statistics_ws: null pointer");
+    LNASR_CHECK_ARG(feats_dtype == LNASR_DT_F32 || feats_dtype == LNASR_DT_F64, "em_statistics_ws: feats must be float32/float64");
+    LNASR_CHECK_ARG(N <= 46340 && n_mix >= 1 && dim >= 1 && dim <= 64 && ld_feats >= dim && n_utt >= 0, "em_statistics_ws: bad shape (dim <= 64)");
+    if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    EmGen g{};
+    g.alpha = alpha; g.beta = beta; g.b = b; g.frame_off = frame_offsets; g.n_utt = n_utt; g.total = total_frames; g.N = N;
+    int rc = em_general_prepare(g, logA, workspace, workspace_bytes, "em_statistics_ws", stream);
+    if (rc) return rc;
+    const int64_t NM = (int64_t)N * n_mix;
+    double* tail = acc + NM * (2 * dim + 1);                           // xi_sum[N*N] | pi_occ[N] | loglik | n_utt
+    rc = em_general_common(g, tail, tail + (int64_t)N * N, tail + (int64_t)N * N + N, tail + (int64_t)N * N + N + 1, gamma_out, stream);
+    if (rc) return rc;
+    const int64_t gtiles = ceil_div(NM, EMG_GT);
+    int64_t fsplit = std::max<int64_t>(1, std::min<int64_t>(ceil_div(total_frames, EMG_FT), (int64_t)sm_count() * 8 / std::max<int64_t>(1, gtiles)));
+    const int64_t per = ceil_div(ceil_div(total_frames, fsplit), EMG_FT) * EMG_FT;
+    fsplit = ceil_div(total_frames, per);
+    LNASR_CHECK_ARG(gtiles <= 65535, "em_statistics_ws: too many Gaussians");
+    dim3 grid((unsigned)fsplit, (unsigned)gtiles);
+    em_moments_kernel<<<grid, 256, 0, stream>>>(g, feats, feats_dtype == LNASR_DT_F64, ld_feats, bm, logw, mu, n_mix, dim, per, acc);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
+extern "C" int lnasr_hmm_em_statistics_ws(const double* b, const double* alpha, const double* beta, const int32_t* obs,
+                                          const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames, const double* logA,
+                                          int32_t N, int32_t n_symbols, double* acc, double* gamma_out, void* workspace,
+                                          size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LNASR_CHECK_ARG(b && alpha && beta && obs && frame_offsets && logA && acc, "hmm_em_statistics_ws: null pointer");
+    LNASR_CHECK_ARG(N >= 1 && N <= 46340 && n_symbols >= 1 && n_utt >= 0, "hmm_em_statistics_ws: bad shape");
+    if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    EmGen g{};
+    g.alpha = alpha; g.beta = beta; g.b = b; g.frame_off = frame_offsets; g.n_utt = n_utt; g.total = total_frames; g.N = N;
+    int rc = em_general_prepare(g, logA, workspace, workspace_bytes, "hmm_em_statistics_ws", stream);
+    if (rc) return rc;
+    // xi_sum[N*N] | gamma_sum[N] | B_sum[N*n_symbols] | pi_occ[N] | loglik | n_utt
+    double* gs = acc + (int64_t)N * N;
+    double* Bs = gs + N;
+    double* pio = Bs + (int64_t)N * n_symbols;
+    rc = em_general_common(g, acc, pio, pio + N, pio + N + 1, gamma_out, stream);
+    if (rc) return rc;
+    em_discrete_kernel<<<(unsigned)ceil_div(total_frames, 64), 256, 0, stream>>>(g, obs, n_symbols, gs, Bs);
+    LNASR_LAUNCH_CHECK();
+    return LNASR_OK;
+}
+
 extern "C" int lnasr_mstep_finalize(const double* acc, int32_t N, int32_t n_mix, int32_t dim, double min_std,
                                     double* logA, double* logpi, double* logw, double* mu, double* var, void* stream) {
     LNASR_CHECK_ARG(acc && logA && logpi && logw && mu && var, "mstep_finalize: null pointer");
@@ -857,7 +1160,8 @@ extern "C" int lnasr_hmm_fb_accumulate(const double* b, const double* alpha, con
                                        int32_t n_utt, int64_t total_frames, const double* logA, int32_t N, int32_t n_symbols,
                                        double* acc, double* gamma_out, double* beta_out, void* stream) {
     LNASR_CHECK_ARG(b && alpha && obs && frame_offsets && logA && acc, "hmm_fb_accumulate: null pointer");
-    LNASR_CHECK_ARG(N >= 1 && N <= 32, "hmm_fb_accumulate: the fused kernel is built for 1 <= N <= 32 (got %d)", N);
+    LNASR_CHECK_ARG(N >= 1 && N <= 32, "hmm_fb_accumulate: the backward-fused kernel is built for 1 <= N <= 32 (got %d); larger models run "
+                    "lnasr_backward_batch + lnasr_hmm_em_statistics_ws", N);
     LNASR_CHECK_ARG(n_symbols >= 1 && n_utt >= 0, "hmm_fb_accumulate: bad shape");
     if (n_utt == 0 || total_frames == 0) return LNASR_OK;
     FbArgs a{};

@@ -563,7 +563,7 @@ static int launch_exact(const void* feats, int ld_feats, int64_t n_frames, const
     y = (int)ceil_div(n_states, spb);
     dim3 grid((unsigned)tiles, (unsigned)y);
     const size_t smem = ((size_t)dim * GX_TILE + (size_t)2 * GX_SGROUPS * (dim + 1) * 8) * sizeof(double);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(gmm_loglik_exact_kernel<FeatT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_loglik_exact_kernel<FeatT, OutT><<<grid, GX_THREADS * GX_SGROUPS, smem, stream>>>(
         (const FeatT*)feats, ld_feats, n_frames, packed, n_states, n_mix, dim, (OutT*)b_out, ld_b, bm_out, spb);
@@ -710,7 +710,7 @@ static int launch_full(const void* feats, int ld_feats, int64_t n_frames, const 
     while (tiles * y < 2LL * sm_count() * 4 && y * 2 <= n_states) y *= 2;
     dim3 grid((unsigned)tiles, (unsigned)y);
     const size_t smem = (size_t)dim * (GX_THREADS + 1) * sizeof(double);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(gmm_loglik_full_kernel<FeatT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_loglik_full_kernel<FeatT, OutT><<<grid, GX_THREADS, smem, stream>>>(
         (const FeatT*)feats, ld_feats, n_frames, linv, nu, cst, logw, n_states, n_mix, dim, (OutT*)b_out, ld_b, bm_out);

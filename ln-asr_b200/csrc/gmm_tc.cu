@@ -98,6 +98,7 @@ constexpr int TC_KP = 80;                     // 2*39 + 1 -> 80
 constexpr int TC_KH = TC_KP / 2;              // K values per ring slot
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr float TC_LN2 = 0.6931471805599453f;
+constexpr float TC_LN2_LO = (float)(0.6931471805599453094 - (double)0.6931471805599453f);
 
 struct TcHeader {       // 512 bytes at the start of the packed image
     uint32_t magic;
@@ -114,7 +115,7 @@ static bool tc_geometry(int n_states, int n_mix, int dim, TcGeom* g) {
     if (n_states < 1 || n_mix < 1 || n_mix > 16 || dim < 1 || dim > TC_MAX_DIM) return false;
     int Mp = 1;
     while (Mp < n_mix) Mp <<= 1;
-    const int Kp = TC_KP;                                      // fixed K axis [x^2 (39) | x (39) | 1 | 0]; dims beyond `dim` are zero
+    const int Kp = TC_KP;                                      // fixed K axis [x0^2, x0, ... x38^2, x38 | 1 | 0]; dims beyond `dim` are zero
     const int gran = 16 / Mp;                                  // states per 16 accumulator columns
     // shared memory: W hi+lo = 2*NT*Kp*4, per-state constants, A ring = 4 * 128 * (Kp/2) * 4, barriers 1 KB
     const int ring = 4 * TC_BM * (Kp / 2) * 4;
@@ -254,13 +255,12 @@ __global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double
     double v = 0.0;
     if (j < n_states && m < n_mix) {
         const int64_t gi = (int64_t)j * n_mix + m;
-        if (k < TC_MAX_DIM) {
-            if (k < dim) v = -0.5 / var[gi * dim + k];
-        } else if (k < 2 * TC_MAX_DIM) {
-            const int d = k - TC_MAX_DIM;
+        if (k < 2 * TC_MAX_DIM) {
+            // K layout [x0^2, x0, x1^2, x1, ...| 1 | 0]: the two terms of a dimension adjacent (see H_KP in gmm_tc16.cu)
+            const int d = k >> 1;
             if (d < dim) {
                 const double sh = shift ? shift[d] : 0.0;
-                v = (mu[gi * dim + d] - sh) / var[gi * dim + d];
+                v = (k & 1) ? (mu[gi * dim + d] - sh) / var[gi * dim + d] : -0.5 / var[gi * dim + d];
             }
         }
         v *= 1.4426950408889634;                          // log2(e): the epilogue works in base 2
@@ -286,9 +286,10 @@ __global__ void gmm_pack_tc_kernel(const double* __restrict__ logw, const double
         if (j < n_states)
             for (int mm_ = 0; mm_ < n_mix; ++mm_) cmax = fmax(cmax, gconst(mm_));
         v = -1e30;
+        const double cmax_f = (cmax > -1e30) ? (double)(float)cmax : cmax;      // what the epilogue adds: the float32 rounding of cmax
         if (j < n_states && m < n_mix) {
             const double c = gconst(m);
-            v = (c > -1e30) ? c - cmax : -1e30;
+            v = (c > -1e30) ? c - cmax_f : -1e30;
         }
         if (m == 0) {
             float* ctab = reinterpret_cast<float*>(packed + sizeof(TcHeader) + (size_t)tile * g.tile_bytes + (size_t)2 * g.NT * g.Kp * 4);
@@ -382,7 +383,8 @@ __device__ __forceinline__ void lse_store(const float* v, const float* c_state, 
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MP; ++i) s += ex2_approx(v[g * MP + i] - mx);
-        const float r = ((mx + lg2_approx(s)) + c_state[st_local0 + g]) * TC_LN2;
+        const float bits = (mx + lg2_approx(s)) + c_state[st_local0 + g];
+        const float r = fmaf(bits, TC_LN2, bits * TC_LN2_LO);
         if (st_global0 + g < st_end) out_row[st_global0 + g] = r;
     }
 }
@@ -467,9 +469,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_tc_kernel(TcArgs a) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int k = half * KH + cc * 4 + e;          // compile-time after unrolling
-                            float v;                                        // K axis: [x^2 (39) | x (39) | 1 | 0]
-                            if (k < TC_MAX_DIM) v = x[k] * x[k];
-                            else if (k < 2 * TC_MAX_DIM) v = x[k - TC_MAX_DIM];
+                            float v;                                        // K axis: [x0^2, x0, x1^2, x1, ... | 1 | 0]
+                            if (k < 2 * TC_MAX_DIM) v = (k & 1) ? x[k >> 1] : x[k >> 1] * x[k >> 1];
                             else v = (k == 2 * TC_MAX_DIM) ? 1.f : 0.f;
                             const float hi = tf32_round(v);
                             q[e] = hi_group ? hi : (v - hi);

@@ -30,10 +30,15 @@ namespace lnasr {
 constexpr uint32_t H_MAGIC = 0x4c4e4836u;    // "LNH6"
 constexpr int H_BM = 128;                     // frames per tile (UMMA M)
 constexpr int H_MAX_DIM = 39;
-constexpr int H_KP = 80;                      // [x^2 (39) | x (39) | 1 | 0]
+constexpr int H_KP = 80;                      // [x0^2, x0, x1^2, x1, ... x38^2, x38 | 1 | 0]: the x^2 and x terms of a dimension are
+                                              // ADJACENT, so the running sums in the accumulator follow -(x-mu)^2/(2 var) dimension by
+                                              // dimension instead of first piling up all of -x^2/(2 var): the tensor core rounds its fp32
+                                              // accumulator toward zero (tools/probe_umma_rounding.py), an error proportional to the
+                                              // magnitude of the partial sums and of one sign for the likely (frame, state) pairs
 constexpr int H_XT_D = 40;
 constexpr int H_SMEM_LIMIT = 227 * 1024;
 constexpr float H_LN2 = 0.6931471805599453f;
+constexpr float H_LN2_LO = (float)(0.6931471805599453094 - (double)0.6931471805599453f);   // ln 2 - float(ln 2) = -1.9e-9: 5e-7 at |b| = 250 bits, every frame
 // output staging of the epilogue (n_mix >= 8: at most 32 states per tile): two [128 frames][33] float buffers
 constexpr int H_OUT_LD = 33;
 constexpr int H_OUT_BYTES = 2 * H_BM * H_OUT_LD * 4;
@@ -139,10 +144,13 @@ __global__ void gmm_pack_tc16_kernel(const double* __restrict__ logw, const doub
     float* ctab = reinterpret_cast<float*>(base + 2 * g.w_part);
     float* cs = reinterpret_cast<float*>(base + 2 * g.w_part + g.cst_bytes);
     if (m == 0) ctab[n / g.Mp] = (float)cmax;
+    // relative to the constant the epilogue will actually add -- the float32 ROUNDING of cmax: the residual of that rounding (up
+    // to 1e-5, fixed per state, so it would add up over the frames a path stays in the state) travels in the constant column
+    const double cmax_f = (cmax > -1e30) ? (double)(float)cmax : cmax;
     double crel = -1e30;
     if (j < n_states && m < n_mix) {
         const double c = gconst(m);
-        if (c > -1e30) crel = c - cmax;
+        if (c > -1e30) crel = c - cmax_f;
     }
     auto put = [&](int k, double v) {
         const __half hi = __float2half_rn((float)v);
@@ -169,16 +177,12 @@ __global__ void gmm_pack_tc16_kernel(const double* __restrict__ logw, const doub
     }
     const int64_t gi = (int64_t)j * n_mix + m;
     auto weight = [&](int k) -> double {
-        if (k < H_MAX_DIM) {
-            if (k >= dim) return 0.0;
-            const double p = scale ? scale[k] : 1.0;
-            return -0.5 / var[gi * dim + k] * LOG2E / (p * p);
-        }
         if (k < 2 * H_MAX_DIM) {
-            const int d = k - H_MAX_DIM;
+            const int d = k >> 1;
             if (d >= dim) return 0.0;
             const double p = scale ? scale[d] : 1.0, sh = shift ? shift[d] : 0.0;
-            return (mu[gi * dim + d] - sh) / var[gi * dim + d] * LOG2E / p;
+            if ((k & 1) == 0) return -0.5 / var[gi * dim + d] * LOG2E / (p * p);          // multiplies x'^2
+            return (mu[gi * dim + d] - sh) / var[gi * dim + d] * LOG2E / p;               // multiplies x'
         }
         return (k == 2 * H_MAX_DIM) ? crel : 0.0;
     };
@@ -205,7 +209,7 @@ __global__ void gmm_pack_tc16_kernel(const double* __restrict__ logw, const doub
 }
 
 // Feature staging, taken all the way to the MMA operand: x' = (x - shift) * scale, and per 128-frame tile the two FP16
-// slices of [x'^2 (39) | x' (39) | 1 | 0] in the UMMA canonical K-major layout ([row/8][k/8][row%8][k%8], 20 480 B each, lo
+// slices of [x'0^2, x'0, x'1^2, x'1, ... | 1 | 0] in the UMMA canonical K-major layout ([row/8][k/8][row%8][k%8], 20 480 B each, lo
 // then hi), so that the contraction kernel fetches a tile with two bulk copies.  (The first version converted the tile
 // with eight producer warps inside every CTA -- each of the ~125 W-tile CTAs streams ALL frames, so the conversion was
 // repeated 125 times.)
@@ -248,8 +252,7 @@ __global__ void __launch_bounds__(256) gmm_tc16_stage_ops_kernel(const float* __
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int k = cc * 8 + 2 * e2 + h;
-                if (k < H_MAX_DIM) { const float x = tile[row][k]; v[h] = x * x; }
-                else if (k < 2 * H_MAX_DIM) v[h] = tile[row][k - H_MAX_DIM];
+                if (k < 2 * H_MAX_DIM) { const float x = tile[row][k >> 1]; v[h] = (k & 1) ? x : x * x; }
                 else v[h] = (k == 2 * H_MAX_DIM) ? 1.f : 0.f;
                 if (s_flag[row]) v[h] = 0.f;
             }
@@ -317,7 +320,8 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
         } else {
             s = h_ex2(fmaf(v[g * MP], q, nm));
         }
-        const float r = ((h_lg2(s) - nm) + c_state[st_local0 + g]) * H_LN2;
+        const float bits = (h_lg2(s) - nm) + c_state[st_local0 + g];
+        const float r = fmaf(bits, H_LN2, bits * H_LN2_LO);
         if (st_global0 + g < st_end) out_row[st_global0 + g] = r;
     }
 }

@@ -20,6 +20,7 @@
 //
 // Tie rule: np.argmax takes the first maximum (hmm.py:166,169) -> strict '>' while scanning ascending i.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 
@@ -650,14 +651,13 @@ trellis_band_kernel(TrellisArgs a) {
 // trellis_band_kernel (a thread keeps SPT consecutive states, their trellis values and their three transition weights in
 // registers), with everything that made a time step slow taken out of it:
 //   * NO block barrier in the time loop.  A thread needs the two values below its range: inside a warp they come by
-//     __shfl_up, across warps through a small shared-memory ring with a producer / consumer counter pair, so warp w runs one
-//     step behind warp w-1 in a skewed pipeline and only ever waits for its neighbour (bar.sync made all eight warps wait
-//     for the slowest one every frame).
+//     __shfl_up, across warps through a small shared-memory ring guarded by mbarrier pairs (full / empty per slot), so warp
+//     w runs one step behind warp w-1 in a skewed pipeline and only ever waits for its neighbour (bar.sync made all eight
+//     warps wait for the slowest one every frame).
 //   * emission rows are PRIVATE: every thread cp.asyncs exactly the SPT values it will consume (PF rows ahead), so
 //     cp.async.wait_group alone makes them visible -- no barrier, and no second pass over shared memory.
-//   * backpointers are 2-BIT distance codes (0 / 1 / 2 = j - i of the chosen predecessor, 3 = "state 0", np.argmax over an
-//     all -inf column, hmm.py:166): one uint16 per thread and frame (SPT = 8) instead of eight -- 0.5 kB per frame for 2000
-//     states instead of 4 kB.
+//   * backpointers are 2-BIT distance codes (0 / 1 / 2 = j - i of the chosen predecessor): one uint16 per thread and frame
+//     (SPT = 8) instead of eight -- 0.5 kB per frame for 2000 states instead of 4 kB.
 //   * the backtrace (hmm.py:168-171) is FUSED: when the forward pass is done the CTA pulls its own backpointer rows back
 //     (L2-resident, 64 rows at a time) into the shared memory the emission ring occupied, one thread chases the pointers
 //     there (a shared-memory load per frame instead of a dependent global load), and the path leaves as coalesced rows.
@@ -665,13 +665,26 @@ trellis_band_kernel(TrellisArgs a) {
 constexpr int TB2_RING = 8;      // halo ring depth: how far a warp may run ahead of its successor
 constexpr int TB2_CH = 64;       // backpointer rows per backtrace chunk
 
-__device__ __forceinline__ int tb2_ld_flag(const int* p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-    return v;
+// mbarrier hand-off of the halo between neighbouring warps: arrive has release, try_wait acquire semantics for the shared
+// memory written before / read after, and the wait is a hardware-suspended SYNCS.PHASECHK instead of a polling loop
+__device__ __forceinline__ void tb2_bar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void tb2_st_flag(int* p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+__device__ __forceinline__ void tb2_bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void tb2_bar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 
 template <int SPT, typename BT, int PF>
@@ -683,13 +696,15 @@ trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
     constexpr int NW = TG_THREADS / 32;
     typedef typename std::conditional<SPT == 8, uint16_t, uint8_t>::type CodeT;      // SPT 2-bit codes
     static_assert(SPT % EPC == 0 && CPT >= 1, "a thread's emission values must be whole 16-byte chunks");
+    static_assert((PF & (PF - 1)) == 0 && (TB2_RING & (TB2_RING - 1)) == 0, "ring sizes must be powers of two");
     // shared memory: emission ring [PF][CPT][TG_THREADS] 16-byte chunks (re-used by the termination column and the backtrace)
     uint4* ering = reinterpret_cast<uint4*>(tg_smem);
     __shared__ double2 halo[TB2_RING][NW];
-    __shared__ int prod[NW], cons[NW];
+    __shared__ __align__(8) uint64_t h_full[TB2_RING][NW], h_empty[TB2_RING][NW];    // [slot][producer warp]
     __shared__ double red_v[NW];
     __shared__ int red_i[NW];
     __shared__ int s_last;
+    __shared__ double s_best;
     const int N = a.N;
     const int64_t p = blockIdx.x;
     const int u = (int)(p / a.n_models), k = (int)(p % a.n_models);
@@ -701,7 +716,11 @@ trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, j0 = tid * SPT;
     const bool own = j0 < N;                                   // N % SPT == 0: an owning thread owns SPT states
     const int n_wp = ((N / SPT) + 31) >> 5;                    // warps that own states
-    if (tid < NW) { prod[tid] = 0; cons[tid] = 0; }
+    if (tid < TB2_RING * NW) {
+        tb2_bar_init(&h_full[0][0] + tid);
+        tb2_bar_init(&h_empty[0][0] + tid);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     // backpointer rows: row (f0 + s) * n_models + k, bt_pitch bytes, thread t's SPT codes at t * sizeof(CodeT)
     uint8_t* bt_rows = a.bt_ws ? reinterpret_cast<uint8_t*>(a.bt_ws) + ((int64_t)f0 * a.n_models + k) * bt_pitch : nullptr;
@@ -710,18 +729,22 @@ trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
 #pragma unroll
     for (int i = 0; i < SPT; ++i) v[i] = neg_inf();
     if (wp < n_wp) {
-        const BT* src = b + f0 * a.ld_b + cbase + j0;
-        auto issue_row = [&](int s) {
-            if (own && s < T) {
-                const BT* g = src + (int64_t)s * a.ld_b;
-                uint4* dst = ering + ((s % PF) * CPT) * TG_THREADS + tid;
+        // running pointers: global emission row about to be fetched, its ring slot; the slot being consumed
+        const BT* gsrc = b + f0 * a.ld_b + cbase + j0;
+        const int64_t gstep = a.ld_b;
+        int s_issue = 0;
+        auto issue_row = [&]() {
+            if (own && s_issue < T) {
+                uint4* dst = ering + ((s_issue & (PF - 1)) * CPT) * TG_THREADS + tid;
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) tr_cp_async(dst + c * TG_THREADS, g + c * EPC, 16);
+                for (int c = 0; c < CPT; ++c) tr_cp_async(dst + c * TG_THREADS, gsrc + c * EPC, 16);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
+            gsrc += gstep;
+            ++s_issue;
         };
 #pragma unroll
-        for (int s = 0; s < PF - 1; ++s) issue_row(s);
+        for (int i = 0; i < PF - 1; ++i) issue_row();
         // transitions into my states by distance: w[i][d] = log A[j - d, j], from the ELL predecessor lists
         double w[SPT][3];
         {
@@ -744,70 +767,77 @@ trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
                     }
             }
         }
-        CodeT* btp = bt_rows ? reinterpret_cast<CodeT*>(bt_rows) + tid : nullptr;
+        CodeT* btp = (bt_rows && own) ? reinterpret_cast<CodeT*>(bt_rows) + tid : nullptr;
         const bool publish = (lane == 31) && (wp + 1 < n_wp);
-        for (int s = 0; s < T; ++s) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");     // my chunks of row s have landed
-            issue_row(s + PF - 1);                                                 // into the slot I read in step s - 1
+        const bool receive = (lane == 0) && (wp > 0);
+        auto load_e = [&](int s, double* e) {
+            const uint4* er = ering + ((s & (PF - 1)) * CPT) * TG_THREADS + tid;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const uint4 q = er[c * TG_THREADS];       // (threads past the last state read an unwritten slot: their values go nowhere)
+                if (sizeof(BT) == 4) {
+                    e[c * EPC + 0] = (double)__uint_as_float(q.x); e[c * EPC + 1] = (double)__uint_as_float(q.y);
+                    e[c * EPC + 2] = (double)__uint_as_float(q.z); e[c * EPC + 3] = (double)__uint_as_float(q.w);
+                } else {
+                    e[c * EPC + 0] = __hiloint2double((int)q.y, (int)q.x);
+                    e[c * EPC + (EPC > 1 ? 1 : 0)] = __hiloint2double((int)q.w, (int)q.z);
+                }
+            }
+        };
+        auto publish_halo = [&](int s) {                               // lane 31 of a warp with a successor
+            const int slot = s & (TB2_RING - 1);
+            tb2_bar_wait(&h_empty[slot][wp], (((uint32_t)s / TB2_RING) & 1u) ^ 1u);   // the slot's previous content has been read
+            halo[slot][wp] = make_double2(v[SPT - 2], v[SPT - 1]);
+            tb2_bar_arrive(&h_full[slot][wp]);
+        };
+        // ---- frame 0: v[0] = pi + b[:, 0]   (hmm.py:159)
+        {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");
+            issue_row();
             double e[SPT];
-            {
-                const uint4* er = ering + ((s % PF) * CPT) * TG_THREADS + tid;
+            load_e(0, e);
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    const uint4 q = own ? er[c * TG_THREADS] : make_uint4(0u, 0u, 0u, 0u);
-                    if (sizeof(BT) == 4) {
-                        e[c * EPC + 0] = (double)__uint_as_float(q.x); e[c * EPC + 1] = (double)__uint_as_float(q.y);
-                        e[c * EPC + 2] = (double)__uint_as_float(q.z); e[c * EPC + 3] = (double)__uint_as_float(q.w);
-                    } else {
-                        e[c * EPC + 0] = __hiloint2double((int)q.y, (int)q.x);
-                        e[c * EPC + (EPC > 1 ? 1 : 0)] = __hiloint2double((int)q.w, (int)q.z);
-                    }
-                }
+            for (int i = 0; i < SPT; ++i) v[i] = own ? __ldg(a.logpi + cbase + j0 + i) + e[i] : neg_inf();
+            if (publish) publish_halo(0);
+            if (btp) { *btp = (CodeT)0; btp = reinterpret_cast<CodeT*>(reinterpret_cast<uint8_t*>(btp) + bt_step); }
+        }
+        for (int s = 1; s < T; ++s) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");     // my chunks of row s have landed
+            issue_row();                                                           // into the slot I read in step s - 1
+            double e[SPT];
+            load_e(s, e);
+            // the two values below my range at step s - 1: my left neighbour's top two states
+            double2 h;
+            h.x = __shfl_up_sync(0xffffffffu, v[SPT - 2], 1);
+            h.y = __shfl_up_sync(0xffffffffu, v[SPT - 1], 1);
+            if (lane == 0) h = make_double2(neg_inf(), neg_inf());
+            if (receive) {
+                const int slot = (s - 1) & (TB2_RING - 1);
+                tb2_bar_wait(&h_full[slot][wp - 1], ((uint32_t)(s - 1) / TB2_RING) & 1u);     // warp wp-1 has published step s - 1
+                h = halo[slot][wp - 1];
+                tb2_bar_arrive(&h_empty[slot][wp - 1]);
             }
+            __syncwarp();
+            // descending i: v[i] is overwritten after the states above it have read it.  Codes: distance 0 / 1 / 2 to the chosen
+            // predecessor, FIRST maximum in ascending predecessor order (np.argmax, hmm.py:166).  A column with no finite
+            // candidate keeps code 2: such a state is never on a path that ends in a finite score, and an utterance whose
+            // every final score is -inf is handled in the backtrace.
             uint32_t code = 0;
-            if (s == 0) {
 #pragma unroll
-                for (int i = 0; i < SPT; ++i) v[i] = own ? __ldg(a.logpi + cbase + j0 + i) + e[i] : neg_inf();
-            } else {
-                // the two values below my range at step s - 1: my left neighbour's top two states
-                double2 h;
-                h.x = __shfl_up_sync(0xffffffffu, v[SPT - 2], 1);
-                h.y = __shfl_up_sync(0xffffffffu, v[SPT - 1], 1);
-                if (lane == 0) {
-                    if (wp > 0) {
-                        while (tb2_ld_flag(&prod[wp - 1]) < s) { }                 // warp wp-1 has published step s - 1
-                        h = halo[(s - 1) % TB2_RING][wp - 1];
-                        tb2_st_flag(&cons[wp], s);                                 // slot (s - 1) % RING may be overwritten
-                    } else {
-                        h = make_double2(neg_inf(), neg_inf());
-                    }
-                }
-                __syncwarp();
-                // descending i: v[i] is overwritten after the states above it have read it
-#pragma unroll
-                for (int i = SPT - 1; i >= 0; --i) {
-                    const double p2 = (i >= 2) ? v[i - 2] : (i == 1 ? h.y : h.x);
-                    const double p1 = (i >= 1) ? v[i - 1] : h.y;
-                    double best = p2 + w[i][2];
-                    uint32_t dist = 2;
-                    const double c1 = p1 + w[i][1];
-                    if (c1 > best) { best = c1; dist = 1; }                        // ascending predecessor index: first max
-                    const double c0 = v[i] + w[i][0];
-                    if (c0 > best) { best = c0; dist = 0; }
-                    if (__double2hiint(best) == (int)0xfff00000 && __double2loint(best) == 0) dist = 3;   // all -inf: np.argmax gives 0
-                    code |= dist << (2 * i);
-                    v[i] = best + e[i];
-                }
+            for (int i = SPT - 1; i >= 0; --i) {
+                const double p2 = (i >= 2) ? v[i - 2] : (i == 1 ? h.y : h.x);
+                const double p1 = (i >= 1) ? v[i - 1] : h.y;
+                double best = p2 + w[i][2];
+                uint32_t dist = 2u << (2 * i);
+                const double c1 = p1 + w[i][1];
+                if (c1 > best) { best = c1; dist = 1u << (2 * i); }
+                const double c0 = v[i] + w[i][0];
+                if (c0 > best) { best = c0; dist = 0u; }
+                code |= dist;
+                v[i] = best + e[i];
             }
-            if (publish) {
-                while (tb2_ld_flag(&cons[wp + 1]) < s - TB2_RING + 1) { }          // the slot's previous content has been read
-                halo[s % TB2_RING][wp] = make_double2(v[SPT - 2], v[SPT - 1]);
-                tb2_st_flag(&prod[wp], s + 1);
-            }
-            if (btp && own) {
-                *btp = (CodeT)code;
-                btp = reinterpret_cast<CodeT*>(reinterpret_cast<uint8_t*>(btp) + bt_step);
-            }
+            if (publish) publish_halo(s);
+            if (btp) { *btp = (CodeT)code; btp = reinterpret_cast<CodeT*>(reinterpret_cast<uint8_t*>(btp) + bt_step); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
@@ -840,12 +870,20 @@ trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
             if (a.score_out) a.score_out[p] = best;
             if (a.last_state) a.last_state[p] = arg;
             s_last = arg;
+            s_best = best;
         }
         __syncthreads();
     }
     if (!a.path_out || !bt_rows) return;
     // ---- fused backtrace: path[T-1] = argmax v[T-1]; path[t] = bt[t+1, path[t+1]]                    (hmm.py:168-171)
     uint32_t* out = a.path_out + (int64_t)k * a.total_frames + f0;
+    if (!(s_best > neg_inf())) {
+        // no state has a finite score at the last frame (or NaN emissions): path[T-1] = 0 and, in a band, state 0 has itself as
+        // its only predecessor, so np.argmax returns 0 at every earlier frame whether column 0 is finite (its one candidate) or
+        // not (all -inf -> 0): the reference's path is all zeros
+        for (int i = tid; i < T; i += TG_THREADS) out[i] = 0u;
+        return;
+    }
     uint8_t* stage = tg_smem;                                  // [TB2_CH][bt_pitch]
     uint32_t* pst = reinterpret_cast<uint32_t*>(tg_smem + (size_t)TB2_CH * bt_pitch);   // [TB2_CH] states of frames lo-1 .. hi-1
     int st = s_last;                                           // state at frame hi (thread 0 carries it across chunks)
@@ -862,8 +900,7 @@ trellis_band2_kernel(TrellisArgs a, int bt_pitch) {
         if (tid == 0) {
             for (int r = hi; r >= lo; --r) {
                 const CodeT cw = reinterpret_cast<const CodeT*>(stage + (size_t)(r - lo) * bt_pitch)[st / SPT];
-                const int code = ((int)cw >> (2 * (st % SPT))) & 3;
-                st = (code == 3) ? 0 : st - code;
+                st -= ((int)cw >> (2 * (st % SPT))) & 3;
                 pst[r - lo] = (uint32_t)st;                    // the state of frame r - 1
             }
         }
@@ -1026,7 +1063,7 @@ static int launch_general(const TrellisArgs& a, cudaStream_t stream) {
     const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
     const size_t smem = 2 * (size_t)a.N * sizeof(double);
     if (smem > 200 * 1024) { set_error("trellis: N=%d does not fit the shared-memory column buffers", a.N); return LNASR_EINVAL; }
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(trellis_general_kernel<BT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trellis_general_kernel<BT, MODE><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a);
     LNASR_LAUNCH_CHECK();
@@ -1039,7 +1076,7 @@ static int launch_reg(const TrellisArgs& a, cudaStream_t stream) {
     const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
     const size_t n_pad = ((size_t)a.N + 3) & ~(size_t)3;
     const size_t smem = 2 * (size_t)a.N * sizeof(double) + (size_t)PF * n_pad * sizeof(BT);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(trellis_reg_kernel<SPT, BT, MODE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trellis_reg_kernel<SPT, BT, MODE, PF><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a);
     LNASR_LAUNCH_CHECK();
@@ -1052,7 +1089,7 @@ static int launch_band(const TrellisArgs& a, cudaStream_t stream) {
     const int64_t n_pairs = (int64_t)a.n_utt * a.n_models;
     const size_t n_pad = ((size_t)a.N + 3) & ~(size_t)3;
     const size_t smem = n_pad * sizeof(double) + 2 * TG_THREADS * sizeof(double2) + (size_t)PF * n_pad * sizeof(BT);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(trellis_band_kernel<SPT, BT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trellis_band_kernel<SPT, BT, PF><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a);
     LNASR_LAUNCH_CHECK();
@@ -1061,7 +1098,8 @@ static int launch_band(const TrellisArgs& a, cudaStream_t stream) {
 
 // backpointer row pitch of trellis_band2_kernel: one code word per owning thread, rounded up to whole 16-byte vectors
 static inline int band2_pitch(int N, int spt) { return ((N / spt) * (spt / 4) + 15) / 16 * 16; }
-static int g_band_version = 2;                                   // lnasr_debug_set_band_kernel: 1 = trellis_band_kernel + backtrace_kernel
+// lnasr_debug_set_band_kernel / environment LNASR_BAND_KERNEL: 1 = trellis_band_kernel + backtrace_kernel
+static int g_band_version = []() { const char* e = getenv("LNASR_BAND_KERNEL"); return (e && e[0] == '1') ? 1 : 2; }();
 
 // does the decode of this call run on trellis_band2_kernel (which also backtraces)?
 static bool band2_eligible(const void* b, int b_dtype, int64_t ld_b, const lnasr_hmm_bank* bank, bool plain_decode) {
@@ -1083,7 +1121,7 @@ static int launch_band2(const TrellisArgs& a, cudaStream_t stream) {
     size_t smem = (size_t)PF * (SPT * sizeof(BT)) * TG_THREADS;                    // the private emission ring
     smem = std::max(smem, (size_t)a.N * sizeof(double));                             // termination column
     smem = std::max(smem, (size_t)TB2_CH * pitch + TB2_CH * sizeof(uint32_t));       // backtrace staging
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         LNASR_CUDA(cudaFuncSetAttribute(trellis_band2_kernel<SPT, BT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trellis_band2_kernel<SPT, BT, PF><<<(unsigned)n_pairs, TG_THREADS, smem, stream>>>(a, pitch);
     LNASR_LAUNCH_CHECK();

@@ -83,6 +83,9 @@ SIGNATURES = {
     "lnasr_fb_workspace_bytes": (sz, [i64, i32]),
     "lnasr_fb_accumulate": (C.c_int, [vp, C.c_int, i32, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
     "lnasr_em_statistics": (C.c_int, [vp, C.c_int, i32, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp]),
+    "lnasr_em_statistics_workspace_bytes": (sz, [i64, i32]),
+    "lnasr_em_statistics_ws": (C.c_int, [vp, C.c_int, i32, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]),
+    "lnasr_hmm_em_statistics_ws": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, sz, vp]),
     "lnasr_mstep_finalize": (C.c_int, [vp, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]),
     "lnasr_hmm_acc_doubles": (i64, [i32, i32]),
     "lnasr_hmm_fb_accumulate": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, vp]),

@@ -95,6 +95,9 @@ class ModelBank:
             raise ValueError("emission must be 'exact', 'tc', 'tc16' or 'auto'")
         self.emission = emission
         self._tc = None
+        if emission in ("tc", "tc16") and self.gmm.full:
+            raise _capi.LnasrError("the tensor-core emission kernels score DIAGONAL covariances; this bank has full `si` matrices "
+                                   "(a model trained by the reference's train() is full-covariance): use emission='exact'")
         if emission in ("tc", "tc16"):
             from .gmm_tc import PackedGmmTC
             self._tc = PackedGmmTC(w, mu, cv if cv.ndim == 3 else np.diagonal(cv, axis1=2, axis2=3),
@@ -289,6 +292,9 @@ class AcousticPipeline:
             tb = self.mfcc._device_tables()
             bank = self.bank
             tc = bank._tc is not None
+            if not tc and bank.gmm.full:
+                raise _capi.LnasrError("lnasr_recognize_batch chains the diagonal-covariance emission kernels; a full-covariance bank "
+                                       "is scored by the staged path (AcousticPipeline.recognize_batch)")
             packed = bank._tc.packed if tc else bank.gmm.packed
             rec = _capi.Recognizer(mfcc=C.pointer(tb), bank=C.pointer(bank.trans.struct), gmm_packed=packed.data_ptr(),
                                    gmm_kind=(2 if bank._tc.fmt == "f16" else 1) if tc else 0, n_mix=bank.m, dim=bank.d)

@@ -4,7 +4,7 @@
 iteration makes a host round trip.  `EmTrainer` keeps the model ON THE DEVICE for the whole run; one iteration is
 
     lnasr_gmm_pack_exact -> lnasr_gmm_loglik_exact (b, bm) -> lnasr_forward_batch (alpha) || lnasr_backward_batch (beta, on a
-    side stream) -> lnasr_em_statistics (frame-parallel: gamma, xi, occupancies, S0/S1/S2c)
+    side stream) -> lnasr_em_statistics_ws (frame-parallel: gamma, xi, occupancies, S0/S1/S2c; any number of states)
     -> [all-reduce of the packed float64 accumulator over ranks] -> lnasr_mstep_finalize (in place)
 
 with no host synchronisation, so iterations can be queued back to back and the only multi-GPU traffic is the
@@ -32,10 +32,13 @@ class EmTrainer:
         if isinstance(model, dict) and "var" in model:
             var = np.asarray(model["var"], dtype=np.float64)
         else:
-            var = np.diagonal(np.asarray(get("si"), dtype=np.float64), axis1=2, axis2=3).copy()
+            si = np.asarray(get("si"), dtype=np.float64)
+            var = np.diagonal(si, axis1=2, axis2=3).copy()
+            d_ = si.shape[-1]
+            if np.any(si.reshape(-1, d_ * d_)[:, np.flatnonzero(~np.eye(d_, dtype=bool).reshape(-1))] != 0.0):
+                raise _capi.LnasrError("EmTrainer trains diagonal-covariance models: `si` has non-zero off-diagonal entries "
+                                       "(pass var = diag(si) explicitly to project, or score with ModelBank(emission='exact'))")
         self.n, self.m, self.d = var.shape
-        if self.n > 32:
-            raise _capi.LnasrError("EmTrainer: the fused Baum-Welch kernel is built for n <= 32 states")
         self.min_std = float(min_std if min_std is not None else (0.01 if isinstance(model, dict) else model.min_std))
         self.logA = _dev.to_dev(np.asarray(get("A"), dtype=np.float64), t.float64)
         self.logpi = _dev.to_dev(np.asarray(get("pi"), dtype=np.float64).reshape(-1), t.float64)
@@ -45,8 +48,22 @@ class EmTrainer:
         lib = _capi.lib()
         self.packed = _dev.empty((int(lib.lnasr_gmm_exact_packed_doubles(self.n, self.m, self.d)),), t.float64)
         self.acc = _dev.zeros((int(lib.lnasr_em_acc_doubles(self.n, self.m, self.d)),), t.float64)
+        # n > 32: the trellis passes read ELL lists of the finite transitions, re-packed from the device-resident log A at every
+        # iteration.  EM never turns an impossible transition into a possible one, so the initial in / out degrees bound them.
+        self._ell = None
+        max_in = max_out = 0
+        if self.n > 32:
+            deg = _dev.zeros((4,), t.int32)
+            _capi.check(lib.lnasr_trans_degree(_capi.ptr(self.logA), 1, self.n, _capi.ptr(deg), _capi.stream_ptr()), "trans_degree")
+            d_in, d_out, _, _ = (int(v) for v in deg.cpu().tolist())
+            max_in, max_out = max(1, d_in), max(1, d_out)
+            self._ell = (_dev.empty((1, max_in, self.n), t.int32), _dev.empty((1, max_in, self.n), t.float64),
+                         _dev.empty((1, max_out, self.n), t.int32), _dev.empty((1, max_out, self.n), t.float64))
+        e = self._ell
         self._bank = _capi.HmmBank(n_models=1, N=self.n, logA=self.logA.data_ptr(), logpi=self.logpi.data_ptr(),
-                                   max_in=0, max_out=0, pred_idx=0, pred_val=0, succ_idx=0, succ_val=0, band=0)
+                                   max_in=max_in, max_out=max_out, pred_idx=e[0].data_ptr() if e else 0,
+                                   pred_val=e[1].data_ptr() if e else 0, succ_idx=e[2].data_ptr() if e else 0,
+                                   succ_val=e[3].data_ptr() if e else 0, band=0)
         self._x = None
 
     def load_batch(self, feats, frame_offsets):
@@ -62,6 +79,8 @@ class EmTrainer:
         self._alpha = _dev.empty((T, self.n), t.float64)
         self._lp = _dev.empty((self._n_utt, 1), t.float64)
         self._beta = _dev.empty((T, self.n), t.float64)
+        self._ws_bytes = int(_capi.lib().lnasr_em_statistics_workspace_bytes(T, self.n))
+        self._ws = _dev.empty((self._ws_bytes,), t.uint8)
         self._side = t.cuda.Stream()
         return self
 
@@ -75,6 +94,10 @@ class EmTrainer:
         _capi.check(lib.lnasr_gmm_pack_exact(ptr(self.logw), ptr(self.mu), ptr(self.var), n, m, d, ptr(self.packed), st), "gmm_pack_exact")
         _capi.check(lib.lnasr_gmm_loglik_exact(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), T, ptr(self.packed), n, m, d,
                                                ptr(self._b), _capi.DT_F64, n, ptr(self._bm), st), "gmm_loglik_exact")
+        if self._ell is not None:
+            e = self._ell
+            _capi.check(lib.lnasr_trans_pack(ptr(self.logA), 1, n, self._bank.max_in, self._bank.max_out, ptr(e[0]), ptr(e[1]),
+                                             ptr(e[2]), ptr(e[3]), st), "trans_pack")
         # the two recursions are independent: backward on a side stream, forward here; everything else is frame-parallel
         t = _dev.torch()
         main = t.cuda.current_stream()
@@ -85,9 +108,10 @@ class EmTrainer:
                                             C.byref(self._bank), ptr(self._alpha), ptr(self._lp), st), "forward_batch")
         self.acc.zero_()
         main.wait_stream(self._side)
-        _capi.check(lib.lnasr_em_statistics(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), ptr(self._b), ptr(self._bm),
-                                            ptr(self._alpha), ptr(self._beta), ptr(self._off_d), self._n_utt, T, ptr(self.logA),
-                                            ptr(self.logw), ptr(self.mu), n, m, d, ptr(self.acc), None, st), "em_statistics")
+        _capi.check(lib.lnasr_em_statistics_ws(ptr(x), _dev.np_dtype_code(x.dtype), x.stride(0), ptr(self._b), ptr(self._bm),
+                                               ptr(self._alpha), ptr(self._beta), ptr(self._off_d), self._n_utt, T, ptr(self.logA),
+                                               ptr(self.logw), ptr(self.mu), n, m, d, ptr(self.acc), None, ptr(self._ws),
+                                               self._ws_bytes, st), "em_statistics_ws")
         if reduce_fn is not None:
             reduce_fn(self.acc)                       # SUM over ranks of S0 | S1 | S2c | xi_sum | pi_occ | loglik | n_utt
         loglik = self.acc[-2:-1].clone()

@@ -72,8 +72,7 @@ class GMMHMM(HMM):
 
     def _packed(self) -> PackedGmm:
         w, mu, si = np.asarray(self.w), np.asarray(self.mu), np.asarray(self.si)
-        key = (id(self.w), id(self.mu), id(self.si), w.shape, mu.shape, si.shape,
-               float(np.sum(w)), float(np.sum(mu)), float(np.sum(si)))
+        key = self._content_key(w, mu, si)                 # content hash: in-place edits of w / mu / si are seen
         if self._gmm is None or self._gmm_key != key:
             self._gmm = PackedGmm(w, mu, si)
             self._gmm_key = key
@@ -109,6 +108,23 @@ class GMMHMM(HMM):
         t = _dev.torch()
         g = self._packed()
         lib = _capi.lib()
+        if g.full and not getattr(self, "_warned_full", False):
+            import warnings
+            warnings.warn("GMMHMM re-estimation is built for diagonal covariance: the scatter statistics keep diag(Sigma') only "
+                          "(the reference's train() returns the full matrix, gmmhmm.py:138-147); the off-diagonals of `si` are "
+                          "used for scoring and dropped by the update", RuntimeWarning, stacklevel=3)
+            self._warned_full = True
+        if self.n > 32:
+            # backward trellis pass (any n, ELL transition lists) + the frame-parallel general statistics kernels
+            beta = self._trans().backward(b, f_off_d, n_utt, total)
+            nbytes = int(lib.lnasr_em_statistics_workspace_bytes(total, self.n))
+            ws = _dev.empty((nbytes,), t.uint8)
+            _capi.check(lib.lnasr_em_statistics_ws(
+                _capi.ptr(x_d), _dev.np_dtype_code(x_d.dtype), x_d.stride(0), _capi.ptr(b), _capi.ptr(bm), _capi.ptr(alpha),
+                _capi.ptr(beta), _capi.ptr(f_off_d), n_utt, total, _capi.ptr(self._trans().logA), _capi.ptr(g.logw_d),
+                _capi.ptr(g.mu_d), self.n, self.m, self.d, _capi.ptr(acc), None, _capi.ptr(ws), nbytes, _capi.stream_ptr()),
+                "em_statistics_ws")
+            return
         if split is None:
             split = self._fb_split if self._fb_split is not None else n_utt >= 8
         ws, ws_bytes = None, 0
@@ -156,6 +172,18 @@ class GMMHMM(HMM):
         self.mu = model["mu"]
         self.si = model["si"]
         self.w = model["w"]
+        self._drop_emission_cache()
+
+    def _drop_emission_cache(self):
+        self._b_np = self._b_dev = self._bm_np = self._bm_dev = None
+
+    def _remember_emissions(self, obs_list, b, bm=None):
+        if len(obs_list) == 1:
+            self._b_np, self._b_dev = None, b
+            self._bm_np, self._bm_dev = None, bm
+
+    def _empty_obs(self):
+        return np.zeros((0, self.d), dtype=self._obs_np_dtype)
 
     def reset(self, init_type):
         """'uniform' or 'random' initial parameters, same draw order as the reference (gmmhmm.py:166-188)."""

@@ -8,6 +8,7 @@ arguments and return shapes; results are numpy arrays of dtype `precision`.  Add
 """
 from __future__ import annotations
 
+import zlib
 from typing import List, Sequence
 
 import numpy as np
@@ -56,10 +57,37 @@ class HMM:
         return self._b_dev
 
     # ------------------------------------------------------------------ device views of the parameters
+    @staticmethod
+    def _content_key(*arrays):
+        """Cache key from the CONTENT of the parameter arrays (shape + CRC-32 + Adler-32 of the bytes): an in-place edit such as
+        h.A[i, j] = -inf, or a new array that happens to reuse a freed object's id, must not leave stale device copies behind."""
+        key = []
+        for a in arrays:
+            a = np.ascontiguousarray(a)
+            if a.nbytes > (64 << 20):
+                # very large parameter arrays (a 2000-state full `si` is 390 MB): hash ~1M evenly spaced elements plus the
+                # object's identity; an in-place edit that misses every sampled element needs an explicit invalidate()
+                flat = a.reshape(-1)
+                sample = np.ascontiguousarray(flat[::max(1, flat.size >> 20)])
+                buf = sample.view(np.uint8)
+                key.append((a.shape, a.dtype.str, id(a), zlib.crc32(buf), zlib.adler32(buf)))
+                continue
+            buf = a.view(np.uint8).reshape(-1) if a.size else b""
+            key.append((a.shape, a.dtype.str, zlib.crc32(buf), zlib.adler32(buf)))
+        return tuple(key)
+
+    def invalidate(self):
+        """Drop every cached device copy of the parameters and emissions (they are re-derived from the numpy attributes on
+        the next call).  Needed only after an in-place edit of a parameter array larger than 64 MB."""
+        self._bank = self._bank_key = None
+        self._drop_emission_cache()
+        if hasattr(self, "_gmm"):
+            self._gmm = self._gmm_key = None
+
     def _trans(self) -> TransitionBank:
         A = np.asarray(self.A, dtype=np.float64)
         pi = np.asarray(self.pi, dtype=np.float64).reshape(-1)
-        key = (A.tobytes(), pi.tobytes()) if A.size <= 4096 else (id(self.A), id(self.pi), A.shape)
+        key = self._content_key(A, pi)
         if self._bank is None or self._bank_key != key:
             self._bank = TransitionBank(A, pi)
             self._bank_key = key
@@ -141,8 +169,20 @@ class HMM:
         return int(_capi.lib().lnasr_hmm_acc_doubles(self.n, self.m))
 
     def _accumulate(self, obs_d, b, bm, alpha, f_off_d, n_utt, total, acc):
-        """Fused backward + statistics of a batch into `acc` (csrc/em.cu)."""
-        _capi.check(_capi.lib().lnasr_hmm_fb_accumulate(
+        """Baum-Welch statistics of a batch into `acc` (csrc/em.cu): the backward-fused kernel for n <= 32, else the backward
+        trellis pass (any n, ELL transition lists) + the frame-parallel general statistics kernels."""
+        t = _dev.torch()
+        lib = _capi.lib()
+        if self.n > 32:
+            beta = self._trans().backward(b, f_off_d, n_utt, total)
+            nbytes = int(lib.lnasr_em_statistics_workspace_bytes(total, self.n))
+            ws = _dev.empty((nbytes,), t.uint8)
+            _capi.check(lib.lnasr_hmm_em_statistics_ws(
+                _capi.ptr(b), _capi.ptr(alpha), _capi.ptr(beta), _capi.ptr(obs_d), _capi.ptr(f_off_d), n_utt, total,
+                _capi.ptr(self._trans().logA), self.n, self.m, _capi.ptr(acc), None, _capi.ptr(ws), nbytes, _capi.stream_ptr()),
+                "hmm_em_statistics_ws")
+            return
+        _capi.check(lib.lnasr_hmm_fb_accumulate(
             _capi.ptr(b), _capi.ptr(alpha), _capi.ptr(obs_d), _capi.ptr(f_off_d), n_utt, total,
             _capi.ptr(self._trans().logA), self.n, self.m, _capi.ptr(acc), None, None, _capi.stream_ptr()),
             "hmm_fb_accumulate")
@@ -173,6 +213,11 @@ class HMM:
         self.A = model["A"]
         self.B = model["B"]
         self.pi = model["pi"]
+        self._drop_emission_cache()
+
+    def _drop_emission_cache(self):
+        """Emissions cached under the OLD parameters must not feed a later _forward(obs) / _backward(obs) without remap."""
+        self._b_np = self._b_dev = None
 
     def reset(self, init_type):
         """'uniform' or 'random' initial parameters (hmm.py:233-250); random draws lie in (0, 1] so no log(0)."""
@@ -225,17 +270,34 @@ class HMM:
         """-> (observations concatenated on the device, host offsets, device offsets)."""
         t = _dev.torch()
         cat, off = _dev.pack_ragged(obs_list, self._obs_np_dtype)
+        if len(obs_list) == 0:
+            cat = self._empty_obs()
         return self._obs_device(cat), off, _dev.to_dev(off, t.int64)
+
+    def _empty_obs(self):
+        return np.zeros((0,), dtype=self._obs_np_dtype)
+
+    def _remember_emissions(self, obs_list, b, bm=None):
+        """The reference's calc_prob / decode / train run _forward(obs, True) / _viterbi(obs, True), which leave self.b (and
+        self.bm) filled as a side effect (hmm.py:82-83, 154-155): keep that for the single-sequence calls."""
+        if len(obs_list) == 1:
+            self._b_np, self._b_dev = None, b
 
     def calc_prob_batch(self, obs_list: Sequence) -> np.ndarray:
         x_d, off, off_d = self._pack(obs_list)
-        b, _ = self._emissions_dev(x_d)
+        if int(off[-1]) == 0:
+            return np.full(len(off) - 1, -np.inf)
+        b, bm = self._emissions_dev(x_d, want_bm=len(obs_list) == 1)
+        self._remember_emissions(obs_list, b, bm)
         _, lp = self._trans().forward(b, off_d, len(off) - 1, int(off[-1]))
         return lp[:, 0].cpu().numpy()
 
     def decode_batch(self, obs_list: Sequence) -> List[np.ndarray]:
         x_d, off, off_d = self._pack(obs_list)
-        b, _ = self._emissions_dev(x_d)
+        if int(off[-1]) == 0:
+            return [np.zeros(0, dtype=np.uint32) for _ in range(len(off) - 1)]
+        b, bm = self._emissions_dev(x_d, want_bm=len(obs_list) == 1)
+        self._remember_emissions(obs_list, b, bm)
         r = self._trans().viterbi(b, off_d, len(off) - 1, int(off[-1]), want_path=True, want_score=False)
         return _dev.split_ragged(r["path"][0].cpu().numpy().astype(np.uint32), off)
 
@@ -243,10 +305,11 @@ class HMM:
         """One E+M step over a batch; returns (model dict, total log-likelihood before the update)."""
         t = _dev.torch()
         n_utt, total = len(off) - 1, int(off[-1])
-        b, bm = self._emissions_dev(x_d, want_bm=True)
-        alpha, _ = self._trans().forward(b, off_d, n_utt, total, want_alpha=True)
         acc = _dev.zeros((self._acc_size(),), t.float64)
-        self._accumulate(x_d, b, bm, alpha, off_d, n_utt, total, acc)
+        if total > 0:                                     # a rank whose shard is empty still enters the collective below
+            b, bm = self._emissions_dev(x_d, want_bm=True)
+            alpha, _ = self._trans().forward(b, off_d, n_utt, total, want_alpha=True)
+            self._accumulate(x_d, b, bm, alpha, off_d, n_utt, total, acc)
         if reduce_fn is not None:
             reduce_fn(acc)
         loglik = float(acc[-2].item())
@@ -270,9 +333,15 @@ class HMM:
         return history
 
     def _total_loglik(self, x_d, off, off_d, reduce_fn=None) -> float:
-        b, _ = self._emissions_dev(x_d)
-        _, lp = self._trans().forward(b, off_d, len(off) - 1, int(off[-1]))
-        s = lp.sum().reshape(1)
+        t = _dev.torch()
+        if int(off[-1]) > 0:
+            b, bm = self._emissions_dev(x_d, want_bm=len(off) == 2)
+            if len(off) == 2:
+                self._remember_emissions([None], b, bm)      # train() ends on calc_prob(obs) of the new model (hmm.py:303)
+            _, lp = self._trans().forward(b, off_d, len(off) - 1, int(off[-1]))
+            s = lp.sum().reshape(1)
+        else:
+            s = _dev.zeros((1,), t.float64)
         if reduce_fn is not None:
             reduce_fn(s)
         return float(s.item())

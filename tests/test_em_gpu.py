@@ -155,3 +155,95 @@ def test_device_resident_em_trainer_matches_oracle(n, mix, d, n_utt):
         assert_close(np.exp(got["A"]), np.exp(ref["A"]), 1e-7, "A")
         assert_close(np.exp(got["pi"]), np.exp(ref["pi"]), 1e-7, "pi")
     assert got["si"].shape == (n, mix, d, d) and len(hist) == 3
+
+
+@pytest.mark.parametrize("n,mix,d,ltr", [(200, 4, 39, True), (40, 3, 39, False), (33, 1, 5, False), (70, 2, 13, True)])
+def test_baum_welch_beyond_thirty_two_states(n, mix, d, ltr):
+    """HMM.train (hmm.py:285-313) / GMMHMM._estimate (gmmhmm.py:69-156) take any n: above 32 states the backward pass is a plain
+    trellis pass (ELL transition lists) and the statistics come from the general frame-parallel kernels (compact transition
+    list, accumulators in global memory).  GMMHMM.train_batch and the device-resident EmTrainer against the oracle's
+    multi-utterance EM: left-to-right (sparse) and dense transition matrices, one-frame and two-frame utterances."""
+    import torch
+    from lnasr.em import EmTrainer
+    from lnasr.gmmhmm import GMMHMM
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(5 * n + mix)
+    mdl = O.random_gmmhmm(n, mix, d, rng, left_to_right=ltr)
+    lens = [47, 1, 33, 2, 60] if n <= 70 else [41, 1, 30]
+    utts = [0.6 * rng.standard_normal((T, d)) for T in lens]
+    with np.errstate(all="ignore"):
+        new_ref, tot = O.em_step_multi_diag(utts, mdl)
+    m = GMMHMM(n, mix, d, A=mdl["A"], pi=mdl["pi"], w=mdl["w"], mu=mdl["mu"], si=mdl["var"][..., None] * np.eye(d))
+    hist = m.train_batch(utts, iters=1, verbose=False)
+    assert abs(hist[0][0] - tot["loglik"]) < 1e-8 * abs(tot["loglik"])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    tr = EmTrainer(mdl).load_batch(torch.from_numpy(np.concatenate(utts)).cuda(), off)
+    ll = float(tr.iterate().item())
+    assert abs(ll - tot["loglik"]) < 1e-8 * abs(tot["loglik"])
+    got = tr.export()
+    for name, mu_, var_, w_, A_, pi_ in (("train_batch", m.mu, m.var, m.w, m.A, m.pi),
+                                         ("EmTrainer", got["mu"], got["var"], got["w"], got["A"], got["pi"])):
+        assert_close(mu_, new_ref["mu"], 1e-8, name + " mu")                 # bar: 1e-4 relative
+        assert_close(var_, new_ref["var"], 1e-8, name + " var")
+        with np.errstate(all="ignore"):
+            assert_close(np.exp(w_), np.exp(new_ref["w"]), 1e-8, name + " w")
+            assert_close(np.exp(A_), np.exp(new_ref["A"]), 1e-8, name + " A", per_column=False)
+            assert_close(np.exp(pi_), np.exp(new_ref["pi"]), 1e-8, name + " pi")
+    # a second iteration runs on the re-packed transition lists of the updated model
+    ll2 = float(tr.iterate().item())
+    with np.errstate(all="ignore"):
+        _, tot2 = O.em_step_multi_diag(utts, new_ref)
+    assert abs(ll2 - tot2["loglik"]) < 1e-7 * abs(tot2["loglik"]) and ll2 >= ll - 1e-6
+
+
+def test_discrete_hmm_training_beyond_thirty_two_states():
+    """Plain HMM._estimate (hmm.py:202-225) with 48 states and 10 symbols: one Baum-Welch step against the oracle."""
+    from lnasr.hmm import HMM
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(48)
+    n, m, T = 48, 10, 90
+    np.random.seed(4)
+    h = HMM(n, m)
+    h.reset("random")
+    A, B, pi = h.A.copy(), h.B.copy(), h.pi.copy()
+    obs = rng.integers(0, m, size=T)
+    b = O.hmm_map_b(B, obs)
+    with np.errstate(all="ignore"):
+        alpha, beta = O.forward(pi, A, b), O.backward(A, b)
+        xi, gamma = O.baumwelch(A, b, alpha, beta)
+        ref = O.estimate_hmm(obs, m, xi, gamma)
+    hist = h.train(obs, iters=1, verbose=False)
+    assert abs(hist[0][0] - O.lse(alpha[-1])) < 1e-9 * abs(O.lse(alpha[-1]))
+    with np.errstate(all="ignore"):
+        assert_close(np.exp(h.A), np.exp(ref["A"]), 1e-9, "A", per_column=False)
+        assert_close(np.exp(h.B), np.exp(ref["B"]), 1e-9, "B", per_column=False)
+        assert_close(np.exp(h.pi), np.exp(ref["pi"]), 1e-9, "pi")
+
+
+def test_in_place_parameter_edits_are_seen():
+    """The device copies of the parameters are keyed on the CONTENT of the numpy arrays: an in-place edit of A or mu changes
+    the next result, and single-sequence calc_prob / decode leave self.b / self.bm filled like the reference's remap=True."""
+    from lnasr.gmmhmm import GMMHMM
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(2)
+    n, mix, d = 60, 2, 5
+    mdl = O.random_gmmhmm(n, mix, d, rng, left_to_right=True)
+    x = 0.6 * rng.standard_normal((40, d))
+    g = GMMHMM(n, mix, d, A=mdl["A"].copy(), pi=mdl["pi"].copy(), w=mdl["w"].copy(), mu=mdl["mu"].copy(),
+               si=mdl["var"][..., None] * np.eye(d))
+    p0 = g.calc_prob(x)
+    assert g.b.shape == (n, 40) and g.bm.shape == (n, mix, 40)
+    np.testing.assert_allclose(g.b, O.map_b(x, mdl["w"], mdl["mu"], mdl["var"])[0], rtol=1e-10)
+    g.A[0, 1] = -np.inf                                                   # in place: same object, same shape
+    g.mu[3, 1, 2] += 0.5
+    mdl["A"][0, 1] = -np.inf
+    mdl["mu"][3, 1, 2] += 0.5
+    with np.errstate(all="ignore"):
+        p_ref = O.calc_prob(x, mdl["pi"], mdl["A"], mdl["w"], mdl["mu"], mdl["var"])
+    p1 = g.calc_prob(x)
+    assert p1 != p0 and abs(p1 - p_ref) < 1e-9 * abs(p_ref)
+    with np.errstate(all="ignore"):
+        path_ref = O.decode(x, mdl["pi"], mdl["A"], mdl["w"], mdl["mu"], mdl["var"])
+    assert np.array_equal(g.decode(x), path_ref)
+    alpha = g._forward(x)                                                 # no remap: uses the emissions decode() left behind
+    assert abs(O.lse(alpha[-1]) - p1) < 1e-9 * abs(p1)
