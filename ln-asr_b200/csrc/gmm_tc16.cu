@@ -288,7 +288,36 @@ __device__ __forceinline__ float h_lg2(float x) {
     return y;
 }
 
-template <int MP>
+// 2^a for a pair of arguments a <= 0 on the FMA pipe instead of the MUFU: round-to-nearest split a = n + f, |f| <= 1/2, a
+// degree-5 polynomial with p(0) = 1 exactly (max relative error 1.7e-7 in float32 FMA arithmetic, inside the 2 ulp of
+// ex2.approx), and n added to the exponent field.  The log-sum-exp epilogue is bound by the MUFU (16 / clk / SM: 16 ex2 per
+// (frame, state) take longer than the 15 MMAs that produced them); a fixed subset of the mixture pairs takes this path so
+// that the two pipes share the exponentials.  The largest term has a = 0 -> exactly 1 on either path.
+__device__ __forceinline__ unsigned long long h_ex2_poly2(float a0, float a1) {
+    constexpr float MAGIC = 12582912.f;                               // 1.5 * 2^23: a + MAGIC rounds a to the nearest integer
+    a0 = fmaxf(a0, -125.f);                                           // 2^-125 ~ 0: padded columns sit at -256 and below
+    a1 = fmaxf(a1, -125.f);
+    const unsigned long long a2 = pack_f2(a0, a1);
+    const unsigned long long t2 = fadd2(a2, pack_f2(MAGIC, MAGIC));
+    const unsigned long long n2 = fadd2(t2, pack_f2(-MAGIC, -MAGIC));
+    const unsigned long long f2 = ffma2(n2, pack_f2(-1.f, -1.f), a2);
+    unsigned long long p2 = pack_f2(1.326470170e-03f, 1.326470170e-03f);
+    p2 = ffma2(p2, f2, pack_f2(9.671504609e-03f, 9.671504609e-03f));
+    p2 = ffma2(p2, f2, pack_f2(5.550733581e-02f, 5.550733581e-02f));
+    p2 = ffma2(p2, f2, pack_f2(2.402224243e-01f, 2.402224243e-01f));
+    p2 = ffma2(p2, f2, pack_f2(6.931470037e-01f, 6.931470037e-01f));
+    p2 = ffma2(p2, f2, pack_f2(1.f, 1.f));
+    float p0, p1, t0, t1;
+    unpack_f2(p2, p0, p1);
+    unpack_f2(t2, t0, t1);
+    // the low mantissa bits of t hold n (two's complement): shifted into the exponent field and added
+    p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+    return pack_f2(p0, p1);
+}
+
+// PMASK: bit i set = mixture pair i of every state takes the polynomial exp2, the others the MUFU
+template <int MP, int PMASK>
 __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state, const float* q_state, float* out_row, int st_local0,
                                             int st_global0, int st_end) {
     // c_state / q_state: per-state constant and 1/t, indexed [st_local0 + g] (shared memory, or registers when the caller
@@ -311,7 +340,7 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
             for (int i = 0; i < MP; i += 2) {
                 float a0, a1;
                 unpack_f2(ffma2(pack_f2(v[g * MP + i], v[g * MP + i + 1]), q2, nm2), a0, a1);
-                const unsigned long long e2 = pack_f2(h_ex2(a0), h_ex2(a1));
+                const unsigned long long e2 = ((PMASK >> (i / 2)) & 1) ? h_ex2_poly2(a0, a1) : pack_f2(h_ex2(a0), h_ex2(a1));
                 s2 = (i == 0) ? e2 : fadd2(s2, e2);
             }
             float s_lo, s_hi;
@@ -326,7 +355,7 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
     }
 }
 
-template <int MP, int PARTS>
+template <int MP, int PARTS, int PMASK>
 __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base, const float* s_c, const float* s_cs, float* s_out,
                                            int warp, int lane, int wt, int64_t fs, int64_t fe, int n_tiles, uint32_t tile_cnt,
                                            uint64_t* t_full, uint64_t* t_empty) {
@@ -377,7 +406,7 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[cj * 16 + i]);
-                        h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, (c16_begin + ci) * (16 / MP), 1 << 30);
+                        h_lse_store<MP, PMASK>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, (c16_begin + ci) * (16 / MP), 1 << 30);
                     }
                 }
             } else {
@@ -387,7 +416,7 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
                     if (c16 < c16_end) {
                         float v[16];
                         tmem_ld16(taddr + c16 * 16, v);
-                        h_lse_store<MP>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, c16 * (16 / MP), 1 << 30);
+                        h_lse_store<MP, PMASK>(v, creg + ci * (16 / MP), qreg + ci * (16 / MP), srow, 0, c16 * (16 / MP), 1 << 30);
                     }
                 }
             }
@@ -396,7 +425,7 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
                 float v[16];
                 tmem_ld16(taddr + c16 * 16, v);
                 const int sl0 = c16 * (16 / MP);
-                h_lse_store<MP>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se);
+                h_lse_store<MP, PMASK>(v, s_c, s_cs, out_row, sl0, st_tile0 + sl0, se);
             }
         }
         tc_fence_before();
@@ -470,6 +499,7 @@ __device__ __forceinline__ void h_mma_role(const H16Args& a, int lane, uint32_t 
 // warp, 1 MMA warp.  (18 warps are allocated as 20, so a thread has at most 96 registers.)
 constexpr int HB_EPI_WARPS = 16, HB_WARP_COPY = 16, HB_WARP_MMA = 17, HB_THREADS = 18 * 32;
 
+template <int PMASK>
 __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
     extern __shared__ __align__(1024) uint8_t h_smem[];
     const int NT = a.NT;
@@ -542,11 +572,11 @@ __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
             // ===================== epilogue: warp w reads TMEM lanes 32 (w & 3) .. (= frame rows), a quarter of the columns
             constexpr int P = HB_EPI_WARPS / 4;
             switch (a.Mp) {
-                case 16: h_epilogue<16, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 8:  h_epilogue<8, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 4:  h_epilogue<4, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 2:  h_epilogue<2, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                default: h_epilogue<1, P>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 16: h_epilogue<16, P, PMASK>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 8:  h_epilogue<8, P, PMASK>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 4:  h_epilogue<4, P, 0>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 2:  h_epilogue<2, P, 0>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                default: h_epilogue<1, P, 0>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
             }
         }
         tile_cnt += n_tiles;
@@ -559,6 +589,9 @@ __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
 }  // namespace lnasr
 
 using namespace lnasr;
+
+static int g_tc16_poly = 2;
+extern "C" int lnasr_debug_set_tc16_poly(int level) { g_tc16_poly = level; return LNASR_OK; }
 
 extern "C" int lnasr_gmm_tc16_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes) {
     H16Geom g;
@@ -628,8 +661,17 @@ extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64
     a.frames_per_split = tiles_per_split * H_BM;
     const int grid = std::min(sms, g.n_wtiles * n_fsplit);
     const size_t smem = ((g.tile_bytes + 127) & ~(size_t)127) + 4 * (size_t)H_BM * H_KP * 2 + 1024 + H_OUT_BYTES;
-    LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_tc16_kernel<<<grid, HB_THREADS, smem, stream>>>(a);
+    // share of the exponentials computed by polynomial on the FMA pipe (lnasr_debug_set_tc16_poly): mixture pairs of a state
+    switch (g_tc16_poly) {
+#define LNASR_H16_LAUNCH(MASK)                                                                                                  \
+        LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        gmm_tc16_kernel<MASK><<<grid, HB_THREADS, smem, stream>>>(a);
+        case 0:  LNASR_H16_LAUNCH(0x00) break;
+        case 1:  LNASR_H16_LAUNCH(0x24) break;          // pairs 2, 5       : 2 of 8
+        case 3:  LNASR_H16_LAUNCH(0xAA) break;          // pairs 1, 3, 5, 7 : 4 of 8
+        default: LNASR_H16_LAUNCH(0x92) break;          // pairs 1, 4, 7    : 3 of 8
+#undef LNASR_H16_LAUNCH
+    }
     LNASR_LAUNCH_CHECK();
     return tc_fixup(feats, ld_feats, n_frames, flags, reinterpret_cast<const double*>((const uint8_t*)packed + g.tail_off), n_states, n_mix,
                     dim, b_out, ld_b, stream);

@@ -29,6 +29,13 @@ constexpr int STEPS_PER_RUN = FRAMES_PER_RUN / 2;
 constexpr double COLSUM_SCALE = 4294967296.0;      // per-utterance column sums are 32.32 fixed point (|c| < 2^18, < 2^13 frames)
 constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
 constexpr int MAX_SLOTS = MAX_MEL / 16;
+constexpr int DCT_LD = 20;            // row stride (doubles) of the tensor-core DCT operand: the 4 x 4 doubles a half-warp loads
+                                      // per fragment fall into 4 x 8 distinct banks
+
+__device__ __forceinline__ void mfcc_dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 struct MfccDev {
     int frame_len, frame_step, n_mel, n_ceps, fb_stride;
@@ -96,13 +103,18 @@ __host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int 
     L.tw_split = o; o += 2 * 128;                         // W512^(b + 16 k2) at [k2*16 + b], k2 < 8
     L.window = o;   o += FFT_N;                           // window (x 1/100 on the integer path), zero past frame_len
     L.logtab = o;   o += 2 * 128;                         // (1/c_i, log c_i) of the table-driven log
-    L.dct = o;      o += n_mel * n_dct_cols;              // [n][k < n_dct_cols]
+    // DCT matrix: [n][k < n_dct_cols], or -- when at most 16 coefficients are wanted (the feature path) -- the B operand of
+    // the float64 tensor-core DCT: [n < n_mel rounded up to 4][DCT_LD] with zero padding
+    L.dct = o;      o += (n_dct_cols <= 16) ? ((n_mel + 3) & ~3) * DCT_LD : n_mel * n_dct_cols;
     L.fb_w = o;     o += (n_mel * fb_stride + 1) / 2;     // float weights
     L.fb_meta = o;  o += (4 * MAX_MEL) / 2 + 2;           // ints: fb_start[64] | fb_len[64] | assign[64] | order[64] | flags
     o = (o + 1) & ~1;
     L.per_hw = o;
     L.stage_off = 2 * 16 * TR_LD + MAX_MEL;               // transpose buffer | log-mel[64] | sample stage
     L.per_hw_doubles = (L.stage_off + (STAGE_SAMPLES * pcm_bytes + 7) / 8 + 1) & ~1;
+    // the two half-warps of a warp read their sample stages with the same instruction: 64 bytes each, in disjoint banks when
+    // the two stages are an odd multiple of 64 bytes apart
+    while ((L.per_hw_doubles & 15) != 8) L.per_hw_doubles += 2;
     L.total = o + n_hw * L.per_hw_doubles;
     return L;
 }
@@ -172,9 +184,20 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     }
     for (int i = tid; i < FFT_N; i += n_threads) s_win[i] = (i < P.frame_len) ? P.window[i] * (int_path ? 0.01 : 1.0) : 0.0;
     for (int i = tid; i < P.n_mel * P.fb_stride; i += n_threads) s_fbw[i] = P.fb_weight[i];
-    for (int i = tid; i < P.n_mel * n_out; i += n_threads) {
-        const int n = i / n_out, k = i - n * n_out;
-        s_dct[i] = P.dct_t[n * P.n_mel + k];
+    // DCT on the float64 tensor cores when at most 16 coefficients are wanted (features: 13); the API-parity path that returns
+    // all n_mel cepstra keeps the SIMT loop
+    const bool dct_mma = n_out <= 16;
+    const int n_mel4 = (P.n_mel + 3) & ~3;
+    if (dct_mma) {
+        for (int i = tid; i < n_mel4 * DCT_LD; i += n_threads) {
+            const int n = i / DCT_LD, k = i - n * DCT_LD;
+            s_dct[i] = (n < P.n_mel && k < n_out) ? P.dct_t[n * P.n_mel + k] : 0.0;
+        }
+    } else {
+        for (int i = tid; i < P.n_mel * n_out; i += n_threads) {
+            const int n = i / n_out, k = i - n * n_out;
+            s_dct[i] = P.dct_t[n * P.n_mel + k];
+        }
     }
     for (int i = tid; i < P.n_mel; i += n_threads) { s_fbs[i] = P.fb_start[i]; s_fbl[i] = P.fb_len[i]; }
     for (int i = tid; i < MAX_MEL; i += n_threads) s_asg[i] = -1;
@@ -226,8 +249,12 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
 
     double* hbase = smem + L.per_hw + (tid >> 4) * L.per_hw_doubles;
     double2* tr = reinterpret_cast<double2*>(hbase);     // [16][TR_LD] complex
-    float* s_pow = reinterpret_cast<float*>(hbase);      // power spectrum (float), aliases tr once the second DFT has read it
+    // power spectra of the warp's TWO frames, interleaved [k][half] (float), in the transpose buffer of half 0 once the second
+    // DFT has read it: the two half-warps run the same mel schedule, so lanes b and b + 16 read / write adjacent floats and a
+    // warp-wide access is one wavefront instead of one per half-warp
+    float* s_pow = reinterpret_cast<float*>(smem + L.per_hw + ((tid >> 5) * 2) * L.per_hw_doubles) + half;
     double* s_lm = hbase + 2 * 16 * TR_LD;
+    for (int i = b; i < MAX_MEL; i += 16) s_lm[i] = 0.0;                  // entries >= n_mel stay zero (k padding of the DCT)
     PcmT* stage = reinterpret_cast<PcmT*>(hbase + L.stage_off);
 
     const int64_t n_runs = (total_frames + FRAMES_PER_RUN - 1) / FRAMES_PER_RUN;
@@ -295,14 +322,18 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     // the per-utterance means -- and with them every feature -- do not depend on the order in which warps flush or on the
     // batch the utterance is scored in (a float64 atomicAdd would make the last bits scheduling-dependent)
     long long acc[MAX_SLOTS] = {0, 0, 0, 0};
+    // coefficient whose sum lives in acc[i] of this lane: b + 16 i (SIMT DCT), or 8 (i / 2) + 2 b + i % 2 in lanes b < 4 (the
+    // accumulator fragment of the tensor-core DCT)
+    auto acc_coef = [&](int i) -> int { return dct_mma ? (b < 4 ? 8 * (i >> 1) + 2 * b + (i & 1) : -1) : b + 16 * i; };
     for (int64_t step = 0; more; ++step) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (act && ctx.u != acc_u) {                      // flush the column sums of the utterance just left
 #pragma unroll
             for (int i = 0; i < MAX_SLOTS; ++i) {
-                if (acc_u >= 0 && b + 16 * i < n_out)
-                    atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, (unsigned long long)acc[i]);
+                const int k = acc_coef(i);
+                if (acc_u >= 0 && k >= 0 && k < n_out)
+                    atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + k, (unsigned long long)acc[i]);
                 acc[i] = 0;
             }
             acc_u = ctx.u;
@@ -321,7 +352,19 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                 if (a < n_a) {
                     const int n0 = 32 * a + 2 * b;
                     const bool ok0 = n0 < rem, ok1 = n0 + 1 < rem;
-                    PcmT xm = sx[n0 - 1], x0 = sx[n0], x1 = sx[n0 + 1];
+                    PcmT xm, x0, x1;
+                    if (kIntPcm) {
+                        // x[n0-1], x[n0], x[n0+1] are 6 bytes inside two consecutive 4-byte words: two 32-bit loads and a funnel
+                        // shift instead of three 2-byte loads
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage) + ((par + n0) >> 1);
+                        const uint32_t w0 = wp[0], w1 = wp[1];
+                        const uint32_t lo = __funnelshift_r(w0, w1, 16 * par);
+                        xm = (PcmT)(short)(lo & 0xffffu);
+                        x0 = (PcmT)(short)(lo >> 16);
+                        x1 = (PcmT)(short)((w1 >> (16 * par)) & 0xffffu);
+                    } else {
+                        xm = sx[n0 - 1]; x0 = sx[n0]; x1 = sx[n0 + 1];
+                    }
                     if (!ok0) x0 = PcmT(0);
                     if (!ok0 || !(n0 > 0 || lead)) xm = PcmT(0);
                     double y0, y1;
@@ -368,20 +411,20 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             const double px = E.x + T.x, py = E.y + T.y;                   // 2 X[k]
             const double qx = E.x - T.x, qy = E.y - T.y;                   // conj(2 X[256-k])
             const double pk = px * px + py * py, pr = qx * qx + qy * qy;
-            s_pow[b + 16 * k2] = (float)pk;
-            s_pow[HALF_N - b - 16 * k2] = (float)pr;
+            s_pow[2 * (b + 16 * k2)] = (float)pk;
+            s_pow[2 * (HALF_N - b - 16 * k2)] = (float)pr;
             esum += pk + pr;
         }
         {
             const double2 z8 = v[NAT16(8)];                                // bin 128 (lane 0): X = conj(Z[128])
             const double p8 = 4.0 * (z8.x * z8.x + z8.y * z8.y);
-            if (b == 0) { s_pow[128] = (float)p8; esum += p8; }
+            if (b == 0) { s_pow[2 * 128] = (float)p8; esum += p8; }
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
         __syncwarp();
         if (power_out && act_cur)
-            for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = s_pow[k] * (float)PSCALE;
+            for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = s_pow[2 * k] * (float)PSCALE;
         // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
         for (int s = 0; s < n_slots; ++s) {
             const int m = s_asg[s * 16 + b];
@@ -392,14 +435,14 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                 // safe in float32 (<= 31 positive terms: relative error ~1e-6, i.e. ~1e-5 dB) -- half the shared-memory bytes
                 // of the hottest loop of this kernel, and FFMA instead of DFMA.  The energy sum above stays float64.
                 const float* w = s_fbw + m * P.fb_stride;
-                const float* pw = s_pow + k0;
+                const float* pw = s_pow + 2 * k0;
                 float e0 = 0.f, e1 = 0.f;
                 int t = 0;
                 for (; t + 1 < len; t += 2) {
-                    e0 = fmaf(w[t], pw[t], e0);
-                    e1 = fmaf(w[t + 1], pw[t + 1], e1);
+                    e0 = fmaf(w[t], pw[2 * t], e0);
+                    e1 = fmaf(w[t + 1], pw[2 * t + 2], e1);
                 }
-                if (t < len) e0 = fmaf(w[t], pw[t], e0);
+                if (t < len) e0 = fmaf(w[t], pw[2 * t], e0);
                 e = (double)(e0 + e1);
             }
             e *= PSCALE;
@@ -410,7 +453,31 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         }
         if (energy_sep && b == 15 && act_cur) raw[f_cur * RAW_LD + P.n_ceps] = (float)log(esum * PSCALE);
         __syncwarp();
-        // ---- DCT-II ortho (mfcc.py:152): thread b produces coefficients b, b+16, ...
+        // ---- DCT-II ortho (mfcc.py:152)
+        if (dct_mma) {
+            // On the float64 tensor cores: D[frame, k] = sum_n lm[frame, n] dct[n, k] as mma.m8n8k4 with the warp's two frames in
+            // rows 0 and 4 of the A operand (lanes 0-3 of each half-warp supply their own half's log-mel values, every other
+            // lane zero) and the coefficients 0..15 as two n-blocks.  The SIMT loop read one table entry (8 bytes) per
+            // multiply-add; here a 4 x 8 block of the table feeds 256 of them, and the DCT stops being a shared-memory item.
+            double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+            const double* bp = s_dct + (lane & 3) * DCT_LD + (lane >> 2);
+            for (int kb = 0; kb < n_mel4; kb += 4) {
+                const double av = (b < 4) ? s_lm[kb + b] : 0.0;
+                mfcc_dmma884(d00, d01, av, bp[kb * DCT_LD]);
+                mfcc_dmma884(d10, d11, av, bp[kb * DCT_LD + 8]);
+            }
+            if (b < 4 && act_cur) {                        // lanes 0-3 / 16-19 hold coefficients 2b, 2b+1 (+8) of frame half
+                const double dv[4] = {d00, d01, d10, d11};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 8 * (i >> 1) + 2 * b + (i & 1);
+                    if (k < n_out) {
+                        acc[i] += __double2ll_rn(dv[i] * COLSUM_SCALE);
+                        if (k >= 1 && k <= P.n_ceps) raw[f_cur * RAW_LD + (k - 1)] = (float)dv[i];
+                    }
+                }
+            }
+        } else
 #pragma unroll
         for (int i = 0; i < MAX_SLOTS; ++i) {
             const int k = b + 16 * i;
@@ -435,8 +502,10 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     }
     if (acc_u >= 0) {
 #pragma unroll
-        for (int i = 0; i < MAX_SLOTS; ++i)
-            if (b + 16 * i < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + b + 16 * i, (unsigned long long)acc[i]);
+        for (int i = 0; i < MAX_SLOTS; ++i) {
+            const int k = acc_coef(i);
+            if (k >= 0 && k < n_out) atomicAdd(colsum + (int64_t)acc_u * MAX_MEL + k, (unsigned long long)acc[i]);
+        }
     }
 }
 

@@ -1,0 +1,51 @@
+#!/usr/bin/env python3
+"""Time the FP16-slice tensor-core emission kernel at the config-4 shape (373 750 frames x 2000 states x 16 mixtures) for each
+share of polynomial exponentials (lnasr_debug_set_tc16_poly 0..3), with the signed error against the float64 kernel.
+One GPU; CUDA events."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "ln-asr_b200"), ROOT):
+    sys.path.insert(0, p)
+
+
+def main():
+    import torch
+    import bench
+    from lnasr import _capi
+    from lnasr.gmm import PackedGmm
+    from lnasr.gmm_tc import PackedGmmTC
+    from lnasr.mfcc import MFCC
+    mdl = bench.make_models("c4")[0]
+    pcm, off = bench.synth_batch(1000, 1250, 48000, 48000)
+    feats = MFCC().calc_mfcc_batch(pcm, sample_offsets=off).feats
+    T = feats.shape[0]
+    g = PackedGmmTC(mdl["w"], mdl["mu"], mdl["var"], fmt="f16")
+    b = torch.empty((T, 2000), dtype=torch.float32, device="cuda")
+    b64 = PackedGmm(mdl["w"], mdl["mu"], mdl["var"]).loglik(feats[:4096])[0]
+    lib = _capi.lib()
+    for rep in range(2):
+        for level in (0, 1, 2, 3):
+            lib.lnasr_debug_set_tc16_poly(level)
+            for _ in range(3):
+                g.loglik(feats, b_out=b)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                g.loglik(feats, b_out=b)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            e = b[:4096].double() - b64
+            print(f"poly level {level}: {ms:.3f} ms per {T} frames = {2 * 79 * 32000 * T / (ms * 1e-3) / 1e12:.0f} algorithmic TFLOP/s; "
+                  f"err vs float64: mean {e.mean():+.3e} rms {e.pow(2).mean().sqrt():.3e} max {e.abs().max():.3e}")
+    lib.lnasr_debug_set_tc16_poly(2)
+
+
+if __name__ == "__main__":
+    main()
