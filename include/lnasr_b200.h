@@ -287,6 +287,17 @@ int lnasr_baumwelch_xi(const double* alpha, const double* beta, const double* b,
                        const int64_t* frame_offsets, int32_t n_utt, int64_t total_frames, int32_t N,
                        double* xi_out, double* gamma_out, void* stream);
 
+/* ================================ before the path: voice activity detection =====================
+ * VadLtsd.detect (third/vadlstd/VadLstd.py:44-74): frames of `winsize` samples every `stepsize` after one step of leading zeros
+ * (utils.split_frames rule), Hamming window, |rfft|, long-term spectral envelope over 2*order frames, LTSD in dB per frame.
+ * window [winsize] and twiddle [winsize/2] (cos, -sin of 2 pi j / winsize) are caller-provided float64 device tables;
+ * adapt != 0 enables the noise update of VadLstd.py:72-73 with factor alpha.  ltsd_out [lnasr_vad_num_frames] float64. */
+int64_t lnasr_vad_num_frames(int64_t n_samples, int32_t winsize, int32_t stepsize);
+size_t lnasr_vad_workspace_bytes(int64_t n_samples, int32_t winsize, int32_t stepsize);
+int lnasr_vad_ltsd(const void* pcm, int pcm_dtype, int64_t n_samples, int32_t winsize, int32_t stepsize, int32_t order,
+                   double threshold, int adapt, double alpha, const double* window, const double* twiddle,
+                   double* ltsd_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ================================ debug / bring-up ==============================================
  * One tcgen05.mma (M=128, N=128, K=8, kind::tf32) on caller-provided shared-memory images with caller-chosen
  * descriptor fields; used by tests/test_umma_probe.py to pin the descriptor semantics on hardware. */

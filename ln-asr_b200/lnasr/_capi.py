@@ -91,6 +91,9 @@ SIGNATURES = {
     "lnasr_hmm_fb_accumulate": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, vp]),
     "lnasr_hmm_mstep_finalize": (C.c_int, [vp, i32, i32, vp, vp, vp, vp]),
     "lnasr_baumwelch_xi": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp]),
+    "lnasr_vad_num_frames": (i64, [i64, i32, i32]),
+    "lnasr_vad_workspace_bytes": (sz, [i64, i32, i32]),
+    "lnasr_vad_ltsd": (C.c_int, [vp, C.c_int, i64, i32, i32, i32, f64, C.c_int, f64, vp, vp, vp, vp, sz, vp]),
     "lnasr_debug_set_probe_second_mma": (C.c_int, [C.c_uint32]),
     "lnasr_debug_set_band_kernel": (C.c_int, [C.c_int]),
     "lnasr_debug_set_tc16_poly": (C.c_int, [C.c_int]),

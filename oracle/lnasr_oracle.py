@@ -27,7 +27,7 @@ __all__ = [
     "hmm_map_b", "forward", "backward", "viterbi", "baumwelch",
     "estimate_hmm", "estimate_gmmhmm", "estimate_gmmhmm_diag",
     "calc_prob", "decode", "train_gmmhmm", "em_accumulate_diag", "em_finalize_diag",
-    "em_step_multi_diag", "random_gmmhmm", "score_words", "score_words_viterbi",
+    "em_step_multi_diag", "random_gmmhmm", "score_words", "score_words_viterbi", "vad_ltsd",
 ]
 
 NEG_INF = -np.inf
@@ -180,6 +180,22 @@ def mfcc(signal: np.ndarray, p: MfccParams = None):
     d13 = np.concatenate([s13[1:2], s13[1:] - s13[:-1]], axis=0)
     dd13 = np.concatenate([d13[1:2], d13[1:] - d13[:-1]], axis=0)
     return power, ceps, np.concatenate([s13, d13, dd13], axis=1)
+
+
+def vad_ltsd(data, winsize=2048, stepsize=1024, order=6, threshold=-6, alpha=None):
+    """VadLtsd.detect (third/vadlstd/VadLstd.py:44-74): LTSD in dB per frame; frames within `order` of either end stay 0."""
+    pad = np.append(np.zeros(stepsize), np.asarray(data, dtype=np.float64))
+    frames = split_frames(pad, winsize, stepsize) * create_hamming(winsize)
+    F = frames.shape[0]
+    amp = np.abs(np.fft.rfft(frames, winsize))
+    noise = np.average(amp[0:2], axis=0) ** 2
+    ltsd = np.zeros(F)
+    for k in range(order, F - order):
+        ltse = amp[k - order:k + order].max(axis=0)
+        ltsd[k] = 10 * np.log10(np.sum(ltse ** 2 / noise) / winsize)
+        if alpha is not None and ltsd[k] < threshold:
+            noise = alpha * noise + (1 - alpha) * (np.sum(ltse) / winsize)
+    return ltsd
 
 
 # --------------------------------------------------------------------------- GMM

@@ -182,6 +182,23 @@ def main():
         gmix=rg.gaussian_mixture_distribution(cw, x, mus, Sigs),
         gmixlog=rg.gaussian_mixture_distribution_log(np.log(cw), x, mus, Sigs),
     )
+    # ---------------------------------------------------------------- VadLtsd (third/vadlstd/VadLstd.py), the step before the path
+    import importlib.util
+    sys.modules.setdefault("snoop", types.ModuleType("snoop"))           # imported at VadLstd.py:19, used only in a comment
+    spec = importlib.util.spec_from_file_location("ref_vadlstd", os.path.join(REF, "third", "vadlstd", "VadLstd.py"))
+    rv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rv)
+    rng = np.random.default_rng(21)
+    vad = {}
+    for tag, n, kw in (("a", 40000, {}), ("b", 30001, {"alpha": 0.9, "threshold": 30.0}), ("c", 9000, {"winsize": 512, "stepsize": 256, "order": 3}),
+                       ("d", 2500, {})):
+        t = np.arange(n) / 16000.0
+        x = 300.0 * rng.standard_normal(n)
+        x[n // 3:2 * n // 3] += 4000.0 * np.sin(2 * np.pi * 220.0 * t[n // 3:2 * n // 3])      # a loud stretch in the middle
+        x = np.clip(np.round(x), -32767, 32767).astype(np.int16)
+        vad["pcm_" + tag] = x
+        vad["ltsd_" + tag] = rv.VadLtsd(**kw).detect(x.astype(np.float64))
+    np.savez_compressed(os.path.join(OUT, "vad.npz"), **vad)
     print("golden fixtures written to", OUT)
 
 

@@ -194,3 +194,13 @@ print("ok")
 ''' % ROOT
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("tag,kw", [("a", {}), ("b", {"alpha": 0.9, "threshold": 30.0}),
+                                    ("c", {"winsize": 512, "stepsize": 256, "order": 3}), ("d", {})])
+def test_vad_ltsd_oracle_matches_reference_golden(golden, tag, kw):
+    """O.vad_ltsd against VadLtsd.detect of the unmodified reference (third/vadlstd/VadLstd.py:44-74), incl. noise adaptation."""
+    g = golden("vad")
+    got = O.vad_ltsd(g["pcm_" + tag], **kw)
+    assert got.shape == g["ltsd_" + tag].shape
+    np.testing.assert_allclose(got, g["ltsd_" + tag], rtol=1e-12, atol=1e-12)
