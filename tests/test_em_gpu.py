@@ -247,3 +247,37 @@ def test_in_place_parameter_edits_are_seen():
     assert np.array_equal(g.decode(x), path_ref)
     alpha = g._forward(x)                                                 # no remap: uses the emissions decode() left behind
     assert abs(O.lse(alpha[-1]) - p1) < 1e-9 * abs(p1)
+
+
+def test_empty_shard_still_enters_the_collective():
+    """A rank whose utterance shard is empty (world_size > number of utterances) must call the all-reduce with a zero
+    accumulator instead of failing before it -- the other ranks would hang.  The reduce hook stands in for the collective."""
+    import torch
+    from lnasr.gmmhmm import GMMHMM
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(8)
+    n, mix, d = 3, 2, 5
+    mdl = O.random_gmmhmm(n, mix, d, rng)
+    utts = [0.6 * rng.standard_normal((T, d)) for T in (20, 31)]
+
+    def model():
+        return GMMHMM(n, mix, d, A=mdl["A"], pi=mdl["pi"], w=mdl["w"], mu=mdl["mu"], si=mdl["var"][..., None] * np.eye(d))
+
+    seen = []
+    full = model()
+    full.train_batch(utts, iters=1, verbose=False, reduce_fn=lambda t: seen.append(t.clone()) or t)
+    acc_full, ll_full = seen[0], seen[1]                                  # the accumulator, then the log-likelihood sum of the new model
+    calls = []
+
+    def fake_allreduce(t):                                                # what NCCL would deliver: the sum over ranks
+        calls.append(tuple(t.shape))
+        assert float(t.abs().sum()) == 0.0                                # this rank contributes nothing
+        t.copy_(acc_full if t.numel() == acc_full.numel() else ll_full)
+        return t
+
+    empty = model()
+    hist = empty.train_batch([], iters=1, verbose=False, reduce_fn=fake_allreduce)
+    assert len(calls) == 2 and len(hist) == 1
+    np.testing.assert_allclose(empty.mu, full.mu, rtol=1e-12)
+    np.testing.assert_allclose(empty.A, full.A, rtol=1e-12)
+    assert empty.calc_prob_batch([]).shape == (0,) and empty.decode_batch([]) == []

@@ -1,5 +1,5 @@
 set -x
-timeout 600 python -m pytest tests/test_mfcc_gpu.py tests/test_tc_gpu.py tests/test_pipeline_gpu.py tests/test_from_pcm_gpu.py tests/test_full_size_gpu.py -q -x -s > gpurun_out/r2D_pytest.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/r2D_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/r2D_pytest.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/r2D_pytest.log
 timeout 300 python tools/bench_gmm.py > gpurun_out/r2D_gmm.txt 2>&1; cat gpurun_out/r2D_gmm.txt
 timeout 600 python bench.py --no-cpu > gpurun_out/r2D_bench.log 2> gpurun_out/r2D_bench.err; python - <<'PY'
 import json
@@ -9,3 +9,4 @@ for k,v in d['secondary'].items(): print(k, v['value'], v['ms_per_step'], v['e2e
 PY
 tail -3 gpurun_out/r2D_bench.err
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mfcc_frames" -c 1 -f -o gpurun_out/r2D_mfcc python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu --no-secondary > gpurun_out/r2D_ncu.log 2>&1; tail -2 gpurun_out/r2D_ncu.log
+timeout 900 python tools/mfcc_sweep.py > gpurun_out/r2D_mfcc_sweep.md 2>&1; tail -30 gpurun_out/r2D_mfcc_sweep.md

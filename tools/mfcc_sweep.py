@@ -4,6 +4,10 @@ frames/s, achieved GB/s of the algorithmic traffic (476 B/frame) against the mea
 fraction.  Writes a markdown table (stdout) -- committed under profiles/.
 
     python tools/mfcc_sweep.py > gpurun_out/mfcc_sweep.md
+    python tools/mfcc_sweep.py --only 1x1        (one case, e.g. under ncu: the batch-1 latency corner)
+
+The audio is generated on the device (noise, int16) so that the 60 s x 4096 corner (3.9 G samples, 7.9 GB) needs no host
+memory; every case of BASELINE configs[4] from 1 s x 1 to 60 s x 4096 runs.
 """
 import json
 import os
@@ -25,14 +29,28 @@ fp64 = bench.fp64_peaks()
 mf = MFCC()
 print("| seconds/utt | batch | frames | ms (CUDA events, best of 5) | frames/s | GB/s (476 B/frame) | % of HBM peak | FP64 TFLOP/s | % of DFMA peak |")
 print("|---|---|---|---|---|---|---|---|---|")
-rng = np.random.default_rng(1234)
-max_samples = 400_000_000
+only = None
+if "--only" in sys.argv:
+    a, b_ = sys.argv[sys.argv.index("--only") + 1].split("x")
+    only = (int(a), int(b_))
+gen = torch.Generator(device="cuda").manual_seed(1234)
+
+
+def device_noise(n):
+    out = torch.empty((n,), dtype=torch.int16, device="cuda")
+    step = 1 << 27
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        out[i:i + m] = torch.randn((m,), device="cuda", generator=gen).mul_(3000.0).round_().clamp_(-32767, 32767).to(torch.int16)
+    return out
+
+
 for secs in (1, 5, 10, 30, 60):
     for batch in (1, 8, 64, 512, 4096):
-        S = 16000 * secs
-        if S * batch > max_samples:
+        if only is not None and (secs, batch) != only:
             continue
-        pcm = torch.from_numpy(np.clip(np.round(3000.0 * rng.standard_normal(S * batch, dtype=np.float32)), -32767, 32767).astype(np.int16)).cuda()
+        S = 16000 * secs
+        pcm = device_noise(S * batch)
         off = np.arange(batch + 1, dtype=np.int64) * S
         best = 1e30
         for rep in range(7):
@@ -49,5 +67,6 @@ for secs in (1, 5, 10, 30, 60):
         tf = fps * bench.MFCC_FP64_FLOPS_PER_FRAME / 1e12
         print(f"| {secs} | {batch} | {frames} | {best:.3f} | {fps:.3e} | {gbs:.1f} | {100 * gbs / hbm:.2f} | {tf:.2f} | {100 * tf / fp64['fp64_fma_tflops']:.1f} |")
         del pcm, mb
+        torch.cuda.empty_cache()
 print(f"\nHBM peak {hbm} GB/s (MEASURED_PEAKS.json); FP64 DFMA peak measured in this run: {fp64['fp64_fma_tflops']:.1f} TFLOP/s; "
       "includes the host-side offset arithmetic of calc_mfcc_batch (small batches are launch/host bound).")
