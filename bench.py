@@ -550,7 +550,7 @@ def run_ours(args, ctx, workload, steps, warmup, with_cpu=True, load_s=1.5):
                     "utterance_groups_per_batch": n_chunks,
                     "one_batch_at_a_time": {"value": e2e_sync_value, "ms_per_step": ms_e2e_sync / steps,
                                             "api": "AcousticPipeline.recognize_batch_host"}},
-            "gpu_launches": launches_per_step(pipe, want_paths) * steps,
+            "gpu_launches": launches_in(step_device) * steps,
             "roofline": roof, "cpu_baseline": cpu,
         }
     del pipe, pcm_dev, pcm_host, res, mb
@@ -612,6 +612,8 @@ def run_em(args, ctx, steps, warmup, load_steps=400):
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     total_frames = ctx.sum_over_ranks(frames)
+    n_launch = launches_in(step)                          # on every rank: the step holds a collective
+    torch.cuda.synchronize()
     line = None
     if rank == 0:
         n, m, d = 3, 8, 39
@@ -628,7 +630,7 @@ def run_em(args, ctx, steps, warmup, load_steps=400):
             "clocks": clocks,
             "e2e": {"value": total_frames / (ms_e2e / 1e3 / steps), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": 8},
-            "gpu_launches": 7 * steps,       # pack x2 (SIMT + DMMA image), loglik, forward, backward, em_statistics, mstep (+ memset)
+            "gpu_launches": n_launch * steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": ach / ctx.hbm_peak, "traffic": None,
                          "algorithmic_bytes_per_frame": per, "kernel": "whole iteration", "peak_source": ctx.peak_src},
             "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "not run for c3"},
@@ -669,14 +671,13 @@ def ncu_traffic(workload, frames, stage):
     return {"bytes": float(st["dram_read_bytes"]) + float(st["dram_write_bytes"]), "kernel": st["kernel"], "source": ent.get("source", "profiles/")}
 
 
-def launches_per_step(pipe, want_paths):
-    """Kernels of liblnasr_b200.so launched by one device-resident step."""
-    n = 3                                   # mfcc_run_index, mfcc_frames, mfcc_finalize
-    n += 2 if pipe.bank.emission in ("tc", "tc16") else 1          # stage + contraction | gmm_loglik_exact
-    n += 1                                  # trellis (N <= 32: backtrace fused into the kernel)
-    if want_paths and pipe.bank.n > 32:
-        n += 1                              # backtrace
-    return n + 1                            # argmax_rows
+def launches_in(fn):
+    """Kernels of liblnasr_b200.so launched while fn() runs: the library counts its own launches (lnasr_launch_count)."""
+    from lnasr import _capi
+    lib = _capi.lib()
+    n0 = int(lib.lnasr_launch_count())
+    fn()
+    return int(lib.lnasr_launch_count()) - n0
 
 
 def stage_times(pipe, pcm_dev, off, want_paths, reps=5):

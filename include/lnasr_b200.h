@@ -298,6 +298,9 @@ int lnasr_vad_ltsd(const void* pcm, int pcm_dtype, int64_t n_samples, int32_t wi
                    double threshold, int adapt, double alpha, const double* window, const double* twiddle,
                    double* ltsd_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* kernels this library has launched so far in this process (all threads, all streams) */
+int64_t lnasr_launch_count(void);
+
 /* ================================ debug / bring-up ==============================================
  * One tcgen05.mma (M=128, N=128, K=8, kind::tf32) on caller-provided shared-memory images with caller-chosen
  * descriptor fields; used by tests/test_umma_probe.py to pin the descriptor semantics on hardware. */

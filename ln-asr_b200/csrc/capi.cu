@@ -1,9 +1,13 @@
 // capi.cu -- error reporting, version and device queries of liblnasr_b200.so (see include/lnasr_b200.h).
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace lnasr {
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 
@@ -55,6 +59,8 @@ __global__ void fp64_mma_probe_kernel(double* out, int iters) {
 }  // namespace lnasr
 
 using namespace lnasr;
+
+extern "C" int64_t lnasr_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 // Measured FP64 peak of the current device in TFLOP/s (2 flops per FMA), for the roofline denominators of the float64
 // kernels: kind 0 = DFMA (SIMT), 1 = mma.sync m8n8k4 f64 (tensor).  Synchronises the stream; scratch must hold

@@ -32,7 +32,14 @@ void set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
-#define LNASR_LAUNCH_CHECK() LNASR_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this macro: it also counts them (lnasr_launch_count: the benchmark's
+// "gpu_launches" is this counter's increase over the timed region, not an estimate)
+void count_launch();
+#define LNASR_LAUNCH_CHECK()                 \
+    do {                                     \
+        ::lnasr::count_launch();             \
+        LNASR_CUDA(cudaGetLastError());      \
+    } while (0)
 
 int sm_count();
 

@@ -25,7 +25,8 @@ constexpr int RAW_LD = 16;            // raw static row: 12 cepstra + energy, pa
 constexpr int MAX_THREADS = 512;      // 16 warps = 32 half-warps per SM (one block per SM); one frame per half-warp at a time
 constexpr int FRAMES_PER_RUN = 8;     // consecutive frames a warp walks (its two halves take alternate frames); small runs
                                       // keep the static schedule balanced for the few-ten-thousand-frame groups of the e2e path
-constexpr int STEPS_PER_RUN = FRAMES_PER_RUN / 2;
+constexpr int SHORT_RUN = 2;          // run length when the batch cannot give every resident warp a run of 8: one frame pair per warp,
+                                      // so a single utterance is one latency-bound step deep instead of four (config 5, batch 1)
 constexpr double COLSUM_SCALE = 4294967296.0;      // per-utterance column sums are 32.32 fixed point (|c| < 2^18, < 2^13 frames)
 constexpr int TR_LD = 17;             // padded row of the 16x16 complex transpose (conflict-free 16-byte rows)
 constexpr int MAX_SLOTS = MAX_MEL / 16;
@@ -40,6 +41,7 @@ __device__ __forceinline__ void mfcc_dmma884(double& c0, double& c1, double a, d
 struct MfccDev {
     int frame_len, frame_step, n_mel, n_ceps, fb_stride;
     int hpf_q;                        // round(100 * hpf_alpha) when that is an integer (exact int16 pre-emphasis), else -1
+    int frames_per_run;               // FRAMES_PER_RUN or SHORT_RUN
     double hpf_alpha;
     const double* window;
     const double2* twiddle;
@@ -257,7 +259,8 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     for (int i = b; i < MAX_MEL; i += 16) s_lm[i] = 0.0;                  // entries >= n_mel stay zero (k padding of the DCT)
     PcmT* stage = reinterpret_cast<PcmT*>(hbase + L.stage_off);
 
-    const int64_t n_runs = (total_frames + FRAMES_PER_RUN - 1) / FRAMES_PER_RUN;
+    const int fpr = P.frames_per_run, spr = fpr >> 1;
+    const int64_t n_runs = (total_frames + fpr - 1) / fpr;
     const int64_t warp_global = (int64_t)blockIdx.x * (n_threads >> 5) + (tid >> 5);
     const int64_t warp_stride = (int64_t)gridDim.x * (n_threads >> 5);
     const int partner = ((16 - b) & 15) + 16 * half;     // lane holding Z[256 - k] for my Z[k]
@@ -284,13 +287,13 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     bool act = false;
     int par = 0;                                         // position of x[-1] inside its 4-byte word
     auto locate = [&](int64_t step) -> bool {
-        const int64_t run = warp_global + (step / STEPS_PER_RUN) * warp_stride;
-        const int64_t f_pair = run * FRAMES_PER_RUN + 2 * (step % STEPS_PER_RUN);
+        const int64_t run = warp_global + (step / spr) * warp_stride;
+        const int64_t f_pair = run * fpr + 2 * (step % spr);
         if (run >= n_runs || f_pair >= total_frames) return false;
         f = f_pair + half;
         act = f < total_frames;
         if (act) {
-            if ((step % STEPS_PER_RUN) == 0 || ctx.u < 0) ctx = make_ctx(__ldg(run_utt + run));   // utterance of the run's first frame
+            if ((step % spr) == 0 || ctx.u < 0) ctx = make_ctx(__ldg(run_utt + run));   // utterance of the run's first frame
             if (f >= ctx.u_f1) {                         // walked into another utterance
                 int u = ctx.u;
                 int64_t f1 = ctx.u_f1;
@@ -510,9 +513,10 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
 }
 
 // utterance of the first frame of every run (so the frames kernel starts a run with one load instead of a binary search)
-__global__ void mfcc_run_index_kernel(const int64_t* __restrict__ frame_off, int n_utt, int64_t n_runs, int* __restrict__ run_utt) {
+__global__ void mfcc_run_index_kernel(const int64_t* __restrict__ frame_off, int n_utt, int64_t n_runs, int frames_per_run,
+                                      int* __restrict__ run_utt) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n_runs) run_utt[r] = find_utt(frame_off, n_utt, r * FRAMES_PER_RUN);
+    if (r < n_runs) run_utt[r] = find_utt(frame_off, n_utt, r * frames_per_run);
 }
 
 // Pass B.  One warp produces 30 consecutive frames (lanes 0,1 carry the two-frame halo); lane = frame so
@@ -613,7 +617,7 @@ extern "C" int lnasr_mfcc_workspace_bytes(int64_t total_frames, int32_t n_utt, s
     size_t raw = (size_t)total_frames * RAW_LD * sizeof(float);
     raw = (raw + 255) & ~(size_t)255;
     size_t col = ((size_t)n_utt * MAX_MEL * sizeof(double) + 255) & ~(size_t)255;
-    *bytes = raw + col + (size_t)ceil_div(total_frames, FRAMES_PER_RUN) * sizeof(int) + 256;
+    *bytes = raw + col + (size_t)ceil_div(total_frames, SHORT_RUN) * sizeof(int) + 256;
     return LNASR_OK;
 }
 
@@ -644,15 +648,17 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     LNASR_CUDA(cudaMemsetAsync(colsum, 0, (size_t)n_utt * MAX_MEL * sizeof(double), stream));
     const size_t col_bytes = ((size_t)n_utt * MAX_MEL * sizeof(double) + 255) & ~(size_t)255;
     int* run_utt = (int*)((char*)workspace + raw_bytes + col_bytes);
+    // runs of 8 frames per warp once there are enough frames to give every resident warp (16 per SM) such a run, else frame pairs
+    const int fpr = (total_frames >= (int64_t)FRAMES_PER_RUN * 16 * sm_count()) ? FRAMES_PER_RUN : SHORT_RUN;
     {
-        const int64_t nr = ceil_div(total_frames, FRAMES_PER_RUN);
-        mfcc_run_index_kernel<<<(unsigned)ceil_div(nr, 256), 256, 0, stream>>>(frame_offsets, n_utt, nr, run_utt);
+        const int64_t nr = ceil_div(total_frames, fpr);
+        mfcc_run_index_kernel<<<(unsigned)ceil_div(nr, 256), 256, 0, stream>>>(frame_offsets, n_utt, nr, fpr, run_utt);
         LNASR_LAUNCH_CHECK();
     }
 
     MfccDev P;
     P.frame_len = tb->frame_len; P.frame_step = tb->frame_step; P.n_mel = tb->n_mel; P.n_ceps = tb->n_ceps;
-    P.fb_stride = tb->fb_stride; P.hpf_alpha = tb->hpf_alpha; P.window = tb->window;
+    P.fb_stride = tb->fb_stride; P.hpf_alpha = tb->hpf_alpha; P.window = tb->window; P.frames_per_run = fpr;
     {
         const double q = tb->hpf_alpha * 100.0;
         const long qi = lround(q);
@@ -670,7 +676,7 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
         smem = (size_t)smem_layout(P.n_mel, P.fb_stride, n_cols, pcm_bytes, threads / 16).total * sizeof(double);
         if (smem <= 226 * 1024 || threads <= 64) break;
     }
-    const int64_t n_runs = ceil_div(total_frames, FRAMES_PER_RUN);
+    const int64_t n_runs = ceil_div(total_frames, fpr);
     int grid = (int)std::min<int64_t>(ceil_div(n_runs, threads / 32), (int64_t)sm_count());
     if (grid < 1) grid = 1;
     if (pcm_dtype == LNASR_DT_I16) {

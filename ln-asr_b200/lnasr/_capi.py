@@ -91,6 +91,7 @@ SIGNATURES = {
     "lnasr_hmm_fb_accumulate": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, vp]),
     "lnasr_hmm_mstep_finalize": (C.c_int, [vp, i32, i32, vp, vp, vp, vp]),
     "lnasr_baumwelch_xi": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp]),
+    "lnasr_launch_count": (i64, []),
     "lnasr_vad_num_frames": (i64, [i64, i32, i32]),
     "lnasr_vad_workspace_bytes": (sz, [i64, i32, i32]),
     "lnasr_vad_ltsd": (C.c_int, [vp, C.c_int, i64, i32, i32, i32, f64, C.c_int, f64, vp, vp, vp, vp, sz, vp]),

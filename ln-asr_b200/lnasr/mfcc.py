@@ -180,8 +180,8 @@ class MFCC:
         else:
             n_utt = len(s_off) - 1
             f_off = _dev.offsets_from_lengths(self.frame_counts(s_off))
-            s_off_d = _dev.to_dev(s_off, t.int64)
-            f_off_d = _dev.to_dev(f_off, t.int64)
+            meta = _dev.to_dev(np.concatenate([s_off, f_off]), t.int64)      # one upload for both offset arrays
+            s_off_d, f_off_d = meta[:n_utt + 1], meta[n_utt + 1:]
         total = int(f_off[-1])
         ncol = 3 * (self.cepstrum_num + 1)
         feats = feats_out if feats_out is not None else _dev.empty((total, ncol), t.float32)
