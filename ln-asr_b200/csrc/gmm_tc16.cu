@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
 
 using namespace lnasr;
 
-static int g_tc16_poly = 2;
+static int g_tc16_poly = 1;      // measured at config 4 (tools/bench_gmm.py): 5.03 / 4.68 / 5.05 / 5.51 ms for levels 0 / 1 / 2 / 3
 extern "C" int lnasr_debug_set_tc16_poly(int level) { g_tc16_poly = level; return LNASR_OK; }
 
 extern "C" int lnasr_gmm_tc16_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes) {
@@ -667,9 +667,10 @@ extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64
         LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         gmm_tc16_kernel<MASK><<<grid, HB_THREADS, smem, stream>>>(a);
         case 0:  LNASR_H16_LAUNCH(0x00) break;
-        case 1:  LNASR_H16_LAUNCH(0x24) break;          // pairs 2, 5       : 2 of 8
+        case 2:  LNASR_H16_LAUNCH(0x92) break;          // pairs 1, 4, 7    : 3 of 8
         case 3:  LNASR_H16_LAUNCH(0xAA) break;          // pairs 1, 3, 5, 7 : 4 of 8
-        default: LNASR_H16_LAUNCH(0x92) break;          // pairs 1, 4, 7    : 3 of 8
+        default: LNASR_H16_LAUNCH(0x24) break;          // pairs 2, 5       : 2 of 8 (the default: beyond a quarter the added
+                                                        // FMA-pipe instructions cost more issue slots than the MUFU time they save)
 #undef LNASR_H16_LAUNCH
     }
     LNASR_LAUNCH_CHECK();

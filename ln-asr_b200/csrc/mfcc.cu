@@ -14,6 +14,7 @@
 //   reference's row-0 rule (mfcc.py:162-172) exchanged through warp shuffles, coalesced 39-float rows.
 //
 // HBM traffic per frame: 320 B pcm (int16) + 64 B raw write + 64 B raw read + 156 B features.
+#include <type_traits>
 #include "common.cuh"
 
 namespace lnasr {
@@ -349,42 +350,51 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             const int rem = (int)min(rem64, (int64_t)(2 * FFT_N));
             const bool lead = s_start > 0;                                  // x[-1] exists
             const PcmT* sx = stage + par + 1;                               // sx[n] = x[n]
+            // CHK = false: the frame lies inside its utterance with a sample before it and 32 n_a after its origin (all but the
+            // first and the last two or three frames of an utterance): none of the per-sample edge tests is needed
+            auto load_frame = [&](auto chk) {
+                constexpr bool CHK = decltype(chk)::value;
 #pragma unroll
-            for (int a = 0; a < 16; ++a) {
-                v[a] = make_double2(0.0, 0.0);
-                if (a < n_a) {
-                    const int n0 = 32 * a + 2 * b;
-                    const bool ok0 = n0 < rem, ok1 = n0 + 1 < rem;
-                    PcmT xm, x0, x1;
-                    if (kIntPcm) {
-                        // x[n0-1], x[n0], x[n0+1] are 6 bytes inside two consecutive 4-byte words: two 32-bit loads and a funnel
-                        // shift instead of three 2-byte loads
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage) + ((par + n0) >> 1);
-                        const uint32_t w0 = wp[0], w1 = wp[1];
-                        const uint32_t lo = __funnelshift_r(w0, w1, 16 * par);
-                        xm = (PcmT)(short)(lo & 0xffffu);
-                        x0 = (PcmT)(short)(lo >> 16);
-                        x1 = (PcmT)(short)((w1 >> (16 * par)) & 0xffffu);
-                    } else {
-                        xm = sx[n0 - 1]; x0 = sx[n0]; x1 = sx[n0 + 1];
+                for (int a = 0; a < 16; ++a) {
+                    v[a] = make_double2(0.0, 0.0);
+                    if (a < n_a) {
+                        const int n0 = 32 * a + 2 * b;
+                        const bool ok0 = !CHK || n0 < rem, ok1 = !CHK || n0 + 1 < rem;
+                        PcmT xm, x0, x1;
+                        if (kIntPcm) {
+                            // x[n0-1], x[n0], x[n0+1] are 6 bytes inside two consecutive 4-byte words: two 32-bit loads and a
+                            // funnel shift instead of three 2-byte loads
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage) + ((par + n0) >> 1);
+                            const uint32_t w0 = wp[0], w1 = wp[1];
+                            const uint32_t lo = __funnelshift_r(w0, w1, 16 * par);
+                            xm = (PcmT)(short)(lo & 0xffffu);
+                            x0 = (PcmT)(short)(lo >> 16);
+                            x1 = (PcmT)(short)((w1 >> (16 * par)) & 0xffffu);
+                        } else {
+                            xm = sx[n0 - 1]; x0 = sx[n0]; x1 = sx[n0 + 1];
+                        }
+                        if (CHK) {
+                            if (!ok0) x0 = PcmT(0);
+                            if (!ok0 || !(n0 > 0 || lead)) xm = PcmT(0);
+                        }
+                        double y0, y1;
+                        if (int_path) {
+                            // y = x[t] - (q/100) x[t-1] = (100 x[t] - q x[t-1]) / 100, exact in int32; 1/100 is in s_win
+                            const int i0 = 100 * (int)x0 - P.hpf_q * (int)xm;
+                            const int i1 = ok1 ? 100 * (int)x1 - P.hpf_q * (int)x0 : 0;
+                            y0 = (double)i0;
+                            y1 = (double)i1;
+                        } else {
+                            // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
+                            y0 = (double)x0 - P.hpf_alpha * (double)xm;
+                            y1 = ok1 ? (double)x1 - P.hpf_alpha * (double)x0 : 0.0;
+                        }
+                        v[a] = make_double2(y0 * s_win[n0], y1 * s_win[n0 + 1]);
                     }
-                    if (!ok0) x0 = PcmT(0);
-                    if (!ok0 || !(n0 > 0 || lead)) xm = PcmT(0);
-                    double y0, y1;
-                    if (int_path) {
-                        // y = x[t] - (q/100) x[t-1] = (100 x[t] - q x[t-1]) / 100, exact in int32; 1/100 is in s_win
-                        const int i0 = 100 * (int)x0 - P.hpf_q * (int)xm;
-                        const int i1 = ok1 ? 100 * (int)x1 - P.hpf_q * (int)x0 : 0;
-                        y0 = (double)i0;
-                        y1 = (double)i1;
-                    } else {
-                        // y[0] = x[0]; y[t] = x[t] - alpha x[t-1]; samples past the end are zero AFTER filtering
-                        y0 = (double)x0 - P.hpf_alpha * (double)xm;
-                        y1 = ok1 ? (double)x1 - P.hpf_alpha * (double)x0 : 0.0;
-                    }
-                    v[a] = make_double2(y0 * s_win[n0], y1 * s_win[n0 + 1]);
                 }
-            }
+            };
+            if (act && lead && rem >= 32 * n_a) load_frame(std::false_type{});
+            else load_frame(std::true_type{});
         }
         const int64_t f_cur = f;
         const bool act_cur = act;

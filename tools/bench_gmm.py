@@ -44,7 +44,7 @@ def main():
             e = b[:4096].double() - b64
             print(f"poly level {level}: {ms:.3f} ms per {T} frames = {2 * 79 * 32000 * T / (ms * 1e-3) / 1e12:.0f} algorithmic TFLOP/s; "
                   f"err vs float64: mean {e.mean():+.3e} rms {e.pow(2).mean().sqrt():.3e} max {e.abs().max():.3e}")
-    lib.lnasr_debug_set_tc16_poly(2)
+    lib.lnasr_debug_set_tc16_poly(1)
 
 
 if __name__ == "__main__":
