@@ -320,8 +320,11 @@ int lnasr_debug_set_umma_swap(int swap);
  * backtrace; default), 1 = trellis_band_kernel + backtrace_kernel */
 int lnasr_debug_set_band_kernel(int version);
 /* lnasr_gmm_loglik_tc16: share of the mixture exponentials computed by polynomial on the FMA pipe instead of the MUFU
- * (0 = none, 1 = 2 of 8 pairs (default), 2 = 3 of 8, 3 = 4 of 8) */
+ * (0 = none (default), 1 = 2 of 8 pairs, 2 = 3 of 8, 3 = 4 of 8; environment LNASR_TC16_POLY) */
 int lnasr_debug_set_tc16_poly(int level);
+/* lnasr_gmm_loglik_tc16: 1 = all sixteen epilogue warps on every tile, 2 = two groups of eight on alternate tiles (default;
+ * environment LNASR_TC16_GROUPS) */
+int lnasr_debug_set_tc16_groups(int groups);
 /* lnasr_debug_umma_probe issues a second, accumulating MMA on the K chunks `byte_offset` further into both images
  * (0 = single MMA): measures how the fp32 TMEM accumulator rounds (tools/probe_umma_rounding.py) */
 int lnasr_debug_set_probe_second_mma(uint32_t byte_offset);

@@ -21,6 +21,7 @@
 // over tiles), warp 17 (one thread) issues the MMAs into one of two TMEM stages, and warps 0-15 run the epilogue (four per
 // TMEM lane quadrant, a quarter of the columns each) and write the results out through a shared-memory staging tile.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -355,13 +356,18 @@ __device__ __forceinline__ void h_lse_store(const float* v, const float* c_state
     }
 }
 
-template <int MP, int PARTS, int PMASK>
+// GROUPS = 1: all 16 epilogue warps work on every tile (four per TMEM lane quadrant, a quarter of the columns each).
+// GROUPS = 2: warps 0-7 take the even tiles (TMEM stage 0), warps 8-15 the odd ones (stage 1), two per quadrant and half of the
+// columns each.  With one group every warp waits for the same accumulator, loads it, runs its exponentials and writes out in
+// lock-step, so the MUFU idles during everybody's load and store phases; two groups working half a tile period apart keep it
+// fed.
+template <int MP, int PARTS, int PMASK, int GROUPS>
 __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base, const float* s_c, const float* s_cs, float* s_out,
                                            int warp, int lane, int wt, int64_t fs, int64_t fe, int n_tiles, uint32_t tile_cnt,
                                            uint64_t* t_full, uint64_t* t_empty) {
     const int NT = a.NT;
-    // PARTS = epilogue warps per TMEM lane quadrant: each takes 1/PARTS of the 16-column groups
-    const int quad = warp & 3, part = warp >> 2;
+    // PARTS = epilogue warps per TMEM lane quadrant (and group): each takes 1/PARTS of the 16-column groups
+    const int quad = warp & 3, part = (warp >> 2) % PARTS, group = (warp >> 2) / PARTS;
     const int row = quad * 32 + lane;
     const int st_tile0 = wt * a.SPT;
     const int st_end = min(a.n_states, st_tile0 + a.SPT);
@@ -382,6 +388,7 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t tc = tile_cnt + t;
         const uint32_t stage = tc & 1;
+        if (GROUPS == 2 && (int)stage != group) continue;          // the other group's tile
         mbar_wait(t_full + stage, (tc >> 1) & 1);
         tc_fence_after();
         const int64_t f = fs + (int64_t)t * H_BM + row;
@@ -394,10 +401,10 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
             // write per (frame, state) to rows 4 * ld_b bytes apart -- 750 M separate L2 write transactions per config-4
             // batch, which bounded the whole kernel (6.8 ms with them, 4.4 ms without).
             float* srow = s_out + (tc & 1) * (H_BM * H_OUT_LD) + row * H_OUT_LD;
-            if (MAXC == 4 && c16_end - c16_begin == 4) {
-                // the usual case (256-column tile, four warps per quadrant): this warp's 64 columns in two TMEM loads
+            if ((MAXC % 2) == 0 && c16_end - c16_begin == MAXC) {
+                // the usual case (256-column tile): this warp's 64 (128) columns in two (four) 32-column TMEM loads
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
+                for (int hh = 0; hh < MAXC / 2; ++hh) {
                     uint32_t raw[32];
                     tmem_ld32(taddr + (c16_begin + 2 * hh) * 16, raw);
 #pragma unroll
@@ -435,7 +442,7 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
             // (64 contiguous, aligned bytes per frame for 16 states: two whole sectors instead of 16 single-float writes).  The
             // barrier joins only the PARTS warps that share a TMEM lane quadrant = the same 32 frame rows; the staging buffers
             // alternate, so this one barrier per tile also protects the buffer's reuse two tiles later.
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(PARTS * 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad + 4 * group), "r"(PARTS * 32) : "memory");
             const float* sbuf = s_out + (tc & 1) * (H_BM * H_OUT_LD) + quad * 32 * H_OUT_LD;
             const int spt_e = st_end - st_tile0;
             const int64_t f0 = fs + (int64_t)t * H_BM + quad * 32;
@@ -450,6 +457,9 @@ __device__ __forceinline__ void h_epilogue(const H16Args& a, uint32_t tmem_base,
                 for (int rr = rsub + part; rr < rsub + (1 << lg); rr += PARTS, op += ostep, sp += PARTS * H_OUT_LD)
                     if (rr < rows) *op = *sp;
             }
+            // two groups: a group stages every one of its tiles in the same buffer, so the write-out above must be over
+            // before the quadrant's warps stage their next tile
+            if (GROUPS == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + quad + 4 * group), "r"(PARTS * 32) : "memory");
         }
     }
 }
@@ -499,7 +509,7 @@ __device__ __forceinline__ void h_mma_role(const H16Args& a, int lane, uint32_t 
 // warp, 1 MMA warp.  (18 warps are allocated as 20, so a thread has at most 96 registers.)
 constexpr int HB_EPI_WARPS = 16, HB_WARP_COPY = 16, HB_WARP_MMA = 17, HB_THREADS = 18 * 32;
 
-template <int PMASK>
+template <int PMASK, int GROUPS>
 __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
     extern __shared__ __align__(1024) uint8_t h_smem[];
     const int NT = a.NT;
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, HB_EPI_WARPS * 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, HB_EPI_WARPS / GROUPS * 32); }
         fence_barrier_init();
     }
     if (warp == HB_WARP_MMA) tmem_alloc(tmem_slot, 512);
@@ -570,13 +580,13 @@ __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
             __syncwarp();
         } else {
             // ===================== epilogue: warp w reads TMEM lanes 32 (w & 3) .. (= frame rows), a quarter of the columns
-            constexpr int P = HB_EPI_WARPS / 4;
+            constexpr int P = HB_EPI_WARPS / 4 / GROUPS;
             switch (a.Mp) {
-                case 16: h_epilogue<16, P, PMASK>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 8:  h_epilogue<8, P, PMASK>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 4:  h_epilogue<4, P, 0>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                case 2:  h_epilogue<2, P, 0>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
-                default: h_epilogue<1, P, 0>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 16: h_epilogue<16, P, PMASK, GROUPS>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 8:  h_epilogue<8, P, PMASK, GROUPS>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 4:  h_epilogue<4, P, 0, GROUPS>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                case 2:  h_epilogue<2, P, 0, GROUPS>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
+                default: h_epilogue<1, P, 0, GROUPS>(a, tmem_base, s_c, s_cs, s_out, warp, lane, wt, fs, fe, n_tiles, tile_cnt, t_full, t_empty); break;
             }
         }
         tile_cnt += n_tiles;
@@ -590,8 +600,15 @@ __global__ void __launch_bounds__(HB_THREADS, 1) gmm_tc16_kernel(H16Args a) {
 
 using namespace lnasr;
 
-static int g_tc16_poly = 1;      // measured at config 4 (tools/bench_gmm.py): 5.03 / 4.68 / 5.05 / 5.51 ms for levels 0 / 1 / 2 / 3
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
+// defaults from measurements at config 4 (tools/bench_gmm.py, bench.py); environment LNASR_TC16_POLY / LNASR_TC16_GROUPS override
+// config 4 inside the pipeline (bench.py, 60 steps): groups 1 / poly 0: 7.12 ms per step, 1 / 1: 7.03, 2 / 0: 6.71-6.78, 2 / 1: 6.79-6.81.
+// Two epilogue groups are worth 5 %; the polynomial exponentials help the lock-step epilogue (4.68 against 5.03 ms in isolation on
+// a cool chip) but not the staggered one, so they stay off by default.
+static int g_tc16_poly = env_int("LNASR_TC16_POLY", 0);
+static int g_tc16_groups = env_int("LNASR_TC16_GROUPS", 2) == 1 ? 1 : 2;
 extern "C" int lnasr_debug_set_tc16_poly(int level) { g_tc16_poly = level; return LNASR_OK; }
+extern "C" int lnasr_debug_set_tc16_groups(int groups) { g_tc16_groups = (groups == 2) ? 2 : 1; return LNASR_OK; }
 
 extern "C" int lnasr_gmm_tc16_packed_bytes(int32_t n_states, int32_t n_mix, int32_t dim, size_t* bytes) {
     H16Geom g;
@@ -664,13 +681,18 @@ extern "C" int lnasr_gmm_loglik_tc16(const float* feats, int32_t ld_feats, int64
     // share of the exponentials computed by polynomial on the FMA pipe (lnasr_debug_set_tc16_poly): mixture pairs of a state
     switch (g_tc16_poly) {
 #define LNASR_H16_LAUNCH(MASK)                                                                                                  \
-        LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-        gmm_tc16_kernel<MASK><<<grid, HB_THREADS, smem, stream>>>(a);
+        if (g_tc16_groups == 2) {                                                                                               \
+            LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel<MASK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gmm_tc16_kernel<MASK, 2><<<grid, HB_THREADS, smem, stream>>>(a);                                                    \
+        } else {                                                                                                                \
+            LNASR_CUDA(cudaFuncSetAttribute(gmm_tc16_kernel<MASK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gmm_tc16_kernel<MASK, 1><<<grid, HB_THREADS, smem, stream>>>(a);                                                    \
+        }
         case 0:  LNASR_H16_LAUNCH(0x00) break;
         case 2:  LNASR_H16_LAUNCH(0x92) break;          // pairs 1, 4, 7    : 3 of 8
         case 3:  LNASR_H16_LAUNCH(0xAA) break;          // pairs 1, 3, 5, 7 : 4 of 8
-        default: LNASR_H16_LAUNCH(0x24) break;          // pairs 2, 5       : 2 of 8 (the default: beyond a quarter the added
-                                                        // FMA-pipe instructions cost more issue slots than the MUFU time they save)
+        default: LNASR_H16_LAUNCH(0x24) break;          // pairs 2, 5       : 2 of 8 (beyond a quarter the added FMA-pipe
+                                                        // instructions cost more issue slots than the MUFU time they save)
 #undef LNASR_H16_LAUNCH
     }
     LNASR_LAUNCH_CHECK();
