@@ -10,6 +10,7 @@ Viterbi score max_j v[T-1, j], lowest index on ties.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import NamedTuple, Optional, Sequence
 
 import numpy as np
@@ -41,8 +42,13 @@ class PendingRecognition:
         return self._event is None or self._event.query()
 
     def _wait(self):
+        """Wait for the batch and take the results out of the pipeline's pinned staging buffers (which the pipeline reuses for
+        a later batch) into tensors this handle owns."""
         if self._event is not None:
             self._event.synchronize()
+            self._words, self._best = self._words.clone(), self._best.clone()
+            if self._paths is not None:
+                self._paths = self._paths.clone()
             self._event, self._keep = None, ()
 
     def result(self):
@@ -63,6 +69,28 @@ class PendingRecognition:
         for f0, f1 in self._path_blocks:
             out[:, f0:f1] = self._paths[self._K * f0:self._K * f1].view(self._K, f1 - f0)
         return out
+
+
+class _HostSlot:
+    """Device and pinned-host buffers of one host batch in flight.  AcousticPipeline keeps a few of these and reuses them
+    round-robin: a steady stream of batches then runs without a single allocation (a fresh multi-GB workspace from the caching
+    allocator, or a fresh pinned buffer, can cost a cudaMalloc / cudaHostAlloc that synchronises the device)."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.done = None          # event: every device-side use of the slot's buffers is over
+        self.handle = None        # weakref to the PendingRecognition whose results sit in the pinned buffers
+
+    def get(self, key, numel, dtype, device=None, pinned=False):
+        t = _dev.torch()
+        b = self.bufs.get(key)
+        if b is None or b.numel() < numel or b.dtype != dtype:
+            if b is not None:
+                t.cuda.synchronize()                                    # growing: nothing may still be using the old buffer
+            b = t.empty((max(int(numel), 1),), dtype=dtype, pin_memory=True) if pinned else \
+                t.empty((max(int(numel), 1),), dtype=dtype, device=device)
+            self.bufs[key] = b
+        return b[:numel]
 
 
 class ModelBank:
@@ -187,18 +215,30 @@ class AcousticPipeline:
         cur = t.cuda.current_stream()
         if not hasattr(self, "_streams"):
             self._streams = (t.cuda.Stream(), t.cuda.Stream(), t.cuda.Stream())
+            self._slots = [_HostSlot() for _ in range(3)]               # batches in flight / not yet collected
+            self._stream_bufs = [_HostSlot(), _HostSlot()]              # per compute stream: workspace, scratch paths
+            self._slot_i = 0
         copy_s, comp_a, comp_b = self._streams
         comps = (comp_a, comp_b) if n_compute_streams >= 2 else (comp_a,)
+        slot = self._slots[self._slot_i % len(self._slots)]
+        self._slot_i += 1
+        prev = slot.handle() if slot.handle is not None else None
+        if prev is not None:
+            prev._wait()                                                 # its results leave the pinned buffers before they are reused
         copy_s.wait_stream(cur)
+        if slot.done is not None:
+            # the batch that used this slot three submissions ago has left the device (its pinned offset buffer is about to be
+            # rewritten by the host, its device buffers by the copy stream); normally long complete
+            slot.done.synchronize()
         total_samples = int(off[-1] - off[0])
         events = []
+        pcm_dev = slot.get("pcm", total_samples, pcm_host.dtype, dev)
 
         def queue_pcm(lo, hi):
             s0, s1 = int(off[lo] - off[0]), int(off[hi] - off[0])
             pcm_dev[s0:s1].copy_(pcm_host[int(off[lo]):int(off[hi])], non_blocking=True)
 
         with t.cuda.stream(copy_s):
-            pcm_dev = t.empty((total_samples,), dtype=pcm_host.dtype, device=dev)
             queue_pcm(*bounds[0])
         # frame counts and offsets relative to each group's first sample / frame: [s_off | f_off] per group, one array
         n_fr = self.mfcc.frame_counts(off)
@@ -210,10 +250,12 @@ class AcousticPipeline:
             meta += [s_rel, f_rel]
             plan.append((pos, pos + len(s_rel), f_rel))
             pos += 2 * len(s_rel)
-        meta_host = t.from_numpy(np.concatenate(meta)).pin_memory()
+        meta_np = np.concatenate(meta)
+        meta_host = slot.get("meta_host", meta_np.size, t.int64, pinned=True)
+        meta_host.numpy()[:] = meta_np
+        meta_dev = slot.get("meta", meta_np.size, t.int64, dev)
         max_frames = max(int(p[2][-1]) for p in plan)
         with t.cuda.stream(copy_s):
-            meta_dev = t.empty((meta_host.numel(),), dtype=t.int64, device=dev)
             meta_dev.copy_(meta_host, non_blocking=True)
             for i, (lo, hi) in enumerate(bounds):
                 if i > 0:
@@ -223,28 +265,24 @@ class AcousticPipeline:
                 events.append(ev)
         for cs in comps:
             cs.wait_stream(cur)
-        with t.cuda.stream(comps[0]):
-            words = t.empty((n_utt,), dtype=t.int32, device=dev)
-            best = t.empty((n_utt,), dtype=t.float64, device=dev)
+        K = self.bank.K
+        total_frames = int(n_fr.sum())
+        words = slot.get("words", n_utt, t.int32, dev)
+        best = slot.get("best", n_utt, t.float64, dev)
+        paths_all = slot.get("paths", K * total_frames, t.int32, dev) if return_paths else None
         # groups alternate between the compute streams: the latency-bound tail of one group (Viterbi chains, kernel tails)
         # overlaps the head of the next.  One C call per group (lnasr_recognize_batch: MFCC -> emissions -> Viterbi -> word).
+        # Workspaces belong to a compute STREAM (stream order makes their reuse by the next group or batch safe).
         lib = _capi.lib()
         rec = self._recognizer_struct()
         max_utt = max(h - l for l, h in bounds)
-        K = self.bank.K
         need = C.c_size_t(0)
         _capi.check(lib.lnasr_recognize_workspace_bytes(max_frames, max_utt, C.byref(rec), int(want_paths), C.byref(need)),
                     "recognize_workspace_bytes")
-        ws, paths = [], []
-        total_frames = int(n_fr.sum())
+        ws = [self._stream_bufs[i].get("ws", need.value, t.uint8, dev) for i in range(len(comps))]
+        paths = [self._stream_bufs[i].get("paths", K * max_frames, t.int32, dev) if (want_paths and not return_paths) else None
+                 for i in range(len(comps))]
         f_start = np.concatenate([[0], np.cumsum([int(p[2][-1]) for p in plan])])
-        with t.cuda.stream(comps[0]):
-            paths_all = t.empty((K * total_frames,), dtype=t.int32, device=dev) if return_paths else None
-        for cs in comps:
-            with t.cuda.stream(cs):
-                cs.wait_stream(comps[0])
-                ws.append(t.empty((need.value,), dtype=t.uint8, device=dev))
-                paths.append(t.empty((K * max_frames,), dtype=t.int32, device=dev) if (want_paths and not return_paths) else None)
         isz = pcm_dev.element_size()
         code = _dev.np_dtype_code(pcm_dev.dtype)
         for i, ((lo, hi), (p0, p1, f_rel), ev) in enumerate(zip(bounds, plan, events)):
@@ -264,24 +302,21 @@ class AcousticPipeline:
                 _timeline.append((ev, done))
         for cs in comps[1:]:
             comps[0].wait_stream(cs)
+        out_w = slot.get("out_w", n_utt, t.int32, pinned=True)
+        out_b = slot.get("out_b", n_utt, t.float64, pinned=True)
+        out_p = slot.get("out_p", K * total_frames, t.int32, pinned=True) if return_paths else None
         with t.cuda.stream(comps[0]):
-            out_w = t.empty((n_utt,), dtype=t.int32, pin_memory=True)
-            out_b = t.empty((n_utt,), dtype=t.float64, pin_memory=True)
             out_w.copy_(words, non_blocking=True)
             out_b.copy_(best, non_blocking=True)
-            out_p = None
             if return_paths:
-                out_p = t.empty((K * total_frames,), dtype=t.int32, pin_memory=True)
                 out_p.copy_(paths_all, non_blocking=True)
             done = t.cuda.Event()
             done.record(comps[0])
-        for cs in comps:
-            for x in (pcm_dev, meta_dev, words, best) + ((paths_all,) if return_paths else ()):
-                x.record_stream(cs)
-        # the device buffers stay referenced by the handle until the result has been collected
+        slot.done = done
         blocks = [(int(f_start[i]), int(f_start[i + 1])) for i in range(len(plan))]
-        return PendingRecognition(out_w, out_b, done, (pcm_dev, meta_dev, words, best, ws, paths, paths_all, meta_host, pcm_host),
-                                  paths=out_p, path_blocks=blocks, n_models=K)
+        h = PendingRecognition(out_w, out_b, done, (pcm_host,), paths=out_p, path_blocks=blocks, n_models=K)
+        slot.handle = weakref.ref(h)
+        return h
 
     def _recognizer_struct(self):
         """lnasr_recognizer for the current device (cached; keeps the referenced structs alive)."""
