@@ -109,8 +109,8 @@ __host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int 
     // DCT matrix: [n][k < n_dct_cols], or -- when at most 16 coefficients are wanted (the feature path) -- the B operand of
     // the float64 tensor-core DCT: [n < n_mel rounded up to 4][DCT_LD] with zero padding
     L.dct = o;      o += (n_dct_cols <= 16) ? ((n_mel + 3) & ~3) * DCT_LD : n_mel * n_dct_cols;
-    L.fb_w = o;     o += (n_mel * fb_stride + 1) / 2;     // float weights
-    L.fb_meta = o;  o += (4 * MAX_MEL) / 2 + 2;           // ints: fb_start[64] | fb_len[64] | assign[64] | order[64] | flags
+    L.fb_w = o;     o += (((n_mel + 15) / 16) * fb_stride * 16 + 1) / 2;   // float weights [slot][tap][16 lanes], zero padded
+    L.fb_meta = o;  o += (4 * MAX_MEL) / 2 + 4;           // ints: fb_start[64] | fb_len[64] | assign[64] | order[64] | flags[8]: energy slot, slot lengths
     o = (o + 1) & ~1;
     L.per_hw = o;
     L.stage_off = 2 * 16 * TR_LD + MAX_MEL;               // transpose buffer | log-mel[64] | sample stage
@@ -186,7 +186,6 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         s_log[i] = make_double2(c, -log(c));
     }
     for (int i = tid; i < FFT_N; i += n_threads) s_win[i] = (i < P.frame_len) ? P.window[i] * (int_path ? 0.01 : 1.0) : 0.0;
-    for (int i = tid; i < P.n_mel * P.fb_stride; i += n_threads) s_fbw[i] = P.fb_weight[i];
     // DCT on the float64 tensor cores when at most 16 coefficients are wanted (features: 13); the API-parity path that returns
     // all n_mel cepstra keeps the SIMT loop
     const bool dct_mma = n_out <= 16;
@@ -249,6 +248,31 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     }
     __syncthreads();
     const bool energy_sep = s_flag[0] < 0;
+    // Banded mel weights transposed for the product loop: slot s runs L_s = the longest filter of the slot taps for ALL lanes
+    // (shorter filters are padded with zero weights), stored [tap][lane] so that the 16 lanes of a frame read 16 consecutive
+    // floats -- a uniform trip count (no divergence, no per-lane loop control) and conflict-free weight loads.
+    if (tid < n_slots) {
+        int L = 0;
+        for (int bb = 0; bb < 16; ++bb) {
+            const int m = s_asg[tid * 16 + bb];
+            if (m >= 0) L = max(L, s_fbl[m]);
+        }
+        s_flag[1 + tid] = L;
+    }
+    __syncthreads();
+    {
+        int base = 0;
+        for (int sl = 0; sl < n_slots; ++sl) {
+            const int L = s_flag[1 + sl];
+            for (int i = tid; i < L * 16; i += n_threads) {
+                const int tap = i >> 4, bb = i & 15;
+                const int m = s_asg[sl * 16 + bb];
+                s_fbw[base * 16 + i] = (m >= 0 && tap < s_fbl[m]) ? P.fb_weight[m * P.fb_stride + tap] : 0.f;
+            }
+            base += L;
+        }
+    }
+    __syncthreads();
 
     double* hbase = smem + L.per_hw + (tid >> 4) * L.per_hw_doubles;
     double2* tr = reinterpret_cast<double2*>(hbase);     // [16][TR_LD] complex
@@ -310,10 +334,17 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             const uintptr_t first = (uintptr_t)(pcm + ctx.u_s0 + (f - ctx.u_f0) * P.frame_step - 1);
             const uintptr_t w0 = first & ~(uintptr_t)3;
             par = (int)((first - w0) / sizeof(PcmT));
-            for (int j = b; j < n_words; j += 16) {
-                uintptr_t src = w0 + 4u * (uintptr_t)j;
-                src = src < pcm_lo ? pcm_lo : (src > pcm_hi ? pcm_hi : src);      // clamped words are never consumed
-                cp_async4(reinterpret_cast<char*>(stage) + 4 * j, reinterpret_cast<const void*>(src));
+            if (w0 >= pcm_lo && w0 + 4u * (uintptr_t)(n_words - 1) <= pcm_hi) {
+                // every word lies inside the PCM buffer (all frames but the first and the last few of the whole batch)
+                const char* src = reinterpret_cast<const char*>(w0) + 4 * b;
+                char* dst = reinterpret_cast<char*>(stage) + 4 * b;
+                for (int j = b; j < n_words; j += 16, src += 64, dst += 64) cp_async4(dst, src);
+            } else {
+                for (int j = b; j < n_words; j += 16) {
+                    uintptr_t src = w0 + 4u * (uintptr_t)j;
+                    src = src < pcm_lo ? pcm_lo : (src > pcm_hi ? pcm_hi : src);      // clamped words are never consumed
+                    cp_async4(reinterpret_cast<char*>(stage) + 4 * j, reinterpret_cast<const void*>(src));
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -435,27 +466,36 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+        // zero-weight taps of the padded mel loop may read up to fb_stride bins past bin 256: stale transpose data there must
+        // at least be finite (0 * NaN)
+        for (int i = lane; i < P.fb_stride; i += 32)
+            *reinterpret_cast<float2*>(s_pow - half + 2 * (HALF_N + 1 + i)) = make_float2(0.f, 0.f);
         __syncwarp();
         if (power_out && act_cur)
             for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = s_pow[2 * k] * (float)PSCALE;
         // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
+        int w_base = 0;
         for (int s = 0; s < n_slots; ++s) {
             const int m = s_asg[s * 16 + b];
+            const int L = s_flag[1 + s];
+            const float* w = s_fbw + w_base * 16 + b;
+            w_base += L;
             double e = esum;                                               // m == -2: ln of the frame energy (mfcc.py:158-160)
             if (m >= 0) {
                 const int k0 = s_fbs[m], len = s_fbl[m];
                 // The power spectrum is a set of positive numbers: once the float64 FFT has produced it, the banded sums are
                 // safe in float32 (<= 31 positive terms: relative error ~1e-6, i.e. ~1e-5 dB) -- half the shared-memory bytes
                 // of the hottest loop of this kernel, and FFMA instead of DFMA.  The energy sum above stays float64.
-                const float* w = s_fbw + m * P.fb_stride;
+                (void)len;
                 const float* pw = s_pow + 2 * k0;
-                float e0 = 0.f, e1 = 0.f;
+                float e0 = 0.f, e1 = 0.f;                                  // even / odd taps, as before (zero taps add exact zeros)
                 int t = 0;
-                for (; t + 1 < len; t += 2) {
-                    e0 = fmaf(w[t], pw[2 * t], e0);
-                    e1 = fmaf(w[t + 1], pw[2 * t + 2], e1);
+#pragma unroll 2
+                for (; t + 1 < L; t += 2) {
+                    e0 = fmaf(w[16 * t], pw[2 * t], e0);
+                    e1 = fmaf(w[16 * t + 16], pw[2 * t + 2], e1);
                 }
-                if (t < len) e0 = fmaf(w[t], pw[2 * t], e0);
+                if (t < L) e0 = fmaf(w[16 * t], pw[2 * t], e0);
                 e = (double)(e0 + e1);
             }
             e *= PSCALE;
