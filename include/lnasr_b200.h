@@ -67,6 +67,9 @@ typedef struct lnasr_mfcc_tables {
     const int32_t* fb_len;    /* [n_mel] number of consecutive non-zero bins */
     const float*   fb_weight; /* [n_mel, fb_stride] the non-zero weights of each triangular filter */
     const double*  dct_t;     /* [n_mel(n), n_mel(k)] DCT-II ortho matrix (float64), transposed: dct_t[n*n_mel+k] */
+    const int32_t* mel_plan;  /* optional: device buffer of lnasr_mfcc_mel_plan_bytes() bytes filled ONCE by lnasr_mfcc_mel_plan()
+                                 for this filter bank (how the kernel walks the banded product); NULL = lnasr_mfcc_batch
+                                 derives it in its workspace on every call (~25 us) */
 } lnasr_mfcc_tables;
 
 /* MFCC.calc_high_pass_filter (lnasr/mfcc.py:50-64) alone: y[0]=x[0]; y[t]=x[t]-alpha*x[t-1]; float64 out */
@@ -74,6 +77,9 @@ int lnasr_preemphasis(const void* pcm, int pcm_dtype /*I16|F32|F64*/, int64_t n_
                       double* out, void* stream);
 /* frames of one utterance: ceil(|S-(L-step)|/step), utils.py:118 (host helper, no device work) */
 int64_t lnasr_mfcc_num_frames(int64_t n_samples, int32_t frame_len, int32_t frame_step);
+/* the mel-product plan of a filter bank (see lnasr_mfcc_tables.mel_plan): reads n_mel, fb_stride, fb_start, fb_len, fb_weight */
+size_t lnasr_mfcc_mel_plan_bytes(void);
+int lnasr_mfcc_mel_plan(const lnasr_mfcc_tables* tables, int32_t* plan /*device out*/, void* stream);
 /* workspace bytes needed by lnasr_mfcc_batch */
 int lnasr_mfcc_workspace_bytes(int64_t total_frames, int32_t n_utt, size_t* bytes /*host out*/);
 /*

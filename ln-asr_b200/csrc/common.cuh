@@ -83,8 +83,15 @@ __device__ __forceinline__ double logaddexp_d(double a, double b) {
 // ln(x), table driven (used for log-mel energies and the mixture log-sum-exp): x = 2^E m, m in [1,2); table entry i = top 7 mantissa bits holds c = 1/(1+(i+1/2)/128)
 // and -ln c; r = m c - 1 has |r| < 2^-8 and ln(1+r) is a degree-6 polynomial (error r^7/7 < 3e-18).  8 DFMA instead
 // of the ~25 of log().  Zero, subnormal, inf and NaN go through log().
+__device__ __forceinline__ bool fast_log_ok(double x) { return x >= 1e-300 && x <= 1e300; }
+__device__ __forceinline__ double fast_log_core(double x, const double2* __restrict__ tab);
 __device__ __forceinline__ double fast_log(double x, const double2* __restrict__ tab) {
-    if (!(x >= 1e-300 && x <= 1e300)) return log(x);
+    if (!fast_log_ok(x)) return log(x);
+    return fast_log_core(x, tab);
+}
+// the branch-free part (x normal, positive): callers with several logarithms test fast_log_ok on all of them first, so that the
+// compiler can run the dependency chains side by side
+__device__ __forceinline__ double fast_log_core(double x, const double2* __restrict__ tab) {
     const int hi = __double2hiint(x);
     const int E = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));

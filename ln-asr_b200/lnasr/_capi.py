@@ -28,6 +28,7 @@ class MfccTables(C.Structure):
         ("frame_len", i32), ("frame_step", i32), ("fft_n", i32), ("n_mel", i32), ("n_ceps", i32),
         ("hpf_alpha", C.c_double), ("fb_stride", i32),
         ("window", vp), ("twiddle", vp), ("fb_start", vp), ("fb_len", vp), ("fb_weight", vp), ("dct_t", vp),
+        ("mel_plan", vp),
     ]
 
 
@@ -53,6 +54,8 @@ SIGNATURES = {
     "lnasr_preemphasis": (C.c_int, [vp, C.c_int, i64, f64, vp, vp]),
     "lnasr_mfcc_num_frames": (i64, [i64, i32, i32]),
     "lnasr_mfcc_workspace_bytes": (C.c_int, [i64, i32, C.POINTER(sz)]),
+    "lnasr_mfcc_mel_plan_bytes": (sz, []),
+    "lnasr_mfcc_mel_plan": (C.c_int, [C.POINTER(MfccTables), vp, vp]),
     "lnasr_mfcc_batch": (C.c_int, [vp, C.c_int, vp, vp, i32, i64, C.POINTER(MfccTables), vp, i32, vp, vp, vp, sz, vp]),
     "lnasr_gmm_exact_packed_doubles": (i64, [i32, i32, i32]),
     "lnasr_gmm_pack_exact": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp]),

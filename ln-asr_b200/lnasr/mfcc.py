@@ -112,7 +112,12 @@ class MFCC:
             n_ceps=self.cepstrum_num, hpf_alpha=float(self.hpf_alpha), fb_stride=stride,
             window=keep["window"].data_ptr(), twiddle=keep["twiddle"].data_ptr(),
             fb_start=keep["fb_start"].data_ptr(), fb_len=keep["fb_len"].data_ptr(),
-            fb_weight=keep["fb_weight"].data_ptr(), dct_t=keep["dct_t"].data_ptr())
+            fb_weight=keep["fb_weight"].data_ptr(), dct_t=keep["dct_t"].data_ptr(), mel_plan=None)
+        # the mel-product plan of this filter bank, derived once on the device (lnasr_mfcc_mel_plan)
+        lib = _capi.lib()
+        keep["mel_plan"] = t.empty((int(lib.lnasr_mfcc_mel_plan_bytes()),), dtype=t.uint8, device="cuda")
+        _capi.check(lib.lnasr_mfcc_mel_plan(C.byref(tb), _capi.ptr(keep["mel_plan"]), _capi.stream_ptr()), "mfcc_mel_plan")
+        tb.mel_plan = keep["mel_plan"].data_ptr()
         self._tables[dev] = (tb, keep)
         return tb
 

@@ -79,6 +79,16 @@ def test_decode_chain_stays_inside_its_buffers(emission, n, m):
     g_ws.check("mfcc workspace")
     feats = g_feats.view(t.float32, (total, 39))
     assert torch.equal(feats.nan_to_num(), mb.feats.nan_to_num())
+    # the same call without a prepared mel plan (lnasr_mfcc_tables.mel_plan = NULL): planned inside the workspace, same bits
+    tb2 = _capi.MfccTables.from_buffer_copy(tb)
+    tb2.mel_plan = None
+    g_feats2, g_ws2 = Guarded(total * 39 * 4), Guarded(need.value)
+    _capi.check(lib.lnasr_mfcc_batch(_capi.ptr(pcm_d), _capi.DT_I16, s_off, f_off, n_utt, total, C.byref(tb2), g_feats2.ptr, 39, None, None,
+                                     g_ws2.ptr, need.value, st), "mfcc_batch")
+    torch.cuda.synchronize()
+    g_feats2.check("mfcc features (own plan)")
+    g_ws2.check("mfcc workspace (own plan)")
+    assert torch.equal(g_feats2.view(t.float32, (total, 39)).nan_to_num(), feats.nan_to_num())
 
     # ---- emissions alone (tensor-core kernels: workspace = operand images + flags)
     ncol = K * n

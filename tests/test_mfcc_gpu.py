@@ -120,3 +120,32 @@ def test_fuzz_lengths_and_alignments(mfcc):
         for u, s in enumerate(batch):
             _, _, F = O.mfcc(s.astype(np.float64))
             assert_close(feats[off[u]:off[u + 1]], F, 1e-4, f"utt{u} len {lens[u]} float={as_float}")
+
+
+def test_filter_bank_without_triangle_structure(monkeypatch):
+    """The frames kernel sums mel energies per interval between filter peaks (a bin feeds at most two neighbouring triangles,
+    mfcc.py:66-106).  A bank that is NOT of that shape -- every bin inside three wide filters -- must take the kernel's general
+    plan (one interval per filter support) and still equal power . bank^T."""
+    from lnasr.mfcc import MFCC
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(5)
+    n_mel = 20
+    bank = np.zeros((n_mel, 257))
+    for m in range(n_mel):
+        lo = 11 * m
+        bank[m, lo:lo + 33] = rng.uniform(0.1, 1.0, size=33)
+    bank[:, 257:] = 0.0
+
+    class WideBank(MFCC):
+        def create_filter_bank(self):
+            return bank.copy()
+
+    monkeypatch.setattr(O, "mel_filter_bank", lambda p=None: bank.copy())
+    m = WideBank(mfbank_num=n_mel)
+    p = O.MfccParams(mfbank_num=n_mel)
+    x = np.clip(np.round(3000.0 * rng.standard_normal(12000)), -32767, 32767).astype(np.int16)
+    P, C, F = m.calc_mfcc(x)
+    Pr, Cr, Fr = O.mfcc(x.astype(np.float64), p)
+    assert_close(P, Pr, 1e-4, "power")
+    assert_close(C, Cr, 1e-4, "cepstrum")
+    assert_close(F, Fr, 1e-4, "features")
