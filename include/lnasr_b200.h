@@ -83,7 +83,7 @@ int lnasr_mfcc_mel_plan(const lnasr_mfcc_tables* tables, int32_t* plan /*device 
 /* workspace bytes needed by lnasr_mfcc_batch */
 int lnasr_mfcc_workspace_bytes(int64_t total_frames, int32_t n_utt, size_t* bytes /*host out*/);
 /*
- * pcm            : concatenated samples, int16 (LNASR_DT_I16) or float32 (LNASR_DT_F32)
+ * pcm            : concatenated samples, int16 (LNASR_DT_I16), float32 (LNASR_DT_F32) or float64 (LNASR_DT_F64)
  * sample_offsets : [n_utt+1] int64, device
  * frame_offsets  : [n_utt+1] int64, device; frame_offsets[u+1]-frame_offsets[u] must equal
  *                  lnasr_mfcc_num_frames(samples of u) and be >= 2 (the reference needs row 1, mfcc.py:164)

@@ -246,9 +246,8 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     // with the trip counts of the per-frame loops known to the compiler
     const int n_a = kStd ? STD_NA : ((P.frame_len + 31) >> 5);
     constexpr double PSCALE = 1.0 / (4.0 * FFT_N);       // the split below works on 2X
-    constexpr int SPW = 4 / (int)sizeof(PcmT);           // samples per 4-byte word
     constexpr int SPQ = 16 / (int)sizeof(PcmT);          // samples per 16-byte chunk
-    const int n_words = (32 * n_a + 2 + SPW) / SPW + 1;  // words covering x[-1 .. 32 n_a] at any alignment
+    const int n_words = ((32 * n_a + 2) * (int)sizeof(PcmT) + 3) / 4 + 2;   // 4-byte words covering x[-1 .. 32 n_a] at any alignment
     const int n_quads = (32 * n_a + 2 + 2 * SPQ - 2) / SPQ;   // 16-byte chunks covering them from any position inside the first
     const uintptr_t pcm_end = (uintptr_t)(pcm + __ldg(sample_off + n_utt)) - 1;      // last byte of the batch
     const uintptr_t pcm_lo = (uintptr_t)pcm & ~(uintptr_t)3, pcm_hi = pcm_end & ~(uintptr_t)3;
@@ -909,7 +908,8 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
                                 float* ceps_out, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LNASR_CHECK_ARG(pcm && sample_offsets && frame_offsets && tb && feats && workspace, "mfcc_batch: null pointer");
-    LNASR_CHECK_ARG(pcm_dtype == LNASR_DT_I16 || pcm_dtype == LNASR_DT_F32, "mfcc_batch: pcm dtype must be int16 or float32");
+    LNASR_CHECK_ARG(pcm_dtype == LNASR_DT_I16 || pcm_dtype == LNASR_DT_F32 || pcm_dtype == LNASR_DT_F64,
+                    "mfcc_batch: pcm dtype must be int16, float32 or float64");
     LNASR_CHECK_ARG(tb->fft_n == FFT_N, "mfcc_batch: only fft_N=512 is built (got %d)", tb->fft_n);
     LNASR_CHECK_ARG(tb->frame_len >= 2 && tb->frame_len <= FFT_N && tb->frame_step >= 1, "mfcc_batch: frame_len must be in [2,512]");
     LNASR_CHECK_ARG(tb->n_mel >= 2 && tb->n_mel <= MAX_MEL, "mfcc_batch: n_mel must be in [2,64]");
@@ -955,7 +955,7 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     P.fb_weight = tb->fb_weight; P.dct_t = tb->dct_t;
 
     // one block per SM, as many half-warps (frames in flight) as shared memory allows, at most 32
-    const int pcm_bytes = (pcm_dtype == LNASR_DT_I16) ? 2 : 4;
+    const int pcm_bytes = (pcm_dtype == LNASR_DT_I16) ? 2 : (pcm_dtype == LNASR_DT_F32 ? 4 : 8);
     const int n_cols = ceps_out ? P.n_mel : P.n_ceps + 1;
     int threads = MAX_THREADS;
     size_t smem = 0;
@@ -976,8 +976,10 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     int rc;
     if (pcm_dtype == LNASR_DT_I16)
         rc = std_shape ? launch(mfcc_frames_kernel<int16_t, true>, (const int16_t*)pcm) : launch(mfcc_frames_kernel<int16_t, false>, (const int16_t*)pcm);
-    else
+    else if (pcm_dtype == LNASR_DT_F32)
         rc = std_shape ? launch(mfcc_frames_kernel<float, true>, (const float*)pcm) : launch(mfcc_frames_kernel<float, false>, (const float*)pcm);
+    else   // float64 samples (what the reference's callers pass, mfcc.py:108): staged as doubles, fewer frames in flight per SM
+        rc = launch(mfcc_frames_kernel<double, false>, (const double*)pcm);
     if (rc != LNASR_OK) return rc;
     LNASR_LAUNCH_CHECK();
     const int64_t n_tiles = ceil_div(total_frames, FIN_FRAMES);

@@ -167,17 +167,23 @@ class MFCC:
         lib = _capi.lib()
         if sample_offsets is None:
             arrs = [np.asarray(s) for s in signals]
-            all_i16 = all(a.dtype == np.int16 for a in arrs)
-            pcm_host, s_off = _dev.pack_ragged(arrs, np.int16 if all_i16 else np.float32)
-            pcm = _dev.to_dev(pcm_host, t.int16 if all_i16 else t.float32)
+            # int16 and float32 audio stay as they are; anything else is scored from float64 samples like the reference does
+            if all(a.dtype == np.int16 for a in arrs):
+                nd, td = np.int16, t.int16
+            elif all(a.dtype == np.float32 for a in arrs):
+                nd, td = np.float32, t.float32
+            else:
+                nd, td = np.float64, t.float64
+            pcm_host, s_off = _dev.pack_ragged(arrs, nd)
+            pcm = _dev.to_dev(pcm_host, td)
         else:
             s_off = sample_offsets if _plan is not None else np.asarray(sample_offsets, dtype=np.int64)
             if isinstance(signals, t.Tensor):
-                pcm = signals if signals.dtype in (t.int16, t.float32) else signals.to(t.float32)
+                pcm = signals if signals.dtype in (t.int16, t.float32, t.float64) else signals.to(t.float64)
                 pcm = _dev.to_dev(pcm)
             else:
                 a = np.asarray(signals)
-                pcm = _dev.to_dev(a if a.dtype == np.int16 else a.astype(np.float32))
+                pcm = _dev.to_dev(a if a.dtype in (np.int16, np.float32, np.float64) else a.astype(np.float64))
         ws = None
         if _plan is not None:
             s_off_d, f_off_d, f_off, ws = _plan

@@ -149,3 +149,32 @@ def test_filter_bank_without_triangle_structure(monkeypatch):
     assert_close(P, Pr, 1e-4, "power")
     assert_close(C, Cr, 1e-4, "cepstrum")
     assert_close(F, Fr, 1e-4, "features")
+
+
+def test_float64_samples_are_not_narrowed(mfcc):
+    """The reference takes float64 audio as it is (mfcc.py:108, e.g. samples normalised to [-1, 1]).  Such samples go through the
+    C ABI as float64 (LNASR_DT_F64): same results as the oracle, and not the results of the same audio rounded to float32."""
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(99)
+    n = 16000
+    t = np.arange(n) / 16000.0
+    x = (0.3 * np.sin(2 * np.pi * 173.0 * t) + 0.05 * rng.standard_normal(n)) / 3.0          # float64, not float32-representable
+    assert x.dtype == np.float64 and not np.array_equal(x, x.astype(np.float32).astype(np.float64))
+    P, C, F = mfcc.calc_mfcc(x)
+    Pr, Cr, Fr = O.mfcc(x)
+    assert_close(P, Pr, 1e-4, "power")
+    assert_close(C, Cr, 1e-4, "cepstrum")
+    assert_close(F, Fr, 1e-4, "features")
+    # power is returned as float32: compare where it is well above the float32 rounding of the narrowed input
+    P32, _, _ = mfcc.calc_mfcc(x.astype(np.float32))
+    rel64 = np.abs(P - Pr) / Pr
+    rel32 = np.abs(P32 - Pr) / Pr
+    assert np.median(rel64) < 2e-7                       # float32 storage of the result
+    assert rel32.max() > 10 * rel64.max()                # the narrowed input is visibly different in the weakest bins
+    # a ragged batch mixing float64 utterances of different lengths
+    sigs = [x[:4000], x[100:9000], x[5:805]]
+    res = mfcc.calc_mfcc_batch(sigs)
+    off = res.frame_offsets_host
+    feats = res.feats.double().cpu().numpy()
+    for u, s in enumerate(sigs):
+        assert_close(feats[off[u]:off[u + 1]], O.mfcc(s)[2], 1e-4, f"float64 utt {u}")
