@@ -334,6 +334,8 @@ int lnasr_debug_set_tc16_groups(int groups);
 /* lnasr_debug_umma_probe issues a second, accumulating MMA on the K chunks `byte_offset` further into both images
  * (0 = single MMA): measures how the fp32 TMEM accumulator rounds (tools/probe_umma_rounding.py) */
 int lnasr_debug_set_probe_second_mma(uint32_t byte_offset);
+/* lnasr_em_statistics_ws (N > 32): 1 = the SIMT moments kernel also where the FP64 tensor-core one would run (dim <= 39) */
+int lnasr_debug_set_em_moments_simt(int on);
 
 #ifdef __cplusplus
 }

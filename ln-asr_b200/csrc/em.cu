@@ -964,6 +964,213 @@ __global__ void __launch_bounds__(256) em_moments_kernel(EmGen g, const void* __
     if (tid < ng && s0 != 0.0) atomicAdd(S0 + jm0 + tid, s0);
 }
 
+// The same moments on the FLOAT64 TENSOR CORES (dim <= 39).  S0 / S1 / S2 of a tile of Gaussians are one contraction over
+// frames,  S[g, :] = sum_t occ[t, g] . [x'^2 | x' | 1][t, :]  with x' = x - c (c = mu_old of the tile's first Gaussian: raw moments
+// about a point inside the tile's cloud instead of the origin), as mma.sync.m8n8k4.f64 with M = Gaussians, K = frames, N = the
+// 80 moment columns [x'0^2, x'0, x'1^2, x'1, ... | 1 | 0].  The SIMT kernel above loads two shared-memory operands per
+// multiply-add pair (it ran at 4x its FP64 time, bound by shared memory); here 12 fragment loads feed 20 DMMAs = 5120
+// multiply-adds.  Block = 8 warps = 2 halves of the 32 Gaussians x 4 slices of the 32 staged frames; every warp keeps its
+// 16 x 80 partial sums in registers for its whole frame range.  At the flush a thread holds S2', S1' of one (Gaussian, dim)
+// pair, which is all the conversion to the accumulators' form needs (both linear in the partial sums, so every warp converts
+// and adds its own):  S1 = S1' + c S0,  S2c = sum occ (x - mu_old)^2 = S2' - 2 (mu_old - c) S1' + (mu_old - c)^2 S0.
+constexpr int EMM_LDA = 36;     // occupancy row stride (doubles): 4 frames x 8 Gaussians of a fragment fall into 32 distinct banks
+constexpr int EMM_COLS = 80;
+constexpr int EMM_LDB = 84;     // moment row stride, same property
+
+__device__ __forceinline__ void em_dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int EMM_THREADS = 256;      // 8 warps = 2 halves of the 32 Gaussians x 4 slices of the round's frames
+constexpr int EMM_FT = 32;            // frames per round
+constexpr int EMM_KS = EMM_THREADS / 64;                        // frame slices
+constexpr int EMM_KSTEPS = EMM_FT / 4 / EMM_KS;                 // k-steps (4 frames) per warp and round
+constexpr int EMM_STAGES = 1;         // rounds in flight (2 = one more round ahead: 86 KB of slots, one block per SM -- slower)
+constexpr int EMM_OQ = EMM_FT * EMG_GT / EMM_THREADS;           // (frame, Gaussian) pairs per thread and round
+constexpr int EMM_RAW_OCC = 4 * EMM_OQ;                         // raw slots per thread: (alpha, beta, b, bm) of each pair
+constexpr int EMM_RAW_X = (EMM_FT * 39 + EMM_THREADS - 1) / EMM_THREADS;      // + its feature values
+constexpr int EMM_RAW = EMM_RAW_OCC + EMM_RAW_X;
+constexpr size_t EMM_RAW_BYTES = (size_t)EMM_STAGES * EMM_RAW * EMM_THREADS * sizeof(double);
+
+// exp(d) for d <= 0 without a table (the shared-memory table of fast_exp_neg is read at random: ~2.5 wavefronts per warp, in
+// a kernel that runs out of shared-memory bandwidth first): d = n ln2 + r, |r| <= ln2 / 2, Taylor to r^13 (< 4e-18)
+__device__ __forceinline__ double exp_neg_poly(double d) {
+    const bool ok = d > -700.0;
+    const double dc = ok ? d : -700.0;
+    const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52: the integer lands in the low word
+    double nf = fma(dc, 1.4426950408889634, MAGIC);
+    const int n = __double2loint(nf);
+    nf -= MAGIC;
+    double r = fma(nf, -0.6931471803691238, dc);                    // ln2, high part (32 significant bits)
+    r = fma(nf, -1.9082146973659064e-10, r);                        //      low part
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return ok ? v : 0.0;
+}
+
+__device__ __forceinline__ void em_cp_async(void* smem_dst, const void* gmem_src, int bytes8) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (bytes8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// The inputs of a round (32 frames) are fetched by cp.async into PRIVATE shared-memory slots (raw[stage][slot][thread]) a
+// round ahead, while the tensor cores work: nothing but the thread's own wait_group stands between a value and its use, and
+// no register is held across the latency (bm is streamed from HBM once: ~2 us away).  Two blocks per SM.
+__global__ void __launch_bounds__(EMM_THREADS, 2) em_moments_mma_kernel(EmGen g, const void* __restrict__ feats, int feats_f64,
+                                                                        int ld_feats, const double* __restrict__ bm,
+                                                                        const double* __restrict__ logw, const double* __restrict__ mu,
+                                                                        int M, int D, int64_t frames_per_block, double* __restrict__ acc) {
+    extern __shared__ __align__(16) double emm_raw[];       // [EMM_STAGES][EMM_RAW][EMM_THREADS]
+    __shared__ double occ_s[EMM_FT][EMM_LDA];
+    __shared__ __align__(16) double x_s[EMM_FT][EMM_LDB];
+    __shared__ double c_s[40];
+    __shared__ double z_s[EMM_STAGES][EMM_FT];              // Z_t of the round's frames (one copy per frame, read by broadcast)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, N = g.N, NM = N * M;
+    const int gh = warp & 1, ks = warp >> 1;               // half of the Gaussian tile, slice of the staged frames
+    const int fr4 = lane & 3, r8 = lane >> 2;
+    const int jm0 = blockIdx.y * EMG_GT;
+    const int ng = min(EMG_GT, NM - jm0);
+    const int64_t t_begin = (int64_t)blockIdx.x * frames_per_block, t_end = min(g.total, t_begin + frames_per_block);
+    if (tid < 40) c_s[tid] = (tid < D) ? mu[(int64_t)jm0 * D + tid] : 0.0;
+    for (int i = tid; i < EMM_FT * EMM_LDB; i += EMM_THREADS) {
+        const int c = i % EMM_LDB;
+        (&x_s[0][0])[i] = (c == 2 * D) ? 1.0 : 0.0;        // the constant column; the padding columns stay zero
+    }
+    double d[2][EMM_COLS / 8][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < EMM_COLS / 8; ++nb) d[mb][nb][0] = d[mb][nb][1] = 0.0;
+    // my (frame, Gaussian) pairs of a round: frames warp + 8 q, Gaussian lane; my feature values: elements tid + 256 q of [32][D]
+    const int gq = lane, jm = jm0 + gq, jst = (gq < ng) ? jm / M : 0;
+    const double lw = (gq < ng) ? logw[jm] : 0.0;
+    const uint32_t d_magic = 0xffffffffu / (uint32_t)D + 1u;      // i / D = umulhi(i, d_magic) for i < 2^16
+    auto prefetch = [&](int64_t t0, int stage) {
+        if (t0 < t_end) {
+            const int nt = (int)min((int64_t)EMM_FT, t_end - t0);
+            double* raw = emm_raw + (size_t)stage * EMM_RAW * EMM_THREADS + tid;
+            if (gq < ng) {
+#pragma unroll
+                for (int q = 0; q < EMM_OQ; ++q) {
+                    const int tt = warp + (EMM_THREADS / 32) * q;
+                    if (tt < nt) {
+                        const int64_t t = t0 + tt;
+                        em_cp_async(raw + (4 * q + 0) * EMM_THREADS, g.alpha + t * N + jst, 1);
+                        em_cp_async(raw + (4 * q + 1) * EMM_THREADS, g.beta + t * N + jst, 1);
+                        em_cp_async(raw + (4 * q + 2) * EMM_THREADS, g.b + t * N + jst, 1);
+                        em_cp_async(raw + (4 * q + 3) * EMM_THREADS, bm + t * NM + jm, 1);
+                    }
+                }
+            }
+            if (tid < nt) em_cp_async(&z_s[stage][tid], g.z + t0 + tid, 1);
+#pragma unroll
+            for (int q = 0; q < EMM_RAW_X; ++q) {
+                const int i = tid + EMM_THREADS * q, r = (D == 1) ? i : (int)__umulhi((uint32_t)i, d_magic), dd = i - r * D;
+                if (r < nt) {
+                    const int64_t row = t0 + r;
+                    if (feats_f64) em_cp_async(raw + (EMM_RAW_OCC + q) * EMM_THREADS, (const double*)feats + row * ld_feats + dd, 1);
+                    else em_cp_async(raw + (EMM_RAW_OCC + q) * EMM_THREADS, (const float*)feats + row * ld_feats + dd, 0);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(t_begin, 0);
+    if (EMM_STAGES == 2) prefetch(t_begin + EMM_FT, 1);
+    __syncthreads();
+    int stage = 0;
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += EMM_FT, stage = (stage + 1) % EMM_STAGES) {
+        const int nt = (int)min((int64_t)EMM_FT, t_end - t0);
+        asm volatile("cp.async.wait_group %0;" ::"n"(EMM_STAGES - 1) : "memory");       // this round's inputs have landed
+        const double* raw = emm_raw + (size_t)stage * EMM_RAW * EMM_THREADS + tid;
+        // mixture occupancies for ALL t (gmmhmm.py:98-100): exp(alpha + beta - Z + log w + bm - b)
+#pragma unroll
+        for (int q = 0; q < EMM_OQ; ++q) {
+            const int tt = warp + (EMM_THREADS / 32) * q;
+            double o = 0.0;
+            if (tt < nt && gq < ng) {
+                const double ab = raw[(4 * q + 0) * EMM_THREADS] + raw[(4 * q + 1) * EMM_THREADS];
+                const double bj = raw[(4 * q + 2) * EMM_THREADS], Z = z_s[stage][tt];
+                if (ab != neg_inf() && Z != neg_inf() && Z == Z && bj != neg_inf())
+                    o = exp_neg_poly(ab - Z + lw + raw[(4 * q + 3) * EMM_THREADS] - bj);
+            }
+            occ_s[tt][gq] = o;
+        }
+#pragma unroll
+        for (int q = 0; q < EMM_RAW_X; ++q) {
+            const int i = tid + EMM_THREADS * q, r = (D == 1) ? i : (int)__umulhi((uint32_t)i, d_magic), dd = i - r * D;
+            if (r < EMM_FT) {
+                double xv = 0.0;                           // rows past the range: zero moments (their occupancies are zero too)
+                if (r < nt) {
+                    const double* slot = raw + (EMM_RAW_OCC + q) * EMM_THREADS;
+                    xv = (feats_f64 ? *slot : (double)*reinterpret_cast<const float*>(slot)) - c_s[dd];
+                }
+                *reinterpret_cast<double2*>(&x_s[r][2 * dd]) = make_double2(xv * xv, xv);
+            }
+        }
+        __syncthreads();                                   // (also: every thread has read z_s[stage] before the prefetch rewrites it)
+        prefetch(t0 + EMM_STAGES * EMM_FT, stage);         // into the slots just consumed
+#pragma unroll
+        for (int kk = 0; kk < EMM_KSTEPS; ++kk) {
+            const int fr = 4 * (ks * EMM_KSTEPS + kk) + fr4;
+            const double a0 = occ_s[fr][16 * gh + r8], a1 = occ_s[fr][16 * gh + 8 + r8];
+            const double* xr = &x_s[fr][r8];
+#pragma unroll
+            for (int nb = 0; nb < EMM_COLS / 8; ++nb) {
+                const double bv = xr[8 * nb];
+                em_dmma884(d[0][nb][0], d[0][nb][1], a0, bv);
+                em_dmma884(d[1][nb][0], d[1][nb][1], a1, bv);
+            }
+        }
+        __syncthreads();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // flush: thread = (Gaussian row r8 of block mb, dims 4 nb + fr4): d[mb][nb] = (S2', S1'); S0 sits in the constant column
+    double* S0 = acc;
+    double* S1 = acc + NM;
+    double* S2 = S1 + (int64_t)NM * D;
+    const int nb1 = (2 * D) >> 3, q1 = ((2 * D) & 7) >> 1;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        double s0v = 0.0;
+#pragma unroll
+        for (int nb = 0; nb < EMM_COLS / 8; ++nb)
+            if (nb == nb1) s0v = d[mb][nb][0];
+        const double s0 = shfl_d(s0v, (lane & ~3) | q1);
+        const int gq = 16 * gh + 8 * mb + r8;
+        if (gq < ng) {
+            if (fr4 == q1 && s0 != 0.0) atomicAdd(S0 + jm0 + gq, s0);
+#pragma unroll
+            for (int nb = 0; nb < EMM_COLS / 8; ++nb) {
+                const int dd = 4 * nb + fr4;
+                if (dd < D) {
+                    const double s2p = d[mb][nb][0], s1p = d[mb][nb][1];
+                    const double c = c_s[dd], dl = mu[(int64_t)(jm0 + gq) * D + dd] - c;
+                    const double s1 = fma(c, s0, s1p);
+                    const double s2 = fma(dl, fma(dl, s0, -2.0 * s1p), s2p);
+                    if (s1 != 0.0) atomicAdd(S1 + (int64_t)(jm0 + gq) * D + dd, s1);
+                    if (s2 != 0.0) atomicAdd(S2 + (int64_t)(jm0 + gq) * D + dd, s2);
+                }
+            }
+        }
+    }
+}
+
 // discrete emissions: gamma_sum[i] += exp gamma[t,i], B_sum[i, obs[t]] += exp gamma[t,i] for t < T-1 (hmm.py:202-225)
 __global__ void __launch_bounds__(256) em_discrete_kernel(EmGen g, const int32_t* __restrict__ obs, int n_symbols,
                                                           double* __restrict__ gamma_sum, double* __restrict__ B_sum) {
@@ -1086,6 +1293,10 @@ extern "C" int lnasr_em_statistics(const void* feats, int feats_dtype, int32_t l
     return launch_stats_ab(a, beta, total_frames, (cudaStream_t)stream);
 }
 
+static int g_em_moments_simt = 0;
+// test / measurement hook: 1 = the SIMT moments kernel also where the tensor-core one would run (tests compare the two)
+extern "C" int lnasr_debug_set_em_moments_simt(int on) { g_em_moments_simt = on; return LNASR_OK; }
+
 extern "C" size_t lnasr_em_statistics_workspace_bytes(int64_t total_frames, int32_t N) {
     return N <= 32 ? 256 : em_general_ws_bytes(total_frames, N);
 }
@@ -1117,7 +1328,11 @@ extern "C" int lnasr_em_statistics_ws(const void* feats, int feats_dtype, int32_
     fsplit = ceil_div(total_frames, per);
     LNASR_CHECK_ARG(gtiles <= 65535, "em_statistics_ws: too many Gaussians");
     dim3 grid((unsigned)fsplit, (unsigned)gtiles);
-    em_moments_kernel<<<grid, 256, 0, stream>>>(g, feats, feats_dtype == LNASR_DT_F64, ld_feats, bm, logw, mu, n_mix, dim, per, acc);
+    if (dim <= 39 && !g_em_moments_simt) {
+        LNASR_CUDA(cudaFuncSetAttribute(em_moments_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMM_RAW_BYTES));
+        em_moments_mma_kernel<<<grid, EMM_THREADS, EMM_RAW_BYTES, stream>>>(g, feats, feats_dtype == LNASR_DT_F64, ld_feats, bm, logw, mu, n_mix, dim, per, acc);
+    } else
+        em_moments_kernel<<<grid, 256, 0, stream>>>(g, feats, feats_dtype == LNASR_DT_F64, ld_feats, bm, logw, mu, n_mix, dim, per, acc);
     LNASR_LAUNCH_CHECK();
     return LNASR_OK;
 }

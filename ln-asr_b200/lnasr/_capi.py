@@ -102,6 +102,7 @@ SIGNATURES = {
     "lnasr_debug_set_band_kernel": (C.c_int, [C.c_int]),
     "lnasr_debug_set_tc16_poly": (C.c_int, [C.c_int]),
     "lnasr_debug_set_tc16_groups": (C.c_int, [C.c_int]),
+    "lnasr_debug_set_em_moments_simt": (C.c_int, [C.c_int]),
     "lnasr_debug_umma_probe": (C.c_int, [vp, i32, vp, i32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_uint32, vp, vp]),
 }

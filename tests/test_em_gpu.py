@@ -196,6 +196,34 @@ def test_baum_welch_beyond_thirty_two_states(n, mix, d, ltr):
     assert abs(ll2 - tot2["loglik"]) < 1e-7 * abs(tot2["loglik"]) and ll2 >= ll - 1e-6
 
 
+def test_moment_kernels_agree():
+    """Above 32 states the Gaussian moments run on the FP64 tensor cores (raw moments about a point of the tile, dim <= 39) or
+    on the SIMT kernel (centred on mu_old; dim <= 64): the two give the same re-estimates, far from the origin too."""
+    from lnasr import _capi
+    from lnasr.gmmhmm import GMMHMM
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(77)
+    n, mix, d = 40, 3, 39
+    mdl = O.random_gmmhmm(n, mix, d, rng, left_to_right=True)
+    mdl["mu"] = mdl["mu"] + 250.0                                   # |mu| / sigma ~ 250: the raw-moment form must not cancel
+    utts = [250.0 + 0.7 * rng.standard_normal((T, d)) for T in (50, 3, 41)]
+    res = []
+    for simt in (0, 1):
+        _capi.lib().lnasr_debug_set_em_moments_simt(simt)
+        try:
+            m = GMMHMM(n, mix, d, A=mdl["A"], pi=mdl["pi"], w=mdl["w"], mu=mdl["mu"], si=mdl["var"][..., None] * np.eye(d))
+            m.train_batch(utts, iters=1, verbose=False)
+        finally:
+            _capi.lib().lnasr_debug_set_em_moments_simt(0)
+        res.append((m.mu.copy(), m.var.copy(), m.w.copy()))
+    with np.errstate(all="ignore"):
+        new_ref, _ = O.em_step_multi_diag(utts, mdl)
+    for mu_, var_, w_ in res:
+        assert_close(mu_, new_ref["mu"], 1e-9, "mu")
+        assert_close(var_, new_ref["var"], 1e-7, "var")
+    assert_close(res[0][1], res[1][1], 1e-8, "var: tensor-core vs SIMT moments")
+
+
 def test_discrete_hmm_training_beyond_thirty_two_states():
     """Plain HMM._estimate (hmm.py:202-225) with 48 states and 10 symbols: one Baum-Welch step against the oracle."""
     from lnasr.hmm import HMM
