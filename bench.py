@@ -507,6 +507,11 @@ def run_ours(args, ctx, workload, steps, warmup, with_cpu=True, load_s=1.5):
             if roof.get("algorithmic_bytes_per_frame"):
                 roof["traffic_note"] += "; algorithmic = %d" % (roof["algorithmic_bytes_per_frame"] * frames)
         roof["peak_source"] = ctx.peak_src
+        if roof["bound"] == "tensor":
+            # the denominator of a tensor-bound stage: the sustained (kernel timed inside a long step) 16-bit dense GEMM rate of
+            # MEASURED_PEAKS.json for the tcgen05 kernels, the FP64 mma rate measured in this run for the exact kernel
+            roof["peak_source"] = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if cfg["emission"] == "tc16" and "bf16_tflops_sustained" in ctx.peaks
+                                   else "measured in this run (fp64_peaks_measured / cuBLAS TF32 probe)")
         roof["stage_ms"] = {k: round(v["ms"], 4) for k, v in stages.items()}
         roof["all_stages"] = {}
         for k in stages:
