@@ -986,7 +986,7 @@ constexpr int EMM_THREADS = 256;      // 8 warps = 2 halves of the 32 Gaussians 
 constexpr int EMM_FT = 32;            // frames per round
 constexpr int EMM_KS = EMM_THREADS / 64;                        // frame slices
 constexpr int EMM_KSTEPS = EMM_FT / 4 / EMM_KS;                 // k-steps (4 frames) per warp and round
-constexpr int EMM_STAGES = 1;         // rounds in flight (2 = one more round ahead: 86 KB of slots, one block per SM -- slower)
+constexpr int EMM_STAGES = 1;         // rounds in flight (measured: one more round ahead = 86 KB of slots, one block per SM -- slower)
 constexpr int EMM_OQ = EMM_FT * EMG_GT / EMM_THREADS;           // (frame, Gaussian) pairs per thread and round
 constexpr int EMM_RAW_OCC = 4 * EMM_OQ;                         // raw slots per thread: (alpha, beta, b, bm) of each pair
 constexpr int EMM_RAW_X = (EMM_FT * 39 + EMM_THREADS - 1) / EMM_THREADS;      // + its feature values
@@ -1039,7 +1039,8 @@ __global__ void __launch_bounds__(EMM_THREADS, 2) em_moments_mma_kernel(EmGen g,
     __shared__ double occ_s[EMM_FT][EMM_LDA];
     __shared__ __align__(16) double x_s[EMM_FT][EMM_LDB];
     __shared__ double c_s[40];
-    __shared__ double z_s[EMM_STAGES][EMM_FT];              // Z_t of the round's frames (one copy per frame, read by broadcast)
+    __shared__ double z_s[EMM_THREADS / 32][EMM_OQ];        // Z_t of the frames of each warp's pairs: fetched by the warp's own lanes
+                                                            // 0..3, so cp.async.wait_group + __syncwarp makes them visible to the warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, N = g.N, NM = N * M;
     const int gh = warp & 1, ks = warp >> 1;               // half of the Gaussian tile, slice of the staged frames
     const int fr4 = lane & 3, r8 = lane >> 2;
@@ -1060,44 +1061,55 @@ __global__ void __launch_bounds__(EMM_THREADS, 2) em_moments_mma_kernel(EmGen g,
     const int gq = lane, jm = jm0 + gq, jst = (gq < ng) ? jm / M : 0;
     const double lw = (gq < ng) ? logw[jm] : 0.0;
     const uint32_t d_magic = 0xffffffffu / (uint32_t)D + 1u;      // i / D = umulhi(i, d_magic) for i < 2^16
-    auto prefetch = [&](int64_t t0, int stage) {
+    // shared-memory slot k of this thread: raw_u + k * SLOT; global sources as running pointers of frame t0 + warp (my first
+    // pair of a round; the others are 8, 16, 24 frames on)
+    constexpr uint32_t SLOT = EMM_THREADS * 8;
+    const uint32_t raw_u = (uint32_t)__cvta_generic_to_shared(emm_raw) + tid * 8;
+    const uint32_t z_u = (uint32_t)__cvta_generic_to_shared(&z_s[warp][0]) + lane * 8;
+    auto cp8 = [](uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); };
+    auto cp4 = [](uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); };
+    const int64_t stepN = (int64_t)(EMM_THREADS / 32) * N, stepNM = (int64_t)(EMM_THREADS / 32) * NM;
+    const char* fbase = (const char*)feats;
+    const int fsz = feats_f64 ? 8 : 4;
+    auto prefetch = [&](int64_t t0) {
         if (t0 < t_end) {
             const int nt = (int)min((int64_t)EMM_FT, t_end - t0);
-            double* raw = emm_raw + (size_t)stage * EMM_RAW * EMM_THREADS + tid;
             if (gq < ng) {
+                const double* pa = g.alpha + (t0 + warp) * N + jst;
+                const double* pb = g.beta + (t0 + warp) * N + jst;
+                const double* pe = g.b + (t0 + warp) * N + jst;
+                const double* pm = bm + (t0 + warp) * NM + jm;
 #pragma unroll
                 for (int q = 0; q < EMM_OQ; ++q) {
-                    const int tt = warp + (EMM_THREADS / 32) * q;
-                    if (tt < nt) {
-                        const int64_t t = t0 + tt;
-                        em_cp_async(raw + (4 * q + 0) * EMM_THREADS, g.alpha + t * N + jst, 1);
-                        em_cp_async(raw + (4 * q + 1) * EMM_THREADS, g.beta + t * N + jst, 1);
-                        em_cp_async(raw + (4 * q + 2) * EMM_THREADS, g.b + t * N + jst, 1);
-                        em_cp_async(raw + (4 * q + 3) * EMM_THREADS, bm + t * NM + jm, 1);
+                    if (warp + (EMM_THREADS / 32) * q < nt) {
+                        cp8(raw_u + (4 * q + 0) * SLOT, pa + q * stepN);
+                        cp8(raw_u + (4 * q + 1) * SLOT, pb + q * stepN);
+                        cp8(raw_u + (4 * q + 2) * SLOT, pe + q * stepN);
+                        cp8(raw_u + (4 * q + 3) * SLOT, pm + q * stepNM);
                     }
                 }
             }
-            if (tid < nt) em_cp_async(&z_s[stage][tid], g.z + t0 + tid, 1);
+            if (lane < EMM_OQ && warp + (EMM_THREADS / 32) * lane < nt) cp8(z_u, g.z + t0 + warp + (EMM_THREADS / 32) * lane);
+            const char* frow = fbase + t0 * ld_feats * fsz;
 #pragma unroll
             for (int q = 0; q < EMM_RAW_X; ++q) {
                 const int i = tid + EMM_THREADS * q, r = (D == 1) ? i : (int)__umulhi((uint32_t)i, d_magic), dd = i - r * D;
                 if (r < nt) {
-                    const int64_t row = t0 + r;
-                    if (feats_f64) em_cp_async(raw + (EMM_RAW_OCC + q) * EMM_THREADS, (const double*)feats + row * ld_feats + dd, 1);
-                    else em_cp_async(raw + (EMM_RAW_OCC + q) * EMM_THREADS, (const float*)feats + row * ld_feats + dd, 0);
+                    const char* src = frow + ((int64_t)r * ld_feats + dd) * fsz;
+                    if (feats_f64) cp8(raw_u + (EMM_RAW_OCC + q) * SLOT, src);
+                    else cp4(raw_u + (EMM_RAW_OCC + q) * SLOT, src);
                 }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    prefetch(t_begin, 0);
-    if (EMM_STAGES == 2) prefetch(t_begin + EMM_FT, 1);
+    prefetch(t_begin);
     __syncthreads();
-    int stage = 0;
-    for (int64_t t0 = t_begin; t0 < t_end; t0 += EMM_FT, stage = (stage + 1) % EMM_STAGES) {
+    const double* raw = emm_raw + tid;
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += EMM_FT) {
         const int nt = (int)min((int64_t)EMM_FT, t_end - t0);
-        asm volatile("cp.async.wait_group %0;" ::"n"(EMM_STAGES - 1) : "memory");       // this round's inputs have landed
-        const double* raw = emm_raw + (size_t)stage * EMM_RAW * EMM_THREADS + tid;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");       // this round's inputs have landed
+        __syncwarp();                                              // ... those fetched by other lanes of the warp (Z) too
         // mixture occupancies for ALL t (gmmhmm.py:98-100): exp(alpha + beta - Z + log w + bm - b)
 #pragma unroll
         for (int q = 0; q < EMM_OQ; ++q) {
@@ -1105,7 +1117,7 @@ __global__ void __launch_bounds__(EMM_THREADS, 2) em_moments_mma_kernel(EmGen g,
             double o = 0.0;
             if (tt < nt && gq < ng) {
                 const double ab = raw[(4 * q + 0) * EMM_THREADS] + raw[(4 * q + 1) * EMM_THREADS];
-                const double bj = raw[(4 * q + 2) * EMM_THREADS], Z = z_s[stage][tt];
+                const double bj = raw[(4 * q + 2) * EMM_THREADS], Z = z_s[warp][q];
                 if (ab != neg_inf() && Z != neg_inf() && Z == Z && bj != neg_inf())
                     o = exp_neg_poly(ab - Z + lw + raw[(4 * q + 3) * EMM_THREADS] - bj);
             }
@@ -1123,8 +1135,8 @@ __global__ void __launch_bounds__(EMM_THREADS, 2) em_moments_mma_kernel(EmGen g,
                 *reinterpret_cast<double2*>(&x_s[r][2 * dd]) = make_double2(xv * xv, xv);
             }
         }
-        __syncthreads();                                   // (also: every thread has read z_s[stage] before the prefetch rewrites it)
-        prefetch(t0 + EMM_STAGES * EMM_FT, stage);         // into the slots just consumed
+        __syncthreads();                                   // (also: every lane has read its warp's z_s before the prefetch rewrites it)
+        prefetch(t0 + EMM_FT);                             // into the slots just consumed
 #pragma unroll
         for (int kk = 0; kk < EMM_KSTEPS; ++kk) {
             const int fr = 4 * (ks * EMM_KSTEPS + kk) + fr4;
