@@ -34,6 +34,7 @@ constexpr int MAX_SLOTS = MAX_MEL / 16;
 constexpr int STD_FRAME_LEN = 400;    // MFCC() defaults (mfcc.py:23-48): the kStd instantiation of the frames kernel has
 constexpr int STD_N_MEL = 40;         // the trip counts of its per-frame loops as constants
 constexpr int STD_N_CEPS = 12;
+constexpr int STD_FB_STRIDE = 32;     // widest mel filter the kStd kernel's shared-memory layout has room for (default bank: 32)
 constexpr int STD_NA = (STD_FRAME_LEN + 31) >> 5;
 // Mel plan (mfcc_setup_kernel -> workspace -> shared memory of the frames kernel).  ints: [0] slots, [1] padded taps of all slots,
 // [2] 1 = interval form, [4 + s] taps of slot s (a multiple of 4), [PLAN_K0 + 16 s + b] first power bin lane b reads in slot s,
@@ -113,8 +114,8 @@ struct SmemLayout {
     int tw_mid, tw_split, window, logtab, dct, fb_w, fb_meta, per_hw, per_hw_doubles, stage_off, total;
 };
 constexpr int STAGE_SAMPLES = FFT_N + 16;     // x[-1 .. 32 n_a + 1) plus alignment slack (copies start on a 16-byte boundary)
-__host__ __device__ inline SmemLayout smem_layout(int n_mel, int fb_stride, int n_dct_cols, int pcm_bytes, int n_hw) {
-    SmemLayout L;
+__host__ __device__ constexpr SmemLayout smem_layout(int n_mel, int fb_stride, int n_dct_cols, int pcm_bytes, int n_hw) {
+    SmemLayout L{};
     int o = 0;
     L.tw_mid = o;   o += 2 * 256;                         // W256^(b k1) at [k1*16 + b]
     L.tw_split = o; o += 2 * 128;                         // W512^(b + 16 k2) at [k2*16 + b], k2 < 8
@@ -179,7 +180,11 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     const int n_mel = kStd ? STD_N_MEL : P.n_mel, n_ceps = kStd ? STD_N_CEPS : P.n_ceps;
     const bool full_ceps = !kStd && (ceps_raw_out != nullptr);
     const int n_out = full_ceps ? n_mel : (n_ceps + 1);       // cepstral coefficients 0..n_out-1 computed
-    const SmemLayout L = smem_layout(n_mel, P.fb_stride, n_out, (int)sizeof(PcmT), n_threads >> 4);
+    // kStd: every offset of the carve-up is a compile-time constant (one base register instead of a dozen pointers that the
+    // compiler either keeps -- the 16 x 16 FFT leaves it ~10 free registers -- or re-derives inside the frame loop)
+    constexpr SmemLayout L_STD = smem_layout(STD_N_MEL, STD_FB_STRIDE, STD_N_CEPS + 1, (int)sizeof(PcmT), MAX_THREADS / 16);
+    const SmemLayout L = kStd ? L_STD : smem_layout(n_mel, P.fb_stride, n_out, (int)sizeof(PcmT), n_threads >> 4);
+    const int fb_stride = kStd ? STD_FB_STRIDE : P.fb_stride;
     double2* s_twm = reinterpret_cast<double2*>(smem + L.tw_mid);
     double2* s_tws = reinterpret_cast<double2*>(smem + L.tw_split);
     double* s_win = smem + L.window;
@@ -474,7 +479,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         for (int o = 8; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
         // zero-weight taps of the padded mel loop may read up to fb_stride bins past bin 256: stale transpose data there must
         // at least be finite (0 * NaN)
-        for (int i = lane; i < P.fb_stride + 4; i += 32)
+        for (int i = lane; i < fb_stride + 4; i += 32)
             *reinterpret_cast<float2*>(s_pow - half + 2 * (HALF_N + 1 + i)) = make_float2(0.f, 0.f);
         __syncwarp();
         if (power_out && act_cur)
@@ -955,18 +960,20 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     P.fb_weight = tb->fb_weight; P.dct_t = tb->dct_t;
 
     // one block per SM, as many half-warps (frames in flight) as shared memory allows, at most 32
+    // the kStd instantiation: MFCC() defaults on the feature path (compile-time trip counts and shared-memory offsets)
+    const bool std_shape = (P.frame_len == STD_FRAME_LEN && P.n_mel == STD_N_MEL && P.n_ceps == STD_N_CEPS && P.fb_stride <= STD_FB_STRIDE &&
+                            !ceps_out && pcm_dtype != LNASR_DT_F64);
     const int pcm_bytes = (pcm_dtype == LNASR_DT_I16) ? 2 : (pcm_dtype == LNASR_DT_F32 ? 4 : 8);
     const int n_cols = ceps_out ? P.n_mel : P.n_ceps + 1;
     int threads = MAX_THREADS;
     size_t smem = 0;
     for (;; threads -= 64) {
-        smem = (size_t)smem_layout(P.n_mel, P.fb_stride, n_cols, pcm_bytes, threads / 16).total * sizeof(double);
+        smem = (size_t)smem_layout(P.n_mel, std_shape ? STD_FB_STRIDE : P.fb_stride, n_cols, pcm_bytes, threads / 16).total * sizeof(double);
         if (smem <= 226 * 1024 || threads <= 64) break;
     }
     const int64_t n_runs = ceil_div(total_frames, fpr);
     int grid = (int)std::min<int64_t>(ceil_div(n_runs, threads / 32), (int64_t)sm_count());
     if (grid < 1) grid = 1;
-    const bool std_shape = (P.frame_len == STD_FRAME_LEN && P.n_mel == STD_N_MEL && P.n_ceps == STD_N_CEPS && !ceps_out);
     auto launch = [&](auto kern, auto* typed_pcm) -> int {
         LNASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, stream>>>(typed_pcm, sample_offsets, frame_offsets, n_utt, total_frames, P, raw, colsum, run_utt,
