@@ -720,19 +720,53 @@ mfcc_setup_kernel(const int64_t* __restrict__ frame_off, int n_utt, int64_t n_ru
         }
         L = (L + 3) & ~3;
         s_L[tid] = L;
-        // early starts: lanes without slack keep their residue, the others take the nearest free one
-        unsigned used = 0;
-        for (int pass = 0; pass < 2; ++pass)
-            for (int bb = 0; bb < 16; ++bb) {
-                const int j = s_asg[tid * 16 + bb];
-                if (j < 0) continue;
-                const int slack = min(L - s_len[j], s_k0[j]);
-                if ((slack == 0) != (pass == 0)) continue;
-                int d = 0;
-                for (int c = 0; c <= slack; ++c)
-                    if (!((used >> ((s_k0[j] - c) & 15)) & 1u)) { d = c; break; }
-                used |= 1u << ((s_k0[j] - d) & 15);
-                s_off[tid * 16 + bb] = d;
+        // early starts: a lane may begin up to `slack` bins before its interval; choose the shifts so that the 16 first bins
+        // have distinct residues mod 16 -- a bipartite matching lane <-> residue (augmenting paths, most constrained lanes
+        // first); lanes without an interval take whatever residue is left (their weights are zero)
+        int k0v[16], slk[16], owner[16];
+        for (int bb = 0; bb < 16; ++bb) {
+            const int j = s_asg[tid * 16 + bb];
+            k0v[bb] = j >= 0 ? s_k0[j] : 15;
+            slk[bb] = j >= 0 ? min(15, min(L - s_len[j], s_k0[j])) : 15;
+            owner[bb] = -1;
+        }
+        for (int want = 0; want <= 15; ++want)
+            for (int b0 = 0; b0 < 16; ++b0) {
+                if (slk[b0] != want) continue;
+                int st_lane[16], st_r[16], st_try[16], sp = 0;
+                unsigned visited = 0;
+                st_lane[0] = b0;
+                st_r[0] = 0;
+                bool done = false;
+                while (sp >= 0 && !done) {
+                    const int b = st_lane[sp];
+                    bool descended = false;
+                    while (st_r[sp] < 16) {
+                        const int r = st_r[sp]++;
+                        if (((k0v[b] - r) & 15) > slk[b] || ((visited >> r) & 1u)) continue;
+                        visited |= 1u << r;
+                        st_try[sp] = r;
+                        if (owner[r] < 0) {
+                            for (int q = sp; q >= 0; --q) owner[st_try[q]] = st_lane[q];
+                            done = true;
+                            break;
+                        }
+                        if (sp + 1 < 16) {
+                            st_lane[sp + 1] = owner[r];
+                            st_r[sp + 1] = 0;
+                            ++sp;
+                            descended = true;
+                            break;
+                        }
+                    }
+                    if (!done && !descended) --sp;
+                }
+            }
+        for (int bb = 0; bb < 16; ++bb) s_off[tid * 16 + bb] = (s_asg[tid * 16 + bb] >= 0) ? 0 : 15;     // unmatched: no shift
+        for (int r = 0; r < 16; ++r)
+            if (owner[r] >= 0) {
+                const int bb = owner[r], c = (k0v[bb] - r) & 15;
+                s_off[tid * 16 + bb] = (s_asg[tid * 16 + bb] >= 0) ? c : 15 - c;      // shift of an interval / first bin of an idle lane
             }
     }
     __syncthreads();
@@ -748,7 +782,7 @@ mfcc_setup_kernel(const int64_t* __restrict__ frame_off, int n_utt, int64_t n_ru
     __syncthreads();
     for (int i = tid; i < PLAN_POS; i += nt) {
         const int j = (i < n_slots * 16) ? s_asg[i] : -1;
-        plan[PLAN_K0 + i] = j >= 0 ? s_k0[j] - s_off[i] : 0;
+        plan[PLAN_K0 + i] = j >= 0 ? s_k0[j] - s_off[i] : ((i < n_slots * 16) ? s_off[i] : 0);
         plan[PLAN_J + i] = j >= 0 ? j : PLAN_NONE;
     }
     float2* pw = reinterpret_cast<float2*>(plan + PLAN_W);

@@ -117,6 +117,8 @@ class MFCC:
         lib = _capi.lib()
         keep["mel_plan"] = t.empty((int(lib.lnasr_mfcc_mel_plan_bytes()),), dtype=t.uint8, device="cuda")
         _capi.check(lib.lnasr_mfcc_mel_plan(C.byref(tb), _capi.ptr(keep["mel_plan"]), _capi.stream_ptr()), "mfcc_mel_plan")
+        # the tables are used from any stream afterwards (AcousticPipeline's compute streams): the plan must be complete first
+        t.cuda.current_stream().synchronize()
         tb.mel_plan = keep["mel_plan"].data_ptr()
         self._tables[dev] = (tb, keep)
         return tb
