@@ -237,7 +237,10 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     // warp-wide access is one wavefront instead of one per half-warp
     float* s_pow = reinterpret_cast<float*>(smem + L.per_hw + ((tid >> 5) * 2) * L.per_hw_doubles) + half;
     // (R, F) sums of the mel intervals of the warp's two frames, [interval][half], in the transpose buffer of half 1
-    float2* s_rf = reinterpret_cast<float2*>(smem + L.per_hw + ((tid >> 5) * 2 + 1) * L.per_hw_doubles) + half;
+    // two float arrays R[interval][half] | F[interval][half]: the intervals of one slot (and the filters of one logarithm round) are
+    // consecutive, so 4-byte accesses at 2 j + half fall into 32 distinct banks (one float2 array collided two-fold)
+    float* s_rf = reinterpret_cast<float*>(smem + L.per_hw + ((tid >> 5) * 2 + 1) * L.per_hw_doubles) + half;
+    constexpr int RF_F = 2 * (PLAN_NONE + 1);             // offset of the F array
     double* s_lm = hbase + 2 * 16 * TR_LD;
     for (int i = b; i < MAX_MEL; i += 16) s_lm[i] = 0.0;                  // entries >= n_mel stay zero (k padding of the DCT)
     PcmT* stage = reinterpret_cast<PcmT*>(hbase + L.stage_off);
@@ -513,7 +516,9 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                             fl = fmaf(wv.y, pv, fl);
                         }
                     }
-                    s_rf[2 * s_plan[PLAN_J + 16 * s + b]] = make_float2(r, fl);
+                    const int jw = 2 * s_plan[PLAN_J + 16 * s + b];
+                    s_rf[jw] = r;
+                    s_rf[RF_F + jw] = fl;
                 }
             }
             __syncwarp();
@@ -525,7 +530,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             for (int i = 0; i < NR; ++i) {
                 const int m = b + 16 * i;
                 double e = esum;                                           // m == n_mel: ln of the frame energy (mfcc.py:158-160)
-                if (i < n_rounds && m < n_mel) e = (double)(s_rf[2 * m].x + s_rf[2 * m + 2].y);
+                if (i < n_rounds && m < n_mel) e = (double)(s_rf[2 * m] + s_rf[RF_F + 2 * m + 2]);
                 e *= PSCALE;
                 if (m < n_mel && e == 0.0) e = 2.220446049250313e-16;      // np.finfo(float).eps
                 ev[i] = (i < n_rounds && m <= n_mel) ? e : 1.0;
