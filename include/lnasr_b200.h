@@ -77,7 +77,9 @@ int lnasr_preemphasis(const void* pcm, int pcm_dtype /*I16|F32|F64*/, int64_t n_
                       double* out, void* stream);
 /* frames of one utterance: ceil(|S-(L-step)|/step), utils.py:118 (host helper, no device work) */
 int64_t lnasr_mfcc_num_frames(int64_t n_samples, int32_t frame_len, int32_t frame_step);
-/* the mel-product plan of a filter bank (see lnasr_mfcc_tables.mel_plan): reads n_mel, fb_stride, fb_start, fb_len, fb_weight */
+/* the mel-product plan of a filter bank (see lnasr_mfcc_tables.mel_plan): reads n_mel, fb_stride, fb_start, fb_len, fb_weight.
+ * One small launch on `stream`; like every buffer the library fills, the plan is ordered only with respect to that stream --
+ * synchronise (or record / wait an event) before lnasr_mfcc_batch uses it from another stream */
 size_t lnasr_mfcc_mel_plan_bytes(void);
 int lnasr_mfcc_mel_plan(const lnasr_mfcc_tables* tables, int32_t* plan /*device out*/, void* stream);
 /* workspace bytes needed by lnasr_mfcc_batch */
