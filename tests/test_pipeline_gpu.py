@@ -148,3 +148,28 @@ def test_submit_host_keeps_batches_in_flight():
     for h, (w_ref, b_ref) in zip(reversed(handles), reversed(ref)):                         # collected out of order
         w, b = h.result()
         assert h.done() and np.array_equal(w.numpy(), w_ref.numpy()) and np.array_equal(b.numpy(), b_ref.numpy())
+
+
+def test_first_use_on_side_streams():
+    """Device-side state that is built lazily (MFCC tables and the mel plan, packed models, transition lists) is complete before
+    another stream can use it: fresh objects whose FIRST call runs inside submit_host (copy + two compute streams) and inside a
+    user's side stream give the results of the plain call."""
+    import torch
+    from lnasr.bank import AcousticPipeline, ModelBank
+    from lnasr.mfcc import MFCC
+    rng = np.random.default_rng(77)
+    models = _models(rng, 3, 5, 4)
+    pcm, off, _ = _batch(rng, [int(x) for x in rng.integers(3000, 12000, size=17)])
+    ref_res, ref_mb = AcousticPipeline(MFCC(), ModelBank(models, emission="exact")).recognize_batch(pcm, off)
+    ref_w = ref_res.words.cpu().numpy()
+    ref_f = ref_mb.feats.cpu()
+    for _ in range(3):
+        pipe = AcousticPipeline(MFCC(), ModelBank(models, emission="exact"))      # nothing of it exists on the device yet
+        h = pipe.submit_host(torch.from_numpy(pcm).pin_memory(), off)
+        assert np.array_equal(h.result()[0].cpu().numpy(), ref_w)
+        side = torch.cuda.Stream()
+        mf = MFCC()
+        with torch.cuda.stream(side):
+            feats = mf.calc_mfcc_batch(torch.from_numpy(pcm).cuda(), sample_offsets=off).feats
+        side.synchronize()
+        assert torch.equal(feats.cpu().nan_to_num(), ref_f.nan_to_num())
