@@ -178,3 +178,26 @@ def test_float64_samples_are_not_narrowed(mfcc):
     feats = res.feats.double().cpu().numpy()
     for u, s in enumerate(sigs):
         assert_close(feats[off[u]:off[u + 1]], O.mfcc(s)[2], 1e-4, f"float64 utt {u}")
+
+
+def test_every_base_alignment_of_the_sample_buffer(mfcc):
+    """The frames kernel copies samples in 16-byte chunks from the boundary at or below x[-1]; the buffer a caller passes may start
+    anywhere inside such a chunk (AcousticPipeline hands out sub-ranges of one device buffer).  Views starting 0..9 samples into
+    an allocation, int16 and float32, two utterances each: same features as the oracle, and nothing outside the view is used."""
+    import torch
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(31)
+    lens = [1203, 2500]
+    sigs = [np.clip(np.round(4000.0 * rng.standard_normal(n)), -32767, 32767).astype(np.int16) for n in lens]
+    ref = [O.mfcc(s.astype(np.float64))[2] for s in sigs]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for dt, scale in ((torch.int16, 1), (torch.float32, 1)):
+        for o in range(10):
+            # poison on both sides of the view: a read outside it that reached the arithmetic would show up in the features
+            buf = torch.full((o + int(off[-1]) + 64,), 32000, dtype=dt, device="cuda")
+            buf[o:o + int(off[-1])] = torch.from_numpy(np.concatenate(sigs)).to(dt).cuda()
+            res = mfcc.calc_mfcc_batch(buf[o:o + int(off[-1])], sample_offsets=off)
+            feats = res.feats.double().cpu().numpy()
+            fo = res.frame_offsets_host
+            for u in range(2):
+                assert_close(feats[fo[u]:fo[u + 1]], ref[u], 1e-4, f"{dt} view at sample {o}, utterance {u}")
