@@ -224,6 +224,31 @@ def test_moment_kernels_agree():
     assert_close(res[0][1], res[1][1], 1e-8, "var: tensor-core vs SIMT moments")
 
 
+def test_large_model_training_from_float32_features():
+    """The features a pipeline hands to the trainer are float32 (MFCC output): the moments kernel fetches them with 4-byte
+    asynchronous copies.  40 states x 3 mixtures, a Gaussian tile that is not full (120 = 3 x 32 + 24), utterances of 1..57 frames;
+    against the oracle on the same float32 values."""
+    import torch
+    from lnasr.em import EmTrainer
+    from oracle import lnasr_oracle as O
+    rng = np.random.default_rng(404)
+    n, mix, d = 40, 3, 39
+    mdl = O.random_gmmhmm(n, mix, d, rng, left_to_right=True)
+    lens = [57, 1, 32, 31, 33, 2]
+    utts32 = [(0.6 * rng.standard_normal((T, d))).astype(np.float32) for T in lens]
+    with np.errstate(all="ignore"):
+        new_ref, tot = O.em_step_multi_diag([u.astype(np.float64) for u in utts32], mdl)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    tr = EmTrainer(mdl).load_batch(torch.from_numpy(np.concatenate(utts32)).cuda(), off)
+    ll = float(tr.iterate().item())
+    assert abs(ll - tot["loglik"]) < 1e-8 * abs(tot["loglik"])
+    got = tr.export()
+    assert_close(got["mu"], new_ref["mu"], 1e-8, "mu")
+    assert_close(got["var"], new_ref["var"], 1e-8, "var")
+    with np.errstate(all="ignore"):
+        assert_close(np.exp(got["w"]), np.exp(new_ref["w"]), 1e-8, "w")
+
+
 def test_discrete_hmm_training_beyond_thirty_two_states():
     """Plain HMM._estimate (hmm.py:202-225) with 48 states and 10 symbols: one Baum-Welch step against the oracle."""
     from lnasr.hmm import HMM
