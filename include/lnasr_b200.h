@@ -89,6 +89,7 @@ int lnasr_mfcc_workspace_bytes(int64_t total_frames, int32_t n_utt, size_t* byte
  * sample_offsets : [n_utt+1] int64, device
  * frame_offsets  : [n_utt+1] int64, device; frame_offsets[u+1]-frame_offsets[u] must equal
  *                  lnasr_mfcc_num_frames(samples of u) and be >= 2 (the reference needs row 1, mfcc.py:164)
+ * total_frames   : < 2^31 per call (frame positions are 32-bit inside the kernels; sample offsets are 64-bit)
  * feats          : [total_frames, ld_feats] float32 out, 3*(n_ceps+1) = 39 columns used
  * power_out      : [total_frames, fft_n/2+1] float32 or NULL   (1st return value of calc_mfcc)
  * ceps_out       : [total_frames, n_mel] float32 or NULL       (2nd return value, incl. its in-place quirk)

@@ -140,7 +140,7 @@ __host__ __device__ constexpr SmemLayout smem_layout(int n_mel, int fb_stride, i
 // where a frame lives: utterance, its sample range
 struct FrameCtx {
     int u;
-    int64_t u_f0, u_f1;  // first frame of this / of the next utterance
+    int u_f0, u_f1;      // first frame of this / of the next utterance (a batch has < 2^31 frames: checked by the launcher)
     int64_t u_s0;        // first sample of the utterance in pcm
     int64_t u_len;       // samples in the utterance
 };
@@ -246,9 +246,10 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     PcmT* stage = reinterpret_cast<PcmT*>(hbase + L.stage_off);
 
     const int fpr = P.frames_per_run, spr = fpr >> 1;
-    const int64_t n_runs = (total_frames + fpr - 1) / fpr;
-    const int64_t warp_global = (int64_t)blockIdx.x * (n_threads >> 5) + (tid >> 5);
-    const int64_t warp_stride = (int64_t)gridDim.x * (n_threads >> 5);
+    const int n_frames = (int)total_frames;
+    const int n_runs = (n_frames + fpr - 1) / fpr;
+    const int warp_global = blockIdx.x * (n_threads >> 5) + (tid >> 5);
+    const int warp_stride = gridDim.x * (n_threads >> 5);
     const int partner = ((16 - b) & 15) + 16 * half;     // lane holding Z[256 - k] for my Z[k]
     // rows a with at least one sample inside the frame; kStd = the default front end (25 ms frames at 16 kHz: 400 samples)
     // with the trip counts of the per-frame loops known to the compiler
@@ -264,8 +265,8 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     auto make_ctx = [&](int u) {
         FrameCtx c;
         c.u = u;
-        c.u_f0 = __ldg(frame_off + u);
-        c.u_f1 = __ldg(frame_off + u + 1);
+        c.u_f0 = (int)__ldg(frame_off + u);
+        c.u_f1 = (int)__ldg(frame_off + u + 1);
         c.u_s0 = __ldg(sample_off + u);
         c.u_len = __ldg(sample_off + u + 1) - c.u_s0;
         return c;
@@ -273,21 +274,21 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     // step s of this warp = pair of frames  f_pair(s), f_pair(s)+1 ; returns false past the warp's last pair (uniform)
     FrameCtx ctx;
     ctx.u = -1; ctx.u_f0 = 0; ctx.u_f1 = -1; ctx.u_s0 = 0; ctx.u_len = 0;
-    int64_t f = 0;
+    int f = 0;
     bool act = false;
     int par = 0;                                         // position (in samples) of x[-1] in the stage
-    auto locate = [&](int64_t step) -> bool {
-        const int64_t run = warp_global + (step / spr) * warp_stride;
-        const int64_t f_pair = run * fpr + 2 * (step % spr);
-        if (run >= n_runs || f_pair >= total_frames) return false;
+    auto locate = [&](int step) -> bool {
+        const int run = warp_global + (step / spr) * warp_stride;
+        const int f_pair = run * fpr + 2 * (step % spr);
+        if (run >= n_runs || f_pair >= n_frames) return false;
         f = f_pair + half;
-        act = f < total_frames;
+        act = f < n_frames;
         if (act) {
             if ((step % spr) == 0 || ctx.u < 0) ctx = make_ctx(__ldg(run_utt + run));   // utterance of the run's first frame
             if (f >= ctx.u_f1) {                         // walked into another utterance
                 int u = ctx.u;
-                int64_t f1 = ctx.u_f1;
-                while (f >= f1) { ++u; f1 = __ldg(frame_off + u + 1); }
+                int f1 = ctx.u_f1;
+                while (f >= f1) { ++u; f1 = (int)__ldg(frame_off + u + 1); }
                 ctx = make_ctx(u);
             }
         }
@@ -297,7 +298,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     // x[-1] (the chunks holding the first and the last byte of the batch are read whole), 4-byte words at the edges of the batch
     auto issue_copy = [&]() {
         if (act) {
-            const uintptr_t first = (uintptr_t)(pcm + ctx.u_s0 + (f - ctx.u_f0) * P.frame_step - 1);
+            const uintptr_t first = (uintptr_t)(pcm + ctx.u_s0 + (int64_t)(f - ctx.u_f0) * P.frame_step - 1);
             const uintptr_t q0 = first & ~(uintptr_t)15;
             const uintptr_t w0 = first & ~(uintptr_t)3;
             if (q0 >= pcm_lo16 && q0 + 16u * (uintptr_t)(n_quads - 1) <= pcm_hi16) {
@@ -328,7 +329,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
     // coefficient whose sum lives in acc[i] of this lane: b + 16 i (SIMT DCT), or 8 (i / 2) + 2 b + i % 2 in lanes b < 4 (the
     // accumulator fragment of the tensor-core DCT)
     auto acc_coef = [&](int i) -> int { return dct_mma ? (b < 4 ? 8 * (i >> 1) + 2 * b + (i & 1) : -1) : b + 16 * i; };
-    for (int64_t step = 0; more; ++step) {
+    for (int step = 0; more; ++step) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (act && ctx.u != acc_u) {                      // flush the column sums of the utterance just left
@@ -344,7 +345,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
         // ---- pre-emphasis (mfcc.py:63) + framing (utils.py:119-130) + window (mfcc.py:138): z[16a+b], a = 0..15
         double2 v[16];
         {
-            const int64_t s_start = (f - ctx.u_f0) * P.frame_step;          // first sample of the frame in its utterance
+            const int64_t s_start = (int64_t)(f - ctx.u_f0) * P.frame_step;  // first sample of the frame in its utterance
             const int64_t rem64 = act ? (ctx.u_len - s_start) : 0;          // samples from the frame origin on
             const int rem = (int)min(rem64, (int64_t)(2 * FFT_N));
             const bool lead = s_start > 0;                                  // x[-1] exists
@@ -414,7 +415,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             } else if (act && lead && rem >= 32 * n_a) load_frame(std::false_type{});
             else load_frame(std::true_type{});
         }
-        const int64_t f_cur = f;
+        const int f_cur = f;
         const bool act_cur = act;
         __syncwarp();                                                      // the stage has been read by every lane
         more = locate(step + 1);
@@ -486,7 +487,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
             *reinterpret_cast<float2*>(s_pow - half + 2 * (HALF_N + 1 + i)) = make_float2(0.f, 0.f);
         __syncwarp();
         if (power_out && act_cur)
-            for (int k = b; k <= HALF_N; k += 16) power_out[f_cur * (HALF_N + 1) + k] = s_pow[2 * k] * (float)PSCALE;
+            for (int k = b; k <= HALF_N; k += 16) power_out[(int64_t)f_cur * (HALF_N + 1) + k] = s_pow[2 * k] * (float)PSCALE;
         // ---- mel filter bank (banded, mfcc.py:148), eps substitution (mfcc.py:149), 20 log10 (mfcc.py:150)
         // Interval form (mfcc_setup_kernel): neighbouring triangles overlap, so a bin k between two filter peaks feeds exactly
         // two filters, j = the higher one (weight wr[k]) and j - 1 (weight wf[k]); interval n_mel is the falling side of the last
@@ -550,7 +551,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                 const int m = b + 16 * i;
                 if (i < n_rounds) {
                     if (m < n_mel) s_lm[m] = 8.685889638065035 * ev[i];    // 20 log10(e) = 20/ln(10) * ln(e)
-                    else if (m == n_mel && act_cur) raw[f_cur * RAW_LD + n_ceps] = (float)ev[i];
+                    else if (m == n_mel && act_cur) raw[(int64_t)f_cur * RAW_LD + n_ceps] = (float)ev[i];
                 }
             }
         }
@@ -576,7 +577,7 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                     const int k = 8 * (i >> 1) + 2 * b + (i & 1);
                     if (k < n_out) {
                         acc[i] += __double2ll_rn(dv[i] * COLSUM_SCALE);
-                        if (k >= 1 && k <= n_ceps) raw[f_cur * RAW_LD + (k - 1)] = (float)dv[i];
+                        if (k >= 1 && k <= n_ceps) raw[(int64_t)f_cur * RAW_LD + (k - 1)] = (float)dv[i];
                     }
                 }
             }
@@ -596,8 +597,8 @@ mfcc_frames_kernel(const PcmT* __restrict__ pcm, const int64_t* __restrict__ sam
                 if (act_cur) {
                     acc[i] += __double2ll_rn(c * COLSUM_SCALE);
                     // raw static row: cepstra 1..n_ceps then ln(sum power) (mfcc.py:158-160)
-                    if (k >= 1 && k <= n_ceps) raw[f_cur * RAW_LD + (k - 1)] = (float)c;
-                    if (full_ceps) ceps_raw_out[f_cur * n_mel + k] = (float)c;
+                    if (k >= 1 && k <= n_ceps) raw[(int64_t)f_cur * RAW_LD + (k - 1)] = (float)c;
+                    if (full_ceps) ceps_raw_out[(int64_t)f_cur * n_mel + k] = (float)c;
                 }
             }
         }
@@ -962,6 +963,7 @@ extern "C" int lnasr_mfcc_batch(const void* pcm, int pcm_dtype, const int64_t* s
     LNASR_CHECK_ARG(ld_feats >= 3 * (tb->n_ceps + 1), "mfcc_batch: ld_feats too small");
     LNASR_CHECK_ARG(3 * (tb->n_ceps + 1) <= 40 && tb->n_ceps + 1 <= RAW_LD, "mfcc_batch: at most 13 static coefficients are built");
     if (n_utt == 0 || total_frames == 0) return LNASR_OK;
+    LNASR_CHECK_ARG(total_frames < ((int64_t)1 << 31) - 64, "mfcc_batch: at most 2^31 frames per call (got %lld)", (long long)total_frames);
     size_t need = 0;
     lnasr_mfcc_workspace_bytes(total_frames, n_utt, &need);
     if (workspace_bytes < need) {
